@@ -1,0 +1,20 @@
+"""add_b200 — B200-native (sm_100a) implementation of Auto-Dynamic-DeepLab's dense-segmentation
+forward path behind the reference's own Python operator API.
+
+The directory is named `auto-dynamic-deeplab_b200/`; import it as `add_b200` (repo-root shim
+`add_b200.py`).  Importing requires the in-tree `libadd_b200.so` (built by
+`__graft_entry__.build()`); there is no CPU / PyTorch fallback."""
+from ._lib import lib, AddError, EXPORTED_SYMBOLS
+from .runtime import (set_default_precision, default_precision, set_tc_enabled, tc_available, Builder, Plan, View,
+                      ConvWeights)
+from .genotypes import PRIMITIVES, AUTODEEPLAB_CELL, NETWORKS
+from .operations import (OPS, ReLUConvBN, DilConv, SepConv, Identity, Zero, FactorizedReduce,
+                         DoubleFactorizedReduce, SynchronizedBatchNorm2d, normalized_shannon_entropy,
+                         confidence_max)
+from .aspp_train import ASPP_train
+from .decoder import Decoder
+from .ADD import ADD, Cell, EDM
+from .metrics import Evaluator
+from .factory import build_add, Args
+
+__version__ = "0.1.0"

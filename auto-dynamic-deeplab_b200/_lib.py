@@ -1,0 +1,71 @@
+"""ctypes binding of libadd_b200.so (see include/add_b200.h).  There is NO fallback: if the
+shared library is missing or a symbol is absent, importing this module raises."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int, c_int32, c_int64, c_uint32, c_void_p, c_float, c_char_p, POINTER
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libadd_b200.so"
+
+ADD_F32, ADD_BF16 = 0, 1
+RELU_IN, RELU_OUT, ACCUMULATE = 1, 2, 4
+
+
+class AddTensor(ctypes.Structure):
+    """add_tensor_t — NHWC activation view (include/add_b200.h)."""
+    _fields_ = [("ptr", c_void_p), ("n", c_int32), ("h", c_int32), ("w", c_int32), ("c", c_int32),
+                ("pix_stride", c_int32), ("dtype", c_int32)]
+
+
+class AddError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  add_b200 has no CPU or PyTorch fallback.")
+    return ctypes.CDLL(str(LIB_PATH))
+
+
+lib = _load()
+
+TP = POINTER(AddTensor)
+_SIGS = {
+    "add_status_string": (c_char_p, [c_int]),
+    "add_version": (c_int, []),
+    "add_device_sm_count": (c_int, []),
+    "add_nchw_to_nhwc": (c_int, [c_void_p, c_int, TP, c_void_p]),
+    "add_nhwc_to_nchw": (c_int, [TP, c_void_p, c_void_p]),
+    "add_conv2d_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
+    "add_conv2d_tc_packed_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "add_conv2d_tc_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "add_conv2d_tc_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
+    "add_sepconv_half_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_void_p]),
+    "add_bilinear_fwd": (c_int, [TP, TP, c_uint32, c_void_p]),
+    "add_global_avgpool_fwd": (c_int, [TP, c_void_p, c_uint32, c_void_p]),
+    "add_edm_mlp_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 6 + [c_void_p, c_void_p]),
+    "add_upsample_logits_nchw": (c_int, [TP, c_void_p, c_int, c_int, c_void_p]),
+    "add_head_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "add_upsample_argmax_fwd": (c_int, [TP, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "add_confusion_workspace_bytes": (c_int64, [c_int64, c_int]),
+    "add_confusion_matrix": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "add_confidence_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "add_confidence_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)          # AttributeError here = the .so does not match the header
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib.add_status_string(int(status)).decode()
+        raise AddError(f"libadd_b200 {what}: {msg} (status {status})")

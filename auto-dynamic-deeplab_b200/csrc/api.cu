@@ -1,0 +1,22 @@
+// api.cu — library-level entry points (status strings, version, device query).
+#include "common.cuh"
+
+extern "C" const char* add_status_string(int status) {
+  switch (status) {
+    case ADD_OK: return "ok";
+    case ADD_ERR_BAD_ARG: return "bad argument (null pointer, negative size, shape mismatch)";
+    case ADD_ERR_UNSUPPORTED: return "unsupported shape/dtype/alignment for the sm_100a kernels";
+    case ADD_ERR_CUDA: return "CUDA launch error (no device, or invalid launch configuration)";
+    case ADD_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown status";
+  }
+}
+
+extern "C" int add_version(void) { return 100; }  // 0.1.0
+
+extern "C" int add_device_sm_count(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return ADD_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return ADD_ERR_CUDA;
+  return sms;
+}

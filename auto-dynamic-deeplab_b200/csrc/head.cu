@@ -1,0 +1,350 @@
+// head.cu — exit-head tail and Evaluator: final bilinear upsample fused with argmax / confusion
+// histogram / entropy, the standalone int64 confusion matrix, and the confidence scalars.
+// All HBM-bound integer/elementwise work.  The histogram is atomics-free: per-warp privatised
+// shared-memory counters, intra-warp collisions resolved with match.any (leader adds popcount),
+// deterministic block merge, per-block partials reduced by a second deterministic kernel.
+#include "common.cuh"
+
+namespace {
+
+constexpr int HD_THREADS = 256;
+constexpr int HD_WARPS = HD_THREADS / 32;
+constexpr int MAX_CLASS = 32;               // num_class <= 32 (Cityscapes: 19)
+constexpr int MAX_BINS = 361 + 7;           // supports num_class <= 19 for the histogram
+
+__host__ __device__ inline int head_blocks_per_image(long long hw) {
+  long long b = (hw + 2047) / 2048;
+  long long cap = 148 * 8;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+// One warp-synchronous histogram update.  `bin` < 0 means "no sample".  All 32 lanes must call.
+__device__ __forceinline__ void warp_hist_add(unsigned int* hist, int bin, int lane) {
+  unsigned peers = __match_any_sync(0xffffffffu, bin);
+  if (bin >= 0 && lane == (__ffs(peers) - 1)) hist[bin] += __popc(peers);
+  __syncwarp();
+}
+
+struct HeadParams {
+  const float* x; int n, h, w, c, xs;      // low-res logits (fp32 NHWC)
+  int H, W; float sh, sw;
+  const long long* gt; long long* pred;
+  unsigned int* part_hist;                  // [n][B][bins]
+  double* part_ent;                         // [n][B]
+  int bins; int B; int want_ent;
+};
+
+__global__ void __launch_bounds__(HD_THREADS)
+upsample_argmax_kernel(const HeadParams p) {
+  __shared__ unsigned int hist[HD_WARPS][MAX_BINS];
+  __shared__ double ent_red[HD_WARPS];
+  const int n = blockIdx.y, b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool do_hist = p.part_hist != nullptr;
+  if (do_hist)
+    for (int i = threadIdx.x; i < HD_WARPS * MAX_BINS; i += HD_THREADS) (&hist[0][0])[i] = 0u;
+  __syncthreads();
+  const long long HW = (long long)p.H * p.W;
+  const long long per = (HW + p.B - 1) / p.B;
+  const long long start = b * per, end = (start + per < HW) ? start + per : HW;
+  const float* xn = p.x + (size_t)n * p.h * p.w * p.xs;
+  const float inv_logc = 1.f / logf((float)p.c);
+  double ent = 0.0;
+  // uniform trip count per warp so match.any sees all 32 lanes
+  for (long long base = start + warp * 32; base < end; base += HD_THREADS) {
+    long long pix = base + lane;
+    int bin = -1;
+    if (pix < end) {
+      int ox = (int)(pix % p.W), oy = (int)(pix / p.W);
+      int y0, y1, x0, x1; float hl0, hl1, wl0, wl1;
+      bilinear_src(oy, p.sh, p.h, y0, y1, hl0, hl1);
+      bilinear_src(ox, p.sw, p.w, x0, x1, wl0, wl1);
+      const float* p00 = xn + ((size_t)y0 * p.w + x0) * p.xs;
+      const float* p01 = xn + ((size_t)y0 * p.w + x1) * p.xs;
+      const float* p10 = xn + ((size_t)y1 * p.w + x0) * p.xs;
+      const float* p11 = xn + ((size_t)y1 * p.w + x1) * p.xs;
+      float v[MAX_CLASS];
+      float best = -INFINITY; int arg = 0;
+#pragma unroll
+      for (int c = 0; c < MAX_CLASS; ++c) {
+        if (c < p.c) {
+          float val = hl0 * (wl0 * __ldg(p00 + c) + wl1 * __ldg(p01 + c)) +
+                      hl1 * (wl0 * __ldg(p10 + c) + wl1 * __ldg(p11 + c));
+          v[c] = val;
+          if (val > best) { best = val; arg = c; }   // first maximum wins, like torch.argmax
+        }
+      }
+      if (p.want_ent) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAX_CLASS; ++c) if (c < p.c) s += expf(v[c] - best);
+        float logs = logf(s), e = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAX_CLASS; ++c) if (c < p.c) {
+          float lp = v[c] - best - logs;
+          e += expf(lp) * lp;
+        }
+        ent += (double)(-e * inv_logc);
+      }
+      if (p.pred) p.pred[(size_t)n * HW + pix] = arg;
+      if (do_hist && p.gt) {
+        long long g = p.gt[(size_t)n * HW + pix];
+        if (g >= 0 && g < p.c) bin = (int)g * p.c + arg;
+      }
+    }
+    if (do_hist) warp_hist_add(hist[warp], bin, lane);
+  }
+  if (p.want_ent) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ent += __shfl_xor_sync(0xffffffffu, ent, o);
+    if (lane == 0) ent_red[warp] = ent;
+  }
+  __syncthreads();
+  if (do_hist) {
+    unsigned int* out = p.part_hist + ((size_t)n * p.B + b) * p.bins;
+    for (int i = threadIdx.x; i < p.bins; i += HD_THREADS) {
+      unsigned int s = 0;
+#pragma unroll
+      for (int wv = 0; wv < HD_WARPS; ++wv) s += hist[wv][i];
+      out[i] = s;
+    }
+  }
+  if (p.want_ent && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int wv = 0; wv < HD_WARPS; ++wv) s += ent_red[wv];
+    p.part_ent[(size_t)n * p.B + b] = s;
+  }
+}
+
+// deterministic second stage: one block per image
+__global__ void __launch_bounds__(HD_THREADS)
+head_finalize_kernel(const unsigned int* __restrict__ part_hist, const double* __restrict__ part_ent,
+                     int B, int bins, long long* __restrict__ cm_out, float* __restrict__ ent_out,
+                     double inv_hw) {
+  int n = blockIdx.x;
+  if (cm_out) {
+    for (int i = threadIdx.x; i < bins; i += HD_THREADS) {
+      long long s = 0;
+      for (int b = 0; b < B; ++b) s += part_hist[((size_t)n * B + b) * bins + i];
+      cm_out[(size_t)n * bins + i] = s;
+    }
+  }
+  if (ent_out && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int b = 0; b < B; ++b) s += part_ent[(size_t)n * B + b];
+    ent_out[n] = (float)(s * inv_hw);
+  }
+}
+
+// ---- materialise NCHW fp32 logits at full resolution -------------------------------------------
+__global__ void __launch_bounds__(256)
+upsample_logits_nchw_kernel(const float* __restrict__ x, int n_img, int h, int w, int c, int xs,
+                            float* __restrict__ dst, int H, int W, float sh, float sw) {
+  long long HW = (long long)H * W, total = HW * n_img;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    int n = (int)(idx / HW); long long pix = idx % HW;
+    int ox = (int)(pix % W), oy = (int)(pix / W);
+    int y0, y1, x0, x1; float hl0, hl1, wl0, wl1;
+    bilinear_src(oy, sh, h, y0, y1, hl0, hl1);
+    bilinear_src(ox, sw, w, x0, x1, wl0, wl1);
+    const float* xn = x + (size_t)n * h * w * xs;
+    const float* p00 = xn + ((size_t)y0 * w + x0) * xs; const float* p01 = xn + ((size_t)y0 * w + x1) * xs;
+    const float* p10 = xn + ((size_t)y1 * w + x0) * xs; const float* p11 = xn + ((size_t)y1 * w + x1) * xs;
+    float* d = dst + (size_t)n * c * HW + pix;
+    for (int ch = 0; ch < c; ++ch) {
+      float val = hl0 * (wl0 * __ldg(p00 + ch) + wl1 * __ldg(p01 + ch)) +
+                  hl1 * (wl0 * __ldg(p10 + ch) + wl1 * __ldg(p11 + ch));
+      __stcs(d + (size_t)ch * HW, val);     // streaming store: 159 MB/image/exit never re-read here
+    }
+  }
+}
+
+// ---- Evaluator._generate_matrix: int64 gt/pred -> int64 [nc*nc] -------------------------------
+__global__ void __launch_bounds__(HD_THREADS)
+confusion_kernel(const long long* __restrict__ gt, const long long* __restrict__ pred, long long n_pix,
+                 int nc, unsigned int* __restrict__ part) {
+  __shared__ unsigned int hist[HD_WARPS][MAX_BINS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < HD_WARPS * MAX_BINS; i += HD_THREADS) (&hist[0][0])[i] = 0u;
+  __syncthreads();
+  const long long per = ((n_pix + gridDim.x - 1) / gridDim.x + 1) & ~1ll;   // even → 16 B aligned pairs
+  const long long start = blockIdx.x * per, end = (start + per < n_pix) ? start + per : n_pix;
+  // two pixels per lane per iteration through 16-byte loads
+  for (long long base = start + warp * 64; base < end; base += HD_THREADS * 2) {
+    long long pix = base + lane * 2;
+    int bin0 = -1, bin1 = -1;
+    if (pix + 1 < end) {
+      longlong2 g = __ldcs(reinterpret_cast<const longlong2*>(gt + pix));
+      longlong2 q = __ldcs(reinterpret_cast<const longlong2*>(pred + pix));
+      if (g.x >= 0 && g.x < nc) bin0 = (int)(g.x * nc + q.x);
+      if (g.y >= 0 && g.y < nc) bin1 = (int)(g.y * nc + q.y);
+    } else if (pix < end) {
+      long long g = gt[pix], q = pred[pix];
+      if (g >= 0 && g < nc) bin0 = (int)(g * nc + q);
+    }
+    // a prediction outside [0,nc) would index past the matrix: drop it like bincount(minlength)
+    // cannot — the reference would grow the vector and fail the reshape; we clamp to "ignore".
+    if (bin0 >= nc * nc) bin0 = -1;
+    if (bin1 >= nc * nc) bin1 = -1;
+    warp_hist_add(hist[warp], bin0, lane);
+    warp_hist_add(hist[warp], bin1, lane);
+  }
+  __syncthreads();
+  int bins = nc * nc;
+  for (int i = threadIdx.x; i < bins; i += HD_THREADS) {
+    unsigned int s = 0;
+#pragma unroll
+    for (int wv = 0; wv < HD_WARPS; ++wv) s += hist[wv][i];
+    part[(size_t)blockIdx.x * bins + i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(HD_THREADS)
+confusion_finalize_kernel(const unsigned int* __restrict__ part, int B, int bins, long long* __restrict__ out) {
+  for (int i = threadIdx.x; i < bins; i += HD_THREADS) {
+    long long s = 0;
+    for (int b = 0; b < B; ++b) s += part[(size_t)b * bins + i];
+    out[i] = s;
+  }
+}
+
+// ---- confidence scalars on NCHW fp32 logits -----------------------------------------------------
+__global__ void __launch_bounds__(256)
+confidence_kernel(const float* __restrict__ logits, int n_img, int c, long long HW, float thr,
+                  double* __restrict__ part) {
+  __shared__ double red[2][8];
+  long long total = HW * n_img;
+  double ent = 0.0, cnt = 0.0;
+  const float inv_logc = 1.f / logf((float)c);
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    int n = (int)(idx / HW); long long pix = idx % HW;
+    const float* p = logits + (size_t)n * c * HW + pix;
+    float v[MAX_CLASS]; float best = -INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < MAX_CLASS; ++ch) if (ch < c) { v[ch] = __ldg(p + (size_t)ch * HW); best = fmaxf(best, v[ch]); }
+    float s = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < MAX_CLASS; ++ch) if (ch < c) s += expf(v[ch] - best);
+    float logs = logf(s), e = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < MAX_CLASS; ++ch) if (ch < c) { float lp = v[ch] - best - logs; e += expf(lp) * lp; }
+    ent += (double)(-e * inv_logc);
+    if (1.f / s > thr) cnt += 1.0;          // max softmax prob = exp(0)/s
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ent += __shfl_xor_sync(0xffffffffu, ent, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = ent; red[1][warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; }
+    part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+  }
+}
+
+__global__ void confidence_finalize_kernel(const double* __restrict__ part, int B, double inv_hw, float* out2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < B; ++i) { a += part[2 * i]; b += part[2 * i + 1]; }
+    out2[0] = (float)(a * inv_hw); out2[1] = (float)(b * inv_hw);
+  }
+}
+
+inline int confusion_blocks(long long n_pix) {
+  long long b = (n_pix + 4095) / 4096;
+  return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
+}
+inline int confidence_blocks(long long total) {
+  long long b = (total + 1023) / 1024;
+  return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
+}
+
+}  // namespace
+
+extern "C" int add_upsample_logits_nchw(const add_tensor_t* x, float* dst, int H, int W, void* stream) {
+  ADD_CHECK_ARG(tensor_ok(x) && dst && H > 0 && W > 0);
+  ADD_CHECK_SUP(x->dtype == ADD_F32);
+  long long total = (long long)x->n * H * W;
+  int blocks = (int)((total + 255) / 256 < 148ll * 32 ? (total + 255) / 256 : 148ll * 32);
+  upsample_logits_nchw_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const float*)x->ptr, x->n, x->h, x->w, x->c, x->pix_stride, dst, H, W,
+      (float)x->h / (float)H, (float)x->w / (float)W);
+  ADD_RETURN_LAUNCH();
+}
+
+extern "C" int64_t add_head_workspace_bytes(int n, int H, int W, int num_class) {
+  if (n <= 0 || H <= 0 || W <= 0 || num_class <= 0) return ADD_ERR_BAD_ARG;
+  int B = head_blocks_per_image((long long)H * W);
+  int64_t hist = (int64_t)n * B * num_class * num_class * sizeof(unsigned int);
+  hist = (hist + 15) & ~15ll;
+  return hist + (int64_t)n * B * sizeof(double);
+}
+
+extern "C" int add_upsample_argmax_fwd(const add_tensor_t* x, int H, int W, const int64_t* gt,
+                                       int64_t* pred_out, int64_t* cm_out, float* entropy_out,
+                                       void* workspace, int64_t workspace_bytes, void* stream) {
+  ADD_CHECK_ARG(tensor_ok(x) && H > 0 && W > 0 && workspace);
+  ADD_CHECK_ARG(!(cm_out && !gt));
+  ADD_CHECK_SUP(x->dtype == ADD_F32 && x->c <= MAX_CLASS);
+  ADD_CHECK_SUP(!cm_out || x->c * x->c <= MAX_BINS);
+  if (workspace_bytes < add_head_workspace_bytes(x->n, H, W, x->c)) return ADD_ERR_WORKSPACE;
+  HeadParams p;
+  p.x = (const float*)x->ptr; p.n = x->n; p.h = x->h; p.w = x->w; p.c = x->c; p.xs = x->pix_stride;
+  p.H = H; p.W = W; p.sh = (float)x->h / (float)H; p.sw = (float)x->w / (float)W;
+  p.gt = (const long long*)gt; p.pred = (long long*)pred_out;
+  p.bins = x->c * x->c; p.B = head_blocks_per_image((long long)H * W);
+  int64_t hist_bytes = ((int64_t)x->n * p.B * p.bins * sizeof(unsigned int) + 15) & ~15ll;
+  p.part_hist = cm_out ? (unsigned int*)workspace : nullptr;
+  p.part_ent = (double*)((char*)workspace + hist_bytes);
+  p.want_ent = entropy_out != nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid(p.B, x->n);
+  upsample_argmax_kernel<<<grid, HD_THREADS, 0, s>>>(p);
+  if (cm_out || entropy_out)
+    head_finalize_kernel<<<x->n, HD_THREADS, 0, s>>>(p.part_hist, p.part_ent, p.B, p.bins,
+                                                      (long long*)cm_out, entropy_out, 1.0 / ((double)H * W));
+  ADD_RETURN_LAUNCH();
+}
+
+extern "C" int64_t add_confusion_workspace_bytes(int64_t n_pixels, int num_class) {
+  if (n_pixels < 0 || num_class <= 0) return ADD_ERR_BAD_ARG;
+  return (int64_t)confusion_blocks(n_pixels) * num_class * num_class * sizeof(unsigned int);
+}
+
+extern "C" int add_confusion_matrix(const int64_t* gt, const int64_t* pred, int64_t n_pixels, int num_class,
+                                    int64_t* cm_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  ADD_CHECK_ARG(cm_out && workspace && n_pixels >= 0 && num_class > 0);
+  ADD_CHECK_ARG(n_pixels == 0 || (gt && pred));
+  ADD_CHECK_SUP(num_class * num_class <= MAX_BINS);
+  ADD_CHECK_SUP(((uintptr_t)gt % 16 == 0) && ((uintptr_t)pred % 16 == 0));
+  if (workspace_bytes < add_confusion_workspace_bytes(n_pixels, num_class)) return ADD_ERR_WORKSPACE;
+  int B = confusion_blocks(n_pixels);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  confusion_kernel<<<B, HD_THREADS, 0, s>>>((const long long*)gt, (const long long*)pred, n_pixels, num_class,
+                                            (unsigned int*)workspace);
+  confusion_finalize_kernel<<<1, HD_THREADS, 0, s>>>((const unsigned int*)workspace, B, num_class * num_class,
+                                                     (long long*)cm_out);
+  ADD_RETURN_LAUNCH();
+}
+
+extern "C" int64_t add_confidence_workspace_bytes(int n, int H, int W) {
+  if (n <= 0 || H <= 0 || W <= 0) return ADD_ERR_BAD_ARG;
+  return (int64_t)confidence_blocks((long long)n * H * W) * 2 * sizeof(double);
+}
+
+extern "C" int add_confidence_nchw(const float* logits, int n, int num_class, int H, int W, float threshold,
+                                   float* out2, void* workspace, int64_t workspace_bytes, void* stream) {
+  ADD_CHECK_ARG(logits && out2 && workspace && n > 0 && H > 0 && W > 0 && num_class > 0);
+  ADD_CHECK_SUP(num_class <= MAX_CLASS);
+  if (workspace_bytes < add_confidence_workspace_bytes(n, H, W)) return ADD_ERR_WORKSPACE;
+  long long HW = (long long)H * W;
+  int B = confidence_blocks(HW * n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  confidence_kernel<<<B, 256, 0, s>>>(logits, n, num_class, HW, threshold, (double*)workspace);
+  confidence_finalize_kernel<<<1, 32, 0, s>>>((const double*)workspace, B, 1.0 / (double)HW, out2);
+  ADD_RETURN_LAUNCH();
+}

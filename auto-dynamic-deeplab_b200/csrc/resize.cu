@@ -1,0 +1,187 @@
+// resize.cu — memory-bound NHWC helpers: bilinear resize, NCHW<->NHWC edges, global average
+// pool, EDM MLP tail.  All HBM-bound: vectorised 4-channel accesses, grid sized to the data.
+#include "common.cuh"
+
+namespace {
+
+// ---- bilinear, align_corners=False -----------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+bilinear_kernel(const TI* __restrict__ x, TO* __restrict__ y, int N, int H, int W, int C, int xs,
+                int Ho, int Wo, int ys, float sh, float sw, uint32_t flags) {
+  const int cv = C >> 2;
+  long long total = (long long)N * Ho * Wo * cv;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    int c = (int)(idx % cv) * 4; long long pix = idx / cv;
+    int ox = (int)(pix % Wo); long long tmp = pix / Wo; int oy = (int)(tmp % Ho); int n = (int)(tmp / Ho);
+    int y0, y1, x0, x1; float hl0, hl1, wl0, wl1;
+    bilinear_src(oy, sh, H, y0, y1, hl0, hl1);
+    bilinear_src(ox, sw, W, x0, x1, wl0, wl1);
+    const TI* xn = x + (size_t)n * H * W * xs + c;
+    float4 v00 = ld4(xn + ((size_t)y0 * W + x0) * xs), v01 = ld4(xn + ((size_t)y0 * W + x1) * xs);
+    float4 v10 = ld4(xn + ((size_t)y1 * W + x0) * xs), v11 = ld4(xn + ((size_t)y1 * W + x1) * xs);
+    if (flags & ADD_RELU_IN) { v00 = relu4(v00); v01 = relu4(v01); v10 = relu4(v10); v11 = relu4(v11); }
+    float4 r;
+    r.x = hl0 * (wl0 * v00.x + wl1 * v01.x) + hl1 * (wl0 * v10.x + wl1 * v11.x);
+    r.y = hl0 * (wl0 * v00.y + wl1 * v01.y) + hl1 * (wl0 * v10.y + wl1 * v11.y);
+    r.z = hl0 * (wl0 * v00.z + wl1 * v01.z) + hl1 * (wl0 * v10.z + wl1 * v11.z);
+    r.w = hl0 * (wl0 * v00.w + wl1 * v01.w) + hl1 * (wl0 * v10.w + wl1 * v11.w);
+    if (flags & ADD_RELU_OUT) r = relu4(r);
+    st4(y + (size_t)pix * ys + c, r);
+  }
+}
+
+// ---- NCHW fp32 -> NHWC (tile transpose through smem) -------------------------------------------
+template <typename TO>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ src, TO* __restrict__ dst, int C, int HW, int Cdst, int ys) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z;
+  int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    int c = c0 + j, p = p0 + tx;
+    tile[j][tx] = (c < C && p < HW) ? __ldg(src + ((size_t)n * C + c) * HW + p) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    int p = p0 + j, c = c0 + tx;
+    if (p < HW && c < Cdst) st1(dst + ((size_t)n * HW + p) * ys + c, tile[tx][j]);
+  }
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const TI* __restrict__ src, float* __restrict__ dst, int C, int HW, int xs) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z;
+  int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    int p = p0 + j, c = c0 + tx;
+    tile[j][tx] = (p < HW && c < C) ? ld1(src + ((size_t)n * HW + p) * xs + c) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    int c = c0 + j, p = p0 + tx;
+    if (c < C && p < HW) dst[((size_t)n * C + c) * HW + p] = tile[tx][j];
+  }
+}
+
+// ---- global average pool: one block per (image, 32-channel group) -----------------------------
+template <typename TI>
+__global__ void __launch_bounds__(256)
+gap_kernel(const TI* __restrict__ x, float* __restrict__ out, int HW, int C, int xs, uint32_t flags) {
+  __shared__ float red[8][33];
+  int n = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), row = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < C) {
+    const TI* xn = x + (size_t)n * HW * xs + c;
+    for (int p = row; p < HW; p += 8) {
+      float v = ld1(xn + (size_t)p * xs);
+      if (flags & ADD_RELU_IN) v = fmaxf(v, 0.f);
+      s += v;
+    }
+  }
+  red[row][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (row == 0 && c < C) {
+    float tot = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tot += red[r][threadIdx.x];
+    out[(size_t)n * C + c] = tot / (float)HW;
+  }
+}
+
+// ---- EDM MLP tail: one block (128 threads) per image -------------------------------------------
+__global__ void __launch_bounds__(128)
+edm_mlp_kernel(const float* __restrict__ pooled, const float* __restrict__ w0, const float* __restrict__ b0,
+               const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+               const float* __restrict__ b2, float* __restrict__ out) {
+  __shared__ float a[128], h0[64], h1[32];
+  int n = blockIdx.x, t = threadIdx.x;
+  a[t] = pooled[(size_t)n * 128 + t];
+  __syncthreads();
+  if (t < 64) {
+    float s = b0[t];
+    for (int k = 0; k < 128; ++k) s = fmaf(w0[t * 128 + k], a[k], s);
+    h0[t] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  if (t < 32) {
+    float s = b1[t];
+    for (int k = 0; k < 64; ++k) s = fmaf(w1[t * 64 + k], h0[k], s);
+    h1[t] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  if (t == 0) {
+    float s = b2[0];
+    for (int k = 0; k < 32; ++k) s = fmaf(w2[k], h1[k], s);
+    out[n] = s;
+  }
+}
+
+}  // namespace
+
+extern "C" int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, uint32_t flags, void* stream) {
+  ADD_CHECK_ARG(tensor_ok(x) && tensor_ok(y));
+  ADD_CHECK_ARG(x->n == y->n && x->c == y->c);
+  ADD_CHECK_SUP(tensor_vec4_ok(x) && tensor_vec4_ok(y));
+  float sh = (float)x->h / (float)y->h, sw = (float)x->w / (float)y->w;
+  long long total = (long long)y->n * y->h * y->w * (y->c / 4);
+  int blocks = (int)((total + 255) / 256 < 148ll * 64 ? (total + 255) / 256 : 148ll * 64);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define BL(TI, TO) bilinear_kernel<TI, TO><<<blocks, 256, 0, s>>>((const TI*)x->ptr, (TO*)y->ptr, x->n, x->h, \
+    x->w, x->c, x->pix_stride, y->h, y->w, y->pix_stride, sh, sw, flags)
+  if (x->dtype == ADD_F32 && y->dtype == ADD_F32) BL(float, float);
+  else if (x->dtype == ADD_BF16 && y->dtype == ADD_BF16) BL(bf16, bf16);
+  else if (x->dtype == ADD_F32 && y->dtype == ADD_BF16) BL(float, bf16);
+  else if (x->dtype == ADD_BF16 && y->dtype == ADD_F32) BL(bf16, float);
+  else return ADD_ERR_UNSUPPORTED;
+#undef BL
+  ADD_RETURN_LAUNCH();
+}
+
+extern "C" int add_nchw_to_nhwc(const float* src, int c_src, const add_tensor_t* y, void* stream) {
+  ADD_CHECK_ARG(src && tensor_ok(y) && c_src > 0 && c_src <= y->c);
+  int HW = y->h * y->w;
+  dim3 grid(ceil_div(HW, 32), ceil_div(y->c, 32), y->n);
+  ADD_CHECK_SUP(grid.y < 65536 && grid.z < 65536);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (y->dtype == ADD_F32)
+    nchw_to_nhwc_kernel<float><<<grid, 256, 0, s>>>(src, (float*)y->ptr, c_src, HW, y->c, y->pix_stride);
+  else
+    nchw_to_nhwc_kernel<bf16><<<grid, 256, 0, s>>>(src, (bf16*)y->ptr, c_src, HW, y->c, y->pix_stride);
+  ADD_RETURN_LAUNCH();
+}
+
+extern "C" int add_nhwc_to_nchw(const add_tensor_t* x, float* dst, void* stream) {
+  ADD_CHECK_ARG(dst && tensor_ok(x));
+  int HW = x->h * x->w;
+  dim3 grid(ceil_div(HW, 32), ceil_div(x->c, 32), x->n);
+  ADD_CHECK_SUP(grid.y < 65536 && grid.z < 65536);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (x->dtype == ADD_F32)
+    nhwc_to_nchw_kernel<float><<<grid, 256, 0, s>>>((const float*)x->ptr, dst, x->c, HW, x->pix_stride);
+  else
+    nhwc_to_nchw_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x->ptr, dst, x->c, HW, x->pix_stride);
+  ADD_RETURN_LAUNCH();
+}
+
+extern "C" int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_t flags, void* stream) {
+  ADD_CHECK_ARG(tensor_ok(x) && out);
+  dim3 grid(ceil_div(x->c, 32), x->n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (x->dtype == ADD_F32)
+    gap_kernel<float><<<grid, 256, 0, s>>>((const float*)x->ptr, out, x->h * x->w, x->c, x->pix_stride, flags);
+  else
+    gap_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x->ptr, out, x->h * x->w, x->c, x->pix_stride, flags);
+  ADD_RETURN_LAUNCH();
+}
+
+extern "C" int add_edm_mlp_fwd(const float* pooled, int n, const float* w0, const float* b0, const float* w1,
+                               const float* b1, const float* w2, const float* b2, float* out, void* stream) {
+  ADD_CHECK_ARG(pooled && w0 && b0 && w1 && b1 && w2 && b2 && out && n > 0);
+  edm_mlp_kernel<<<n, 128, 0, static_cast<cudaStream_t>(stream)>>>(pooled, w0, b0, w1, b1, w2, b2, out);
+  ADD_RETURN_LAUNCH();
+}

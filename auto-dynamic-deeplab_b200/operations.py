@@ -1,0 +1,288 @@
+"""Operator zoo — B200 drop-ins for the reference's `modeling/operations.py`.
+
+Same public names, constructor signatures and `state_dict` keys as the reference
+(operations.py:7-180) so `load_state_dict(reference_checkpoint)` works unchanged; the compute is
+different: every module *emits* fused libadd_b200 launches (ReLU-on-load, BN folded into the conv
+weights, node-sum as accumulate-into-slice) instead of calling ATen ops.  `torch.nn.Conv2d` /
+`BatchNorm2d` objects appear here only as parameter containers that fix the state_dict layout;
+their `forward` is never invoked.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import runtime as rt
+from .runtime import Builder, ConvWeights, View, RELU_IN, RELU_OUT, ACCUMULATE
+from ._lib import lib, check
+
+
+class SynchronizedBatchNorm2d(nn.BatchNorm2d):
+    """Parameter/statistics holder with the reference's class name
+    (modeling/sync_batchnorm/batchnorm.py:180).  In eval mode — the only mode on this path — it is
+    exactly `F.batch_norm` with running stats (batchnorm.py:50-53) and is folded into the conv."""
+
+
+class AddModule(nn.Module):
+    """Base: generation-tracked weight cache + the emit/forward protocol."""
+
+    def __init__(self):
+        super().__init__()
+        self._prep_gen = -1
+
+    # any parameter movement / reload invalidates folded weights and recorded plans
+    def _apply(self, fn, *a, **k):
+        rt.bump_generation()
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        rt.bump_generation()
+        return super()._load_from_state_dict(*a, **k)
+
+    def invalidate(self) -> None:
+        """Call after mutating parameters in place (e.g. an optimizer step)."""
+        rt.bump_generation()
+
+    def _ensure_prepared(self) -> None:
+        if self._prep_gen != rt.generation():
+            self._prepare()
+            self._prep_gen = rt.generation()
+
+    def _prepare(self) -> None:  # fold BN, permute weights
+        raise NotImplementedError
+
+    def _check_eval(self) -> None:
+        if self.training:
+            raise NotImplementedError(
+                f"{type(self).__name__}: training-mode forward (batch statistics / autograd) is not part of "
+                "the accelerated inference path; call .eval() (SURVEY §8f lists training as 'next')")
+
+    # ---- stand-alone call: NCHW in → NCHW (channels_last) out -------------------------------
+    def out_shape(self, n, c, h, w):
+        return n, c, h, w
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self._check_eval()
+        rt.require_cuda(x)
+        dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        b = Builder(x.device, dtype, record=False)
+        xv = rt.as_nhwc_view(x, b, dtype)
+        n, c, h, w = self.out_shape(*x.shape)
+        yv = b.alloc(n, h, w, c)
+        self.emit(b, xv, yv, 0)
+        return yv.nchw()
+
+    def emit(self, b: Builder, x: View, y: View, flags: int = 0) -> None:
+        raise NotImplementedError
+
+
+def _conv_holder(cin, cout, k, stride=1, padding=0, dilation=1, groups=1, bias=False) -> nn.Conv2d:
+    return nn.Conv2d(cin, cout, k, stride=stride, padding=padding, dilation=dilation, groups=groups, bias=bias)
+
+
+class ReLUConvBN(AddModule):
+    """ReLU → conv → BN as ONE launch (reference: operations.py:18-29; keys op.1.weight, op.2.*)."""
+
+    def __init__(self, C_in, C_out, kernel_size, stride, padding, BatchNorm, eps=1e-5, momentum=0.1, affine=True):
+        super().__init__()
+        self.op = nn.Sequential(nn.ReLU(inplace=False),
+                                _conv_holder(C_in, C_out, kernel_size, stride, padding),
+                                BatchNorm(C_out, eps=eps, momentum=momentum, affine=affine))
+        self.stride, self.padding, self.C_out = stride, padding, C_out
+
+    def _prepare(self):
+        self.cw = ConvWeights(self.op[1].weight, self.op[2])
+
+    def out_shape(self, n, c, h, w):
+        k = self.op[1].kernel_size[0]
+        return (n, self.C_out, (h + 2 * self.padding - k) // self.stride + 1,
+                (w + 2 * self.padding - k) // self.stride + 1)
+
+    def emit(self, b, x, y, flags=0):
+        self._ensure_prepared()
+        b.conv(x, y, self.cw, self.stride, self.padding, 1, RELU_IN | flags, "ReLUConvBN")
+
+
+class DilConv(AddModule):
+    """ReLU → DENSE C→C k×k dilated conv → BN as one implicit-GEMM launch
+    (reference: operations.py:32-43 — no `groups`, so this is NOT depthwise)."""
+
+    def __init__(self, C_in, C_out, kernel_size, stride, padding, dilation, BatchNorm, eps=1e-5, momentum=0.1, affine=True):
+        super().__init__()
+        self.op = nn.Sequential(nn.ReLU(inplace=False),
+                                _conv_holder(C_in, C_out, kernel_size, stride, padding, dilation),
+                                BatchNorm(C_out, eps=eps, momentum=momentum, affine=affine))
+        self.stride, self.padding, self.dilation, self.C_out, self.k = stride, padding, dilation, C_out, kernel_size
+
+    def _prepare(self):
+        self.cw = ConvWeights(self.op[1].weight, self.op[2])
+
+    def out_shape(self, n, c, h, w):
+        e = self.dilation * (self.k - 1) + 1
+        return (n, self.C_out, (h + 2 * self.padding - e) // self.stride + 1, (w + 2 * self.padding - e) // self.stride + 1)
+
+    def emit(self, b, x, y, flags=0):
+        self._ensure_prepared()
+        b.conv(x, y, self.cw, self.stride, self.padding, self.dilation, RELU_IN | flags, "DilConv")
+
+
+class SepConv(AddModule):
+    """(ReLU → depthwise k×k → pointwise 1×1 → BN) ×2 as TWO fused launches; the mid activation is
+    stored post-ReLU (reference: operations.py:46-62; keys op.1/2/3/5/6/7)."""
+
+    def __init__(self, C_in, C_out, kernel_size, stride, padding, BatchNorm, eps=1e-5, momentum=0.1, affine=True):
+        super().__init__()
+        if stride != 1 or C_in != C_out:
+            raise NotImplementedError("SepConv: ADD only instantiates stride 1, C_in == C_out (ADD.py:61)")
+        self.op = nn.Sequential(
+            nn.ReLU(inplace=False),
+            _conv_holder(C_in, C_in, kernel_size, stride, padding, groups=C_in),
+            _conv_holder(C_in, C_out, 1),
+            BatchNorm(C_out, eps=eps, momentum=momentum, affine=affine),
+            nn.ReLU(inplace=False),
+            _conv_holder(C_out, C_out, kernel_size, 1, padding, groups=C_out),
+            _conv_holder(C_out, C_out, 1),
+            BatchNorm(C_out, eps=eps, momentum=momentum, affine=affine))
+        self.k, self.C = kernel_size, C_out
+
+    def _prepare(self):
+        def dw(conv):  # [C,1,k,k] -> [k][k][C]
+            return conv.weight.detach().float()[:, 0].permute(1, 2, 0).contiguous()
+        self.dw1, self.dw2 = dw(self.op[1]), dw(self.op[5])
+        self.pw1 = ConvWeights(self.op[2].weight, self.op[3])
+        self.pw2 = ConvWeights(self.op[6].weight, self.op[7])
+
+    def emit(self, b, x, y, flags=0):
+        self._ensure_prepared()
+        mid = b.scratch(x.n, x.h, x.w, self.C)
+        b.sepconv_half(x, mid, self.dw1, self.pw1, self.k, RELU_IN | RELU_OUT, "SepConv.half1")
+        b.sepconv_half(mid, y, self.dw2, self.pw2, self.k, flags, "SepConv.half2")
+        b.release(mid)
+
+
+class Identity(AddModule):
+    """operations.py:65-71."""
+
+    def _prepare(self):
+        pass
+
+    def forward(self, x):
+        return x
+
+    def emit(self, b, x, y, flags=0):
+        raise NotImplementedError("skip_connect inside a fused cell is a supernet-only op (SURVEY §8f #2)")
+
+
+class Zero(AddModule):
+    """operations.py:74-83 (supernet-only; not on the ADD inference path)."""
+
+    def __init__(self, stride):
+        super().__init__()
+        self.stride = stride
+
+    def forward(self, x):
+        raise NotImplementedError("'none' is a supernet-only primitive (SURVEY §8f #2)")
+
+
+def _unsupported_pool(name):
+    def make(C, stride, BatchNorm, eps, momentum, affine):
+        raise NotImplementedError(f"{name} is a supernet-only primitive, not on the ADD path (SURVEY §8f #2)")
+    return make
+
+
+# operations.py:7-16 — same keys, same lambda signature.
+OPS = {
+    'none': lambda C, stride, BatchNorm, eps, momentum, affine: Zero(stride),
+    'avg_pool_3x3': _unsupported_pool('avg_pool_3x3'),
+    'max_pool_3x3': _unsupported_pool('max_pool_3x3'),
+    'skip_connect': lambda C, stride, BatchNorm, eps, momentum, affine: Identity(),
+    'sep_conv_3x3': lambda C, stride, BatchNorm, eps, momentum, affine: SepConv(C, C, 3, stride, 1, BatchNorm, eps=eps, momentum=momentum, affine=affine),
+    'sep_conv_5x5': lambda C, stride, BatchNorm, eps, momentum, affine: SepConv(C, C, 5, stride, 2, BatchNorm, eps=eps, momentum=momentum, affine=affine),
+    'dil_conv_3x3': lambda C, stride, BatchNorm, eps, momentum, affine: DilConv(C, C, 3, stride, 2, 2, BatchNorm, eps=eps, momentum=momentum, affine=affine),
+    'dil_conv_5x5': lambda C, stride, BatchNorm, eps, momentum, affine: DilConv(C, C, 5, stride, 4, 2, BatchNorm, eps=eps, momentum=momentum, affine=affine),
+}
+
+
+class _FactorizedReduceBase(AddModule):
+    """ReLU; two stride-s 1×1 convs on the lattices at offset 0 and s/2; channel-cat; BN — as two
+    launches that write the two channel halves directly, each with its half of the BN folded in.
+    The odd lattice is the same kernel with pad = -s/2 (out-of-range taps read zero, matching the
+    reference's ConstantPad2d + slice)."""
+    STEP = 2
+
+    def __init__(self, C_in, C_out, BatchNorm, eps=1e-5, momentum=0.1, affine=True, _bn_kwargs=None):
+        super().__init__()
+        assert C_out % 2 == 0
+        self.relu = nn.ReLU(inplace=False)
+        self.conv_1 = _conv_holder(C_in, C_out // 2, 1, stride=self.STEP)
+        self.conv_2 = _conv_holder(C_in, C_out // 2, 1, stride=self.STEP)
+        self.bn = BatchNorm(C_out, **(_bn_kwargs if _bn_kwargs is not None else dict(eps=eps, momentum=momentum, affine=affine)))
+        self.C_out = C_out
+
+    def _prepare(self):
+        half = self.C_out // 2
+        scale, shift = rt.bn_scale_shift(self.bn)
+
+        class _Half:  # a BN view restricted to one half of the channels
+            def __init__(s, lo, hi, bn):
+                s.running_var, s.running_mean = bn.running_var[lo:hi], bn.running_mean[lo:hi]
+                s.weight = bn.weight[lo:hi] if bn.weight is not None else None
+                s.bias = bn.bias[lo:hi] if bn.bias is not None else None
+                s.eps = bn.eps
+        self.cw1 = ConvWeights(self.conv_1.weight, _Half(0, half, self.bn))
+        self.cw2 = ConvWeights(self.conv_2.weight, _Half(half, self.C_out, self.bn))
+
+    def out_shape(self, n, c, h, w):
+        s = self.STEP
+        return n, self.C_out, (h - 1) // s + 1, (w - 1) // s + 1
+
+    def emit(self, b, x, y, flags=0):
+        self._ensure_prepared()
+        half = self.C_out // 2
+        b.conv(x, y.slice(0, half), self.cw1, self.STEP, 0, 1, RELU_IN | flags, type(self).__name__ + ".even")
+        b.conv(x, y.slice(half, half), self.cw2, self.STEP, -(self.STEP // 2), 1, RELU_IN | flags,
+               type(self).__name__ + ".odd")
+
+
+class FactorizedReduce(_FactorizedReduceBase):
+    """operations.py:86-101."""
+    STEP = 2
+
+
+class DoubleFactorizedReduce(_FactorizedReduceBase):
+    """operations.py:104-119 — stride 4, offset 2; its BN ignores the eps/momentum args (Q10)."""
+    STEP = 4
+
+    def __init__(self, C_in, C_out, BatchNorm, eps=1e-5, momentum=0.1, affine=True):
+        super().__init__(C_in, C_out, BatchNorm, _bn_kwargs=dict(affine=affine))
+
+
+# ---- confidence scalars (operations.py:161-180) ------------------------------------------------
+
+def _confidence(x: torch.Tensor, threshold: float, num_class: int):
+    rt.require_cuda(x, "logits")
+    n, c, h, w = x.shape
+    assert c == num_class
+    x = x.float().contiguous()
+    nbytes = lib.add_confidence_workspace_bytes(n, h, w)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    import ctypes
+    s = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    check(lib.add_confidence_nchw(x.data_ptr(), n, c, h, w, float(threshold), out.data_ptr(), ws.data_ptr(),
+                                  nbytes, s), "confidence_nchw")
+    return out
+
+
+def normalized_shannon_entropy(x, num_class=19):
+    """operations.py:161-170: -Σ p·log p / log(num_class), summed over batch and pixels, / (H·W);
+    returned as a Python float (a device sync, as in the reference's `.item()`)."""
+    return _confidence(x, 2.0, num_class)[0].item()
+
+
+def confidence_max(x, thresold, num_class=19):
+    """operations.py:172-180: fraction of pixels whose max softmax probability exceeds `thresold`."""
+    return _confidence(x, thresold, num_class)[1].item()

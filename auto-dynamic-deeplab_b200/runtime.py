@@ -1,0 +1,306 @@
+"""Host-side runtime: NHWC views, folded weights, and the launch recorder / replayer.
+
+The drop-in modules never call PyTorch compute ops on activations.  They *emit* libadd_b200
+launches through a `Builder`: eagerly (per-op modules called on their own) or recorded into a
+`Plan` that `ADD.forward` replays — optionally as one CUDA graph — with every concat / node-sum
+expressed as channel-slice writes.  PyTorch supplies device memory, streams and graphs only.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AddTensor, lib, check, ADD_F32, ADD_BF16, RELU_IN, RELU_OUT, ACCUMULATE
+
+_GENERATION = 0  # bumped whenever any add_b200 module's parameters may have changed
+
+
+def bump_generation() -> None:
+    global _GENERATION
+    _GENERATION += 1
+
+
+def generation() -> int:
+    return _GENERATION
+
+
+_DTYPES = {torch.float32: ADD_F32, torch.bfloat16: ADD_BF16}
+_PRECISION = {"fp32": torch.float32, "bf16": torch.bfloat16}
+_default_precision = "fp32"
+
+
+def set_default_precision(p: str) -> None:
+    """'fp32' (exact CUDA-core path) or 'bf16' (bf16 activations, tensor-core contractions)."""
+    global _default_precision
+    if p not in _PRECISION:
+        raise ValueError(f"precision must be one of {list(_PRECISION)}")
+    _default_precision = p
+    bump_generation()
+
+
+def default_precision() -> str:
+    return _default_precision
+
+
+def act_dtype(precision: Optional[str] = None) -> torch.dtype:
+    return _PRECISION[precision or _default_precision]
+
+
+def require_cuda(t: torch.Tensor, what: str = "input") -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"add_b200: {what} must be a CUDA tensor — this framework has no CPU fallback "
+                           "(the CPU oracle lives in oracle/ and is test infrastructure only)")
+
+
+class View:
+    """Channel-slice view of a dense NHWC buffer (torch tensor of shape [N,H,W,Ctot])."""
+    __slots__ = ("buf", "c_off", "c")
+
+    def __init__(self, buf: torch.Tensor, c_off: int = 0, c: Optional[int] = None):
+        assert buf.dim() == 4 and buf.is_contiguous()
+        self.buf = buf
+        self.c_off = c_off
+        self.c = buf.shape[3] - c_off if c is None else c
+        assert 0 <= c_off and c_off + self.c <= buf.shape[3]
+
+    n = property(lambda s: s.buf.shape[0])
+    h = property(lambda s: s.buf.shape[1])
+    w = property(lambda s: s.buf.shape[2])
+    dtype = property(lambda s: s.buf.dtype)
+
+    def slice(self, off: int, c: int) -> "View":
+        return View(self.buf, self.c_off + off, c)
+
+    def desc(self) -> AddTensor:
+        b = self.buf
+        return AddTensor(b.data_ptr() + self.c_off * b.element_size(), b.shape[0], b.shape[1], b.shape[2],
+                         self.c, b.shape[3], _DTYPES[b.dtype])
+
+    def nchw(self) -> torch.Tensor:
+        """Logical NCHW tensor (channels_last strides) aliasing this view — zero copy."""
+        t = self.buf[..., self.c_off:self.c_off + self.c]
+        return t.permute(0, 3, 1, 2)
+
+
+class ConvWeights:
+    """A conv (+ folded eval-mode BN) ready for the kernels: fp32 [kh][kw][Cin][Cout] with the BN
+    scale folded in, fp32 bias (w' = w·γ/σ, b' = β − μ·γ/σ), and, lazily, the
+    bf16 UMMA-packed image for the tcgen05 path."""
+
+    def __init__(self, weight: torch.Tensor, bn=None, bias: Optional[torch.Tensor] = None,
+                 cin_pad: Optional[int] = None):
+        w = weight.detach().float()
+        co, ci, kh, kw = w.shape
+        if bn is not None:
+            scale, shift = bn_scale_shift(bn)
+            w = w * scale.view(-1, 1, 1, 1)
+            b = shift if bias is None else shift + bias.detach().float() * scale
+        else:
+            b = bias.detach().float() if bias is not None else None
+        w = w.permute(2, 3, 1, 0).contiguous()  # [kh][kw][Cin][Cout]
+        if cin_pad is not None and cin_pad > ci:
+            wp = torch.zeros(kh, kw, cin_pad, co, device=w.device, dtype=w.dtype)
+            wp[:, :, :ci] = w
+            w, ci = wp, cin_pad
+        self.w = w.contiguous()
+        self.bias = b.contiguous() if b is not None else None
+        self.cin, self.cout, self.kh, self.kw = ci, co, kh, kw
+        self._packed: Optional[torch.Tensor] = None
+
+    def packed_tc(self) -> torch.Tensor:
+        if self._packed is None:
+            nbytes = lib.add_conv2d_tc_packed_bytes(self.cin, self.cout, self.kh, self.kw)
+            if nbytes < 0:
+                check(int(nbytes), "conv2d_tc_packed_bytes")
+            host = torch.empty(nbytes, dtype=torch.uint8)
+            w_host = self.w.cpu().contiguous()
+            check(lib.add_conv2d_tc_pack(w_host.data_ptr(), self.cin, self.cout, self.kh, self.kw,
+                                         host.data_ptr()), "conv2d_tc_pack")
+            self._packed = host.to(self.w.device)
+        return self._packed
+
+
+def bn_scale_shift(bn) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-mode BatchNorm as y = x*scale + shift (fp32)."""
+    var = bn.running_var.detach().float()
+    mean = bn.running_mean.detach().float()
+    inv = torch.rsqrt(var + bn.eps)
+    gamma = bn.weight.detach().float() if bn.weight is not None else torch.ones_like(var)
+    beta = bn.bias.detach().float() if bn.bias is not None else torch.zeros_like(var)
+    scale = gamma * inv
+    return scale, beta - mean * scale
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# Which convs go to the tcgen05 path.  Set by conv_tc availability probing (see tc_available()).
+_TC_STATE = {"enabled": True, "probed": None}
+
+
+def tc_available() -> bool:
+    if _TC_STATE["probed"] is None:
+        _TC_STATE["probed"] = lib.add_conv2d_tc_packed_bytes(64, 64, 1, 1) > 0
+    return bool(_TC_STATE["probed"]) and _TC_STATE["enabled"]
+
+
+def set_tc_enabled(flag: bool) -> None:
+    _TC_STATE["enabled"] = bool(flag)
+    bump_generation()
+
+
+class Builder:
+    """Emits kernel launches.  record=False: launch immediately on the current stream.
+    record=True: append to a launch list that `Plan` replays."""
+
+    def __init__(self, device: torch.device, dtype: torch.dtype, record: bool = False):
+        self.device = device
+        self.dtype = dtype
+        self.record = record
+        self.launches: List[Tuple[Callable, tuple, str]] = []
+        self.keep: List[object] = []
+        self._pool: Dict[tuple, List[torch.Tensor]] = {}
+        self.bytes_allocated = 0
+
+    # ---- memory ---------------------------------------------------------------------------
+    def alloc(self, n: int, h: int, w: int, c: int, dtype: Optional[torch.dtype] = None) -> View:
+        t = torch.empty((n, h, w, c), device=self.device, dtype=dtype or self.dtype)
+        self.bytes_allocated += t.numel() * t.element_size()
+        self.keep.append(t)
+        return View(t)
+
+    def scratch(self, n: int, h: int, w: int, c: int, dtype: Optional[torch.dtype] = None) -> View:
+        key = (n, h, w, c, dtype or self.dtype)
+        pool = self._pool.setdefault(key, [])
+        if pool:
+            return View(pool.pop())
+        return self.alloc(n, h, w, c, dtype)
+
+    def release(self, v: View) -> None:
+        b = v.buf
+        self._pool.setdefault((b.shape[0], b.shape[1], b.shape[2], b.shape[3], b.dtype), []).append(b)
+
+    def raw(self, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
+        t = torch.empty(tuple(shape), device=self.device, dtype=dtype)
+        self.bytes_allocated += t.numel() * t.element_size()
+        self.keep.append(t)
+        return t
+
+    # ---- launch plumbing ------------------------------------------------------------------
+    def _emit(self, fn, args: tuple, tag: str) -> None:
+        if self.record:
+            self.launches.append((fn, args, tag))
+        else:
+            s = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            check(fn(*args, s), tag)
+
+    def _d(self, v: View):
+        d = v.desc()
+        self.keep.append(d)
+        return ctypes.byref(d)
+
+    # ---- ops --------------------------------------------------------------------------------
+    def conv(self, x: View, y: View, cw: ConvWeights, stride: int = 1, pad: int = 0, dil: int = 1,
+             flags: int = 0, tag: str = "conv") -> None:
+        assert x.c == cw.cin and y.c == cw.cout, (x.c, cw.cin, y.c, cw.cout, tag)
+        self.keep.append(cw)
+        use_tc = (x.dtype == torch.bfloat16 and tc_available())
+        if use_tc:
+            self._emit(lib.add_conv2d_tc_fwd,
+                       (self._d(x), self._d(y), cw.packed_tc().data_ptr(), _ptr(cw.bias), cw.kh, cw.kw,
+                        stride, pad, dil, flags), tag + ":tc")
+        else:
+            self._emit(lib.add_conv2d_fwd,
+                       (self._d(x), self._d(y), cw.w.data_ptr(), _ptr(cw.bias), cw.kh, cw.kw,
+                        stride, pad, dil, flags), tag)
+
+    def sepconv_half(self, x: View, y: View, w_dw: torch.Tensor, pw: ConvWeights, k: int, flags: int,
+                     tag: str = "sephalf") -> None:
+        self.keep.extend((w_dw, pw))
+        self._emit(lib.add_sepconv_half_fwd,
+                   (self._d(x), self._d(y), w_dw.data_ptr(), pw.w.data_ptr(), _ptr(pw.bias), k, flags), tag)
+
+    def bilinear(self, x: View, y: View, flags: int = 0, tag: str = "bilinear") -> None:
+        self._emit(lib.add_bilinear_fwd, (self._d(x), self._d(y), flags), tag)
+
+    def gap(self, x: View, out: torch.Tensor, flags: int = 0, tag: str = "gap") -> None:
+        self._emit(lib.add_global_avgpool_fwd, (self._d(x), out.data_ptr(), flags), tag)
+
+    def nchw_to_nhwc(self, src: torch.Tensor, c_src: int, y: View, tag: str = "nchw2nhwc") -> None:
+        self.keep.append(src)
+        self._emit(lib.add_nchw_to_nhwc, (src.data_ptr(), c_src, self._d(y)), tag)
+
+    def nhwc_to_nchw(self, x: View, dst: torch.Tensor, tag: str = "nhwc2nchw") -> None:
+        self._emit(lib.add_nhwc_to_nchw, (self._d(x), dst.data_ptr()), tag)
+
+    def upsample_logits(self, x: View, dst: torch.Tensor, H: int, W: int, tag: str = "upsample_logits") -> None:
+        self._emit(lib.add_upsample_logits_nchw, (self._d(x), dst.data_ptr(), H, W), tag)
+
+    def upsample_argmax(self, x: View, H: int, W: int, gt: Optional[torch.Tensor], pred: Optional[torch.Tensor],
+                        cm: Optional[torch.Tensor], ent: Optional[torch.Tensor], tag: str = "upsample_argmax") -> None:
+        nbytes = lib.add_head_workspace_bytes(x.n, H, W, x.c)
+        ws = self.raw((nbytes,), torch.uint8)
+        self._emit(lib.add_upsample_argmax_fwd,
+                   (self._d(x), H, W, _ptr(gt), _ptr(pred), _ptr(cm), _ptr(ent), ws.data_ptr(), nbytes), tag)
+
+    def edm_mlp(self, pooled: torch.Tensor, n: int, ws: Sequence[torch.Tensor], out: torch.Tensor,
+                tag: str = "edm_mlp") -> None:
+        self.keep.extend(ws)
+        self._emit(lib.add_edm_mlp_fwd, (pooled.data_ptr(), n, *[t.data_ptr() for t in ws], out.data_ptr()), tag)
+
+
+class Plan:
+    """A recorded launch list bound to its buffers; `run()` replays it on the current stream,
+    `capture()` turns it into a CUDA graph (launch-bound inner loops: ~400 kernels per forward)."""
+
+    def __init__(self, builder: Builder, start: int = 0, stop: Optional[int] = None):
+        assert builder.record
+        self.builder = builder
+        self.launches = builder.launches[start:stop]
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.generation = generation()
+
+    @property
+    def n_launches(self) -> int:
+        return len(self.launches)
+
+    def run_eager(self) -> None:
+        s = ctypes.c_void_p(torch.cuda.current_stream(self.builder.device).cuda_stream)
+        for fn, args, tag in self.launches:
+            rc = fn(*args, s)
+            if rc != 0:
+                check(rc, tag)
+
+    def capture(self) -> None:
+        self.run_eager()  # warm-up: cudaFuncSetAttribute calls must not happen inside capture
+        torch.cuda.current_stream(self.builder.device).synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run_eager()
+        self.graph = g
+
+    def run(self) -> None:
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run_eager()
+
+
+def as_nhwc_view(x: torch.Tensor, builder: Builder, dtype: torch.dtype, c_pad: Optional[int] = None) -> View:
+    """Bring a logical-NCHW tensor (the reference's API layout) into an NHWC View of `dtype`.
+    Zero copy when it already is channels_last in the right dtype with no padding needed."""
+    require_cuda(x)
+    n, c, h, w = x.shape
+    cp = c_pad or c
+    if x.dtype == dtype and cp == c and x.permute(0, 2, 3, 1).is_contiguous():
+        return View(x.permute(0, 2, 3, 1))
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        # dtype/stride normalisation of an API-edge tensor (plumbing, not the hot path)
+        x = x.float().contiguous()
+    y = builder.alloc(n, h, w, cp, dtype)
+    builder.nchw_to_nhwc(x, c, y)
+    return y

@@ -1,0 +1,132 @@
+/*
+ * add_b200.h — C ABI of libadd_b200.so, the B200 (sm_100a) kernels behind the ADD
+ * dense-segmentation forward path.
+ *
+ * The reference (HankKung/Auto-Dynamic-DeepLab) has no native layer: its "FFI" for this path is
+ * the set of ATen/cuDNN calls its Python modules dispatch to.  Each entry point below names the
+ * reference call site(s) it replaces (file:line under /root/reference).  The Python drop-in
+ * modules in auto-dynamic-deeplab_b200/ bind these symbols with ctypes.
+ *
+ * Conventions
+ *  - Plain C: device pointers, ints, a cudaStream_t passed as void*.  No torch types.
+ *  - The caller owns every buffer (inputs, outputs, workspaces).  The library never allocates,
+ *    never synchronises, and is re-entrant; work is enqueued on `stream`.
+ *  - Activations are NHWC ("channels_last") views described by add_tensor_t; a view may be a
+ *    channel slice of a wider buffer (pix_stride > c), which is how concat / node-sum are fused.
+ *  - Return value: ADD_OK (0) or a negative add_status_t.  add_status_string() explains it.
+ *  - There is no CPU fallback: without a CUDA device every launch returns ADD_ERR_CUDA.
+ */
+#ifndef ADD_B200_H_
+#define ADD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ADD_OK = 0,
+  ADD_ERR_BAD_ARG = -1,      /* null pointer, negative size, bad enum                     */
+  ADD_ERR_UNSUPPORTED = -2,  /* shape / dtype / alignment the kernels do not implement    */
+  ADD_ERR_CUDA = -3,         /* cudaGetLastError() after launch was not cudaSuccess       */
+  ADD_ERR_WORKSPACE = -4     /* caller-provided workspace too small                       */
+} add_status_t;
+
+typedef enum { ADD_F32 = 0, ADD_BF16 = 1 } add_dtype_t;
+
+/* NHWC activation view.  Element (n,y,x,ch) lives at
+ *   ptr + ((n*h + y)*w + x) * pix_stride + ch          (in elements of `dtype`)
+ * so a channel slice of a wider concat buffer is {ptr = base + c_off, c, pix_stride = C_total}. */
+typedef struct {
+  void*   ptr;
+  int32_t n, h, w, c;
+  int32_t pix_stride;
+  int32_t dtype;             /* add_dtype_t */
+} add_tensor_t;
+
+/* op flags */
+#define ADD_RELU_IN    1u    /* apply ReLU to the input as it is loaded (ReLU→conv order)         */
+#define ADD_RELU_OUT   2u    /* apply ReLU to the result before it is stored                      */
+#define ADD_ACCUMULATE 4u    /* y += result instead of y = result (cell node sum, ADD.py:108)     */
+
+const char* add_status_string(int status);
+int  add_version(void);               /* 10000*major + 100*minor + patch                       */
+int  add_device_sm_count(void);       /* SMs of the current device, <0 on error                */
+
+/* ---- layout / dtype edges --------------------------------------------------------------- */
+
+/* NCHW fp32 (the reference's tensor layout at its Python API) → NHWC view (fp32 or bf16).
+ * Channels c_src..y->c-1 of the destination are zero-filled (stem0 pads 3 → 4 channels). */
+int add_nchw_to_nhwc(const float* src, int c_src, const add_tensor_t* y, void* stream);
+/* NHWC view → NCHW fp32. */
+int add_nhwc_to_nchw(const add_tensor_t* x, float* dst, void* stream);
+
+/* ---- dense convolution (CUDA-core fp32 accumulate; any dtype mix) ------------------------ */
+/* Replaces nn.Conv2d + folded eval-mode BatchNorm (+ReLU) call sites: ReLUConvBN
+ * (operations.py:18-29), DilConv (operations.py:32-43), FactorizedReduce / DoubleFactorizedReduce
+ * (operations.py:86-119, as two launches with pad = 0 and pad = -stride/2 into channel halves),
+ * stems (ADD.py:154-169), low_level_conv (ADD.py:255-259), ASPP_train branches
+ * (aspp_train.py:16-25), Decoder._conv (decoder.py:12-21), EDM.conv (ADD.py:508).
+ *   y[n,oy,ox,co] (+)= act( bias[co] + sum_{ky,kx,ci} w[ky][kx][ci][co] *
+ *                           relu?(x[n, oy*stride - pad + ky*dil, ox*stride - pad + kx*dil, ci]) )
+ * w: fp32, layout [kh][kw][Cin][Cout] with the BN scale already folded in; bias: fp32[Cout] or NULL.
+ * `pad` may be negative (FactorizedReduce's odd lattice).  Out-of-range taps read zero. */
+int add_conv2d_fwd(const add_tensor_t* x, const add_tensor_t* y, const float* w, const float* bias,
+                   int kh, int kw, int stride, int pad, int dil, uint32_t flags, void* stream);
+
+/* ---- dense convolution on tcgen05 tensor cores (bf16 in, fp32 TMEM accumulate) ----------- */
+/* Same contract as add_conv2d_fwd for bf16 activations; weights are pre-packed by
+ * add_conv2d_tc_pack() into the UMMA shared-memory image the kernel streams with bulk copies. */
+int64_t add_conv2d_tc_packed_bytes(int cin, int cout, int kh, int kw);
+int add_conv2d_tc_pack(const float* w_hwio, int cin, int cout, int kh, int kw, void* packed_host);
+int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, const void* w_packed,
+                      const float* bias, int kh, int kw, int stride, int pad, int dil,
+                      uint32_t flags, void* stream);
+
+/* ---- SepConv half: ReLU → depthwise k×k → pointwise 1×1 → folded BN ---------------------- */
+/* Replaces operations.py:51-54 and :55-58 (two calls make one SepConv, operations.py:46-62).
+ * w_dw: fp32 [k][k][C]; w_pw: fp32 [Cin][Cout] (BN scale folded); bias fp32[Cout]. Stride 1, pad k/2. */
+int add_sepconv_half_fwd(const add_tensor_t* x, const add_tensor_t* y, const float* w_dw,
+                         const float* w_pw, const float* bias, int k, uint32_t flags, void* stream);
+
+/* ---- bilinear resize, align_corners=False (F.interpolate: ADD.py:76,84,89,317; decoder.py:24) */
+int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, uint32_t flags, void* stream);
+
+/* ---- global average pool (aspp_train.py:49, ADD.py:522): out[n][c] fp32 = mean_hw relu?(x) */
+int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_t flags, void* stream);
+
+/* ---- EDM tail (ADD.py:509-513,523-525): pooled[n][128] → Linear/ReLU ×2 → Linear → out[n] */
+int add_edm_mlp_fwd(const float* pooled, int n, const float* w0, const float* b0, const float* w1,
+                    const float* b1, const float* w2, const float* b2, float* out, void* stream);
+
+/* ---- exit head: final bilinear (decoder.py:28) fused with its consumers -------------------- */
+/* logits view x: [n,h,w,num_class] fp32 NHWC at decoder resolution; (H,W) = input image size.   */
+/* (a) materialise the reference's return value: NCHW fp32 [n,num_class,H,W]                    */
+int add_upsample_logits_nchw(const add_tensor_t* x, float* dst, int H, int W, void* stream);
+/* (b) upsample → argmax (eval.py:183) → optional int64 prediction map and/or confusion matrix
+ *     (utils/metrics.py:34-39).  gt: int64 [n,H,W] or NULL; pred_out: int64 [n,H,W] or NULL;
+ *     cm_out: int64 [n][num_class*num_class] per-image matrices or NULL;
+ *     entropy_out: float [n] per-image normalized Shannon entropy (operations.py:161-170) or NULL.
+ *     workspace: add_head_workspace_bytes() bytes.                                              */
+int64_t add_head_workspace_bytes(int n, int H, int W, int num_class);
+int add_upsample_argmax_fwd(const add_tensor_t* x, int H, int W, const int64_t* gt,
+                            int64_t* pred_out, int64_t* cm_out, float* entropy_out,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- Evaluator (utils/metrics.py:34-39): int64 confusion matrix, atomics-free ------------ */
+int64_t add_confusion_workspace_bytes(int64_t n_pixels, int num_class);
+int add_confusion_matrix(const int64_t* gt, const int64_t* pred, int64_t n_pixels, int num_class,
+                         int64_t* cm_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- confidence scalars on materialised NCHW fp32 logits (operations.py:161-180) ---------- */
+/* out[0] = normalized Shannon entropy summed over batch and pixels / (H*W);
+ * out[1] = fraction of pixels whose max softmax prob > threshold (also / (H*W)).               */
+int64_t add_confidence_workspace_bytes(int n, int H, int W);
+int add_confidence_nchw(const float* logits, int n, int num_class, int H, int W, float threshold,
+                        float* out2, void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADD_B200_H_ */

@@ -1,0 +1,134 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(/root/reference, read-only) on seeded inputs and weights.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The reference has no tests or golden vectors of its own, so these fixtures — outputs
+of the reference itself — are what pins the oracle (oracle/add_oracle.py) and, through it, the CUDA
+path.  Weights are NOT stored: they are regenerated deterministically (CPU RNG, fixed seeds) by
+`tests/util.py::make_weights`, which builds OUR drop-in module; loading its state_dict into the
+reference module with strict=True is itself the key-compatibility check.  A checksum of the
+weights is stored so RNG drift is detected instead of silently mis-compared.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, "/root/reference")
+
+import util  # noqa: E402  (tests/util.py)
+from modeling import operations as ref_ops  # noqa: E402
+from modeling.ADD import ADD as RefADD, EDM as RefEDM, Cell as RefCell  # noqa: E402
+from modeling.aspp_train import ASPP_train as RefASPP  # noqa: E402
+from modeling.decoder import Decoder as RefDecoder  # noqa: E402
+from utils.metrics import Evaluator as RefEvaluator  # noqa: E402
+
+torch.cuda.synchronize = lambda *a, **k: None   # ADD.dynamic_inference calls it (ADD.py:380); CPU here
+torch.set_num_threads(8)
+OUT = Path(__file__).resolve().parent
+BN = torch.nn.BatchNorm2d
+
+
+def f32(t):
+    return t.detach().cpu().numpy().astype(np.float32)
+
+
+def gen_ops():
+    g = {}
+    for name, spec in util.OP_CASES.items():
+        ours, x = util.make_op_case(name)
+        kind, args = spec["kind"], spec["args"]
+        if kind == "OPS":
+            ref = ref_ops.OPS[args[0]](args[1], 1, BN, 1e-5, 0.1, True)
+        else:
+            ref = getattr(ref_ops, kind)(*args, BN)
+        ref.load_state_dict(ours.state_dict(), strict=True)
+        ref.eval()
+        with torch.no_grad():
+            y = ref(x)
+        g[name + "/y"] = f32(y)
+        g[name + "/wsum"] = np.float64(util.weight_checksum(ours.state_dict()))
+    # ASPP_train / Decoder / EDM
+    ours, x = util.make_aspp_case()
+    ref = RefASPP(util.ASPP_CASE["C"], util.ASPP_CASE["out"], BN, depth=util.ASPP_CASE["depth"], mult=util.ASPP_CASE["mult"])
+    ref.load_state_dict(ours.state_dict(), strict=True); ref.eval()
+    with torch.no_grad():
+        g["aspp/y"] = f32(ref(x))
+    g["aspp/wsum"] = np.float64(util.weight_checksum(ours.state_dict()))
+    ours, x, low, size = util.make_decoder_case()
+    ref = RefDecoder(19, BN); ref.load_state_dict(ours.state_dict(), strict=True); ref.eval()
+    with torch.no_grad():
+        g["decoder/y"] = f32(ref(x.clone(), low.clone(), size))
+    g["decoder/wsum"] = np.float64(util.weight_checksum(ours.state_dict()))
+    ours, x = util.make_edm_case()
+    ref = RefEDM(); ref.load_state_dict(ours.state_dict(), strict=True); ref.eval()
+    with torch.no_grad():
+        g["edm/y"] = f32(ref(x.clone()))
+    g["edm/wsum"] = np.float64(util.weight_checksum(ours.state_dict()))
+    # confidence scalars
+    lg = util.make_logits_case()
+    g["conf/entropy"] = np.float64(ref_ops.normalized_shannon_entropy(lg))
+    g["conf/max_0.3"] = np.float64(ref_ops.confidence_max(lg, 0.3))
+    g["conf/max_0.6"] = np.float64(ref_ops.confidence_max(lg, 0.6))
+    # Evaluator
+    for cname, (gt, pred) in util.make_evaluator_cases().items():
+        ev = RefEvaluator(19)
+        cm = ev._generate_matrix(gt, pred)
+        g[f"evaluator/{cname}/cm"] = cm.numpy().astype(np.int64)
+        ev.add_batch(gt, pred)
+        g[f"evaluator/{cname}/miou"] = np.float64(ev.Mean_Intersection_over_Union())
+    np.savez_compressed(OUT / "ops.npz", **g)
+    print("ops.npz", len(g), "entries")
+
+
+def gen_nets():
+    g = {}
+    for cname, spec in util.NET_CASES.items():
+        ours = util.make_net(spec)
+        na, ci, low = util.net_arch(spec)
+        ref = RefADD(na, ci, util.cell_arch(), 19, SimpleNamespace(F=spec["F"], B=5, sync_bn=False), low)
+        ref.load_state_dict(ours.state_dict(), strict=True)
+        ref.eval()
+        g[f"{cname}/wsum"] = np.float64(util.weight_checksum(ours.state_dict()))
+        for (h, w) in spec["sizes"]:
+            x, gt = util.make_input(1, h, w)
+            with torch.no_grad():
+                outs = ref(x)
+            tag = f"{cname}/{h}x{w}"
+            for e, o in enumerate(outs):
+                g[f"{tag}/forward/{e}"] = f32(o)
+                ev = RefEvaluator(19)
+                g[f"{tag}/cm/{e}"] = ev._generate_matrix(gt, torch.argmax(o, 1)).numpy().astype(np.int64)
+            if spec.get("dynamic"):
+                with torch.no_grad():
+                    lg, feat = ref.get_feature(x)
+                g[f"{tag}/get_feature/logits"] = f32(lg)
+                g[f"{tag}/get_feature/feature_sum"] = np.float64(feat.double().abs().sum().item())
+                edm_ours = util.make_edm()
+                edm = RefEDM(); edm.load_state_dict(edm_ours.state_dict(), strict=True); edm.eval()
+                with torch.no_grad():
+                    c0 = float(edm(feat.clone()))
+                g[f"{tag}/edm_value"] = np.float64(c0)
+                for label, thr in (("exit", c0 + 1.0), ("noexit", c0 - 1.0)):
+                    with torch.no_grad():
+                        y, ee, _, cv = ref.dynamic_inference(x, threshold=thr, confidence='edm', edm=edm)
+                    assert ee == (1 if label == "exit" else 0)
+                    g[f"{tag}/dynamic_edm/{label}/y"] = f32(y)
+                    g[f"{tag}/dynamic_edm/{label}/conf"] = np.float64(float(cv))
+        print(cname, "done")
+    np.savez_compressed(OUT / "nets.npz", **g)
+    print("nets.npz", len(g), "entries", os.path.getsize(OUT / "nets.npz") / 1e6, "MB")
+
+
+if __name__ == "__main__":
+    gen_ops()
+    gen_nets()

@@ -1,0 +1,99 @@
+"""GPU: whole-network parity (all exits, get_feature, EDM-gated dynamic_inference, fused evaluate)
+against the golden outputs of the unmodified reference.
+Tolerances: fp32 logits <= 1e-3 max-norm relative (north_star), argmax agreement >= 99.9 %,
+confusion matrix bit-exact given identical predictions."""
+import numpy as np
+import pytest
+import torch
+
+import util
+import add_b200
+from util import orc
+
+pytestmark = pytest.mark.gpu
+NETS = np.load(util.ROOT / "tests/golden/nets.npz")
+DEV = "cuda:0"
+
+
+def _agree(a, b):
+    return float((a.argmax(1) == b.argmax(1)).float().mean())
+
+
+@pytest.mark.parametrize("cname", sorted(util.NET_CASES))
+@pytest.mark.parametrize("graph", [False, True])
+def test_forward_all_exits(cname, graph):
+    spec = util.NET_CASES[cname]
+    net = util.make_net(spec).to(DEV)
+    net.use_cuda_graph = graph
+    for (h, w) in spec["sizes"]:
+        x, gt = util.make_input(1, h, w)
+        tag = f"{cname}/{h}x{w}"
+        outs = net(x.to(DEV))
+        n_exits = len([k for k in NETS.files if k.startswith(f"{tag}/forward/")])
+        assert len(outs) == n_exits
+        for e, o in enumerate(outs):
+            ref = torch.from_numpy(NETS[f"{tag}/forward/{e}"])
+            assert tuple(o.shape) == tuple(ref.shape) and o.dtype == torch.float32
+            assert util.rel_err(o, ref) < 1e-3
+            assert _agree(o.cpu(), ref) >= 0.999
+            # Evaluator on OUR predictions vs oracle histogram of the same predictions: bit-exact
+            pred = o.argmax(1)
+            ev = add_b200.Evaluator(19)
+            cm = ev._generate_matrix(gt.to(DEV), pred).cpu().numpy()
+            assert np.array_equal(cm, orc.generate_matrix(gt.numpy(), pred.cpu().numpy()))
+        # fused head: argmax + confusion matrix without materialising full-res logits
+        cms = net.evaluate(x.to(DEV), gt.to(DEV)).cpu().numpy()
+        for e, o in enumerate(outs):
+            want = orc.generate_matrix(gt.numpy(), o.argmax(1).cpu().numpy())
+            assert np.array_equal(cms[e].sum(0), want)
+
+
+def test_batch_is_per_image():
+    """Batch sharding relies on images being independent: batch-of-3 == three batch-of-1 runs."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec).to(DEV)
+    x, _ = util.make_input(3, 33, 65, seed=4321)
+    outs = [o.clone() for o in net(x.to(DEV))]
+    for i in range(3):
+        single = net(x[i:i + 1].to(DEV))
+        for e in range(len(outs)):
+            assert util.rel_err(single[e][0], outs[e][i]) < 1e-6
+
+
+def test_get_feature_and_dynamic_inference():
+    cname = "searched-dense-C2"
+    spec = util.NET_CASES[cname]
+    net = util.make_net(spec).to(DEV)
+    edm = util.make_edm().to(DEV)
+    for (h, w) in spec["sizes"]:
+        tag = f"{cname}/{h}x{w}"
+        x, _ = util.make_input(1, h, w)
+        xd = x.to(DEV)
+        lg, feat = net.get_feature(xd)
+        assert util.rel_err(lg, torch.from_numpy(NETS[f"{tag}/get_feature/logits"])) < 1e-3
+        assert feat.double().abs().sum().item() == pytest.approx(float(NETS[f"{tag}/get_feature/feature_sum"]), rel=1e-4)
+        c0 = float(NETS[f"{tag}/edm_value"])
+        got = float(edm(feat.contiguous()))
+        assert got == pytest.approx(c0, rel=1e-3, abs=1e-4)
+        for label, thr in (("exit", c0 + 1.0), ("noexit", c0 - 1.0)):
+            y, ee, secs, cv = net.dynamic_inference(xd, threshold=thr, confidence='edm', edm=edm)
+            assert ee == (1 if label == "exit" else 0)
+            assert secs > 0
+            assert float(cv) == pytest.approx(float(NETS[f"{tag}/dynamic_edm/{label}/conf"]), rel=1e-3, abs=1e-4)
+            ref = torch.from_numpy(NETS[f"{tag}/dynamic_edm/{label}/y"])
+            assert util.rel_err(y, ref) < 1e-3
+            assert _agree(y.cpu(), ref) >= 0.999
+
+
+def test_entropy_gate_runs_and_matches_oracle():
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec).to(DEV)
+    x, _ = util.make_input(1, 33, 65)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    arch = util.oracle_arch(spec)
+    with torch.no_grad():
+        y_ref, ee_ref, cv_ref = orc.add_dynamic_inference(sd, arch, x, 0.5, 'entropy')
+    y, ee, _, cv = net.dynamic_inference(x.to(DEV), threshold=0.5, confidence='entropy')
+    assert ee == ee_ref
+    assert cv == pytest.approx(cv_ref, rel=1e-3, abs=1e-4)
+    assert util.rel_err(y, y_ref) < 1e-3

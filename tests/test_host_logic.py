@@ -1,0 +1,70 @@
+"""CPU: host-side logic of the drop-in modules — executed cell DAG, state_dict compatibility,
+BN folding, architecture tables."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+import util
+import add_b200
+from add_b200 import runtime as rt
+from add_b200.ADD import executed_edges
+from util import orc
+
+
+def test_executed_dag_matches_oracle_and_survey_q1():
+    steps = executed_edges(add_b200.AUTODEEPLAB_CELL, 5)
+    want = orc.executed_cell_dag(add_b200.AUTODEEPLAB_CELL, 5)
+    assert [[(j, k) for j, k, _ in s] for s in want] == steps
+    prims = [[add_b200.PRIMITIVES[p] for _, _, p in s] for s in want]
+    # s2 = dil5(s0)+sep3(s1); s3 = sep3(s0)+dil3(s1); s4 = sep3(s0)+sep3(s3);
+    #            s5 = sep5(s2)+sep5(s4); s6 = dil5(s4)+sep5(s5)
+    assert prims == [['dil_conv_5x5', 'sep_conv_3x3'], ['sep_conv_3x3', 'dil_conv_3x3'],
+                     ['sep_conv_3x3', 'sep_conv_3x3'], ['sep_conv_5x5', 'sep_conv_5x5'],
+                     ['dil_conv_5x5', 'sep_conv_5x5']]
+    assert [[j for j, _ in s] for s in steps] == [[0, 1], [0, 1], [0, 3], [2, 4], [4, 5]]
+
+
+def test_state_dict_has_reference_key_count():
+    net = util.make_net(util.NET_CASES["searched-dense-C2"], randomize_bn=False)
+    assert len(net.state_dict()) == 1998          # SURVEY §8b [probed]
+    keys = set(net.state_dict())
+    for k in ("stem0.0.weight", "cells.0.preprocess.conv_1.weight", "cells.3.pre_preprocess.1.op.1.weight",
+              "cells.3.pre_preprocess_1x1.op.2.running_var", "cells.5._ops.9.op.6.weight", "aspp.aspp5_bn.bias",
+              "decoder._conv.7.bias", "low_level_conv.1.weight"):
+        assert k in keys, k
+    edm = util.make_edm()
+    assert set(edm.state_dict()) == {"conv.weight", "edm.0.weight", "edm.0.bias", "edm.2.weight", "edm.2.bias",
+                                     "edm.4.weight", "edm.4.bias"}
+
+
+def test_bn_fold_equals_batch_norm():
+    m, x = util.make_op_case("relu_conv_bn_1x1")
+    cw = rt.ConvWeights(m.op[1].weight, m.op[2])
+    w = cw.w.permute(3, 2, 0, 1).contiguous()     # back to [Cout,Cin,kh,kw]
+    with torch.no_grad():
+        y = F.conv2d(F.relu(x), w, cw.bias)
+        ref = orc.relu_conv_bn({"m." + k: v for k, v in m.state_dict().items()}, "m", x)
+    assert util.rel_err(y, ref) < 1e-5
+
+
+def test_network_tables_match_reference_drivers():
+    assert add_b200.NETWORKS["searched-dense"][2] == ([1, 2, 2, 2, 3, 2, 2, 1, 1, 1, 1, 2], [5], 0)
+    assert add_b200.NETWORKS["autodeeplab-dense"][2][2] == 2
+    a = orc.Arch.searched_dense(3)
+    assert (list(a.network_arch), list(a.C_index)) == tuple(add_b200.NETWORKS["searched-dense"][3][:2])
+    assert np.array_equal(orc.AUTODEEPLAB_GENOTYPE, add_b200.AUTODEEPLAB_CELL)
+
+
+def test_generation_invalidates_on_load():
+    m, _ = util.make_op_case("relu_conv_bn_1x1")
+    g0 = rt.generation()
+    m.load_state_dict(m.state_dict())
+    assert rt.generation() > g0
+
+
+def test_training_mode_is_refused():
+    import pytest
+    m, x = util.make_op_case("dil_conv_3x3_c40")
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(x)

@@ -1,0 +1,109 @@
+"""CPU: the oracle (oracle/add_oracle.py) against the golden fixtures produced by the UNMODIFIED
+reference (tests/golden/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import util
+from util import orc
+
+OPS = np.load(util.ROOT / "tests/golden/ops.npz")
+NETS = np.load(util.ROOT / "tests/golden/nets.npz")
+TOL = 2e-5   # same ATen arithmetic, different op grouping only
+
+
+def _sd(module, prefix="m"):
+    return {f"{prefix}.{k}": v.detach() for k, v in module.state_dict().items()}
+
+
+def _oracle_op(name, m, x):
+    spec = util.OP_CASES[name]
+    sd = _sd(m)
+    kind, args = spec["kind"], spec["args"]
+    if kind == "OPS":
+        return orc.apply_primitive(sd, "m", args[0], x)
+    if kind == "ReLUConvBN":
+        return orc.relu_conv_bn(sd, "m", x, args[3], args[4])
+    if kind == "FactorizedReduce":
+        return orc.factorized_reduce(sd, "m", x, 2)
+    if kind == "DoubleFactorizedReduce":
+        return orc.factorized_reduce(sd, "m", x, 4)
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("name", sorted(util.OP_CASES))
+def test_op_matches_reference(name):
+    m, x = util.make_op_case(name)
+    assert util.weight_checksum(m.state_dict()) == pytest.approx(float(OPS[name + "/wsum"]), rel=1e-12)
+    with torch.no_grad():
+        y = _oracle_op(name, m, x)
+    ref = torch.from_numpy(OPS[name + "/y"])
+    assert y.shape == ref.shape
+    assert util.rel_err(y, ref) < TOL
+
+
+def test_aspp_decoder_edm_match_reference():
+    m, x = util.make_aspp_case()
+    with torch.no_grad():
+        y = orc.aspp_train(_sd(m), "m", x, util.ASPP_CASE["mult"])
+    assert util.rel_err(y, torch.from_numpy(OPS["aspp/y"])) < TOL
+    m, x, low, size = util.make_decoder_case()
+    with torch.no_grad():
+        y = orc.decoder(_sd(m), "m", x, low, size)
+    assert util.rel_err(y, torch.from_numpy(OPS["decoder/y"])) < TOL
+    m, x = util.make_edm_case()
+    with torch.no_grad():
+        y = orc.edm_forward({k: v.detach() for k, v in m.state_dict().items()}, x)
+    assert util.rel_err(y, torch.from_numpy(OPS["edm/y"])) < TOL
+
+
+def test_confidence_scalars_match_reference():
+    lg = util.make_logits_case()
+    assert orc.normalized_shannon_entropy(lg) == pytest.approx(float(OPS["conf/entropy"]), rel=1e-5)
+    assert orc.confidence_max(lg, 0.3) == pytest.approx(float(OPS["conf/max_0.3"]), abs=1e-12)
+    assert orc.confidence_max(lg, 0.6) == pytest.approx(float(OPS["conf/max_0.6"]), abs=1e-12)
+
+
+@pytest.mark.parametrize("cname", sorted(util.make_evaluator_cases()))
+def test_evaluator_bit_exact(cname):
+    gt, pred = util.make_evaluator_cases()[cname]
+    cm = orc.generate_matrix(gt.numpy(), pred.numpy())
+    ref = OPS[f"evaluator/{cname}/cm"]
+    assert cm.dtype == np.int64 and np.array_equal(cm, ref)
+    miou, ref_miou = orc.mean_iou(cm), float(OPS[f"evaluator/{cname}/miou"])
+    assert (np.isnan(miou) and np.isnan(ref_miou)) or miou == pytest.approx(ref_miou, rel=1e-6)
+
+
+@pytest.mark.parametrize("cname", sorted(util.NET_CASES))
+def test_network_matches_reference(cname):
+    spec = util.NET_CASES[cname]
+    net = util.make_net(spec)
+    assert util.weight_checksum(net.state_dict()) == pytest.approx(float(NETS[f"{cname}/wsum"]), rel=1e-12)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    arch = util.oracle_arch(spec)
+    for (h, w) in spec["sizes"]:
+        x, gt = util.make_input(1, h, w)
+        tag = f"{cname}/{h}x{w}"
+        with torch.no_grad():
+            outs = orc.add_forward(sd, arch, x)
+        for e, o in enumerate(outs):
+            ref = torch.from_numpy(NETS[f"{tag}/forward/{e}"])
+            assert o.shape == ref.shape
+            assert util.rel_err(o, ref) < 1e-4
+            pred = torch.argmax(ref, 1)   # identical predictions -> bit-exact matrix
+            assert np.array_equal(orc.generate_matrix(gt.numpy(), pred.numpy()), NETS[f"{tag}/cm/{e}"])
+        if spec.get("dynamic"):
+            with torch.no_grad():
+                lg, feat = orc.add_get_feature(sd, arch, x)
+            assert util.rel_err(lg, torch.from_numpy(NETS[f"{tag}/get_feature/logits"])) < 1e-4
+            assert feat.double().abs().sum().item() == pytest.approx(float(NETS[f"{tag}/get_feature/feature_sum"]), rel=1e-4)
+            edm = util.make_edm()
+            edm_sd = {k: v.detach() for k, v in edm.state_dict().items()}
+            with torch.no_grad():
+                c0 = float(orc.edm_forward(edm_sd, feat))
+            assert c0 == pytest.approx(float(NETS[f"{tag}/edm_value"]), rel=1e-3, abs=1e-4)
+            for label, thr in (("exit", c0 + 1.0), ("noexit", c0 - 1.0)):
+                with torch.no_grad():
+                    y, ee, cv = orc.add_dynamic_inference(sd, arch, x, thr, 'edm', edm_sd)
+                assert ee == (1 if label == "exit" else 0)
+                assert util.rel_err(y, torch.from_numpy(NETS[f"{tag}/dynamic_edm/{label}/y"])) < 1e-4

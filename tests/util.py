@@ -1,0 +1,148 @@
+"""Shared deterministic test cases (CPU-side construction only; no GPU work here).
+
+Every case is rebuilt from fixed seeds by OUR modules' constructors — the same code path
+tests/golden/make_golden.py used when it drove the reference — so no weights are stored."""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import add_b200  # noqa: E402
+from oracle import add_oracle as orc  # noqa: E402
+
+BN = torch.nn.BatchNorm2d
+
+# name -> how to build the module and its input
+OP_CASES = {
+    "sep_conv_3x3_c40": dict(kind="OPS", args=("sep_conv_3x3", 40), x=(2, 40, 13, 17)),
+    "sep_conv_5x5_c40": dict(kind="OPS", args=("sep_conv_5x5", 40), x=(2, 40, 13, 17)),
+    "sep_conv_3x3_c80": dict(kind="OPS", args=("sep_conv_3x3", 80), x=(1, 80, 9, 20)),
+    "sep_conv_5x5_c160": dict(kind="OPS", args=("sep_conv_5x5", 160), x=(1, 160, 6, 7)),
+    "sep_conv_3x3_c20": dict(kind="OPS", args=("sep_conv_3x3", 20), x=(1, 20, 8, 8)),
+    "dil_conv_3x3_c40": dict(kind="OPS", args=("dil_conv_3x3", 40), x=(2, 40, 13, 17)),
+    "dil_conv_5x5_c40": dict(kind="OPS", args=("dil_conv_5x5", 40), x=(2, 40, 13, 17)),
+    "dil_conv_5x5_c80": dict(kind="OPS", args=("dil_conv_5x5", 80), x=(1, 80, 9, 11)),
+    "dil_conv_3x3_c20": dict(kind="OPS", args=("dil_conv_3x3", 20), x=(1, 20, 7, 9)),
+    "relu_conv_bn_1x1": dict(kind="ReLUConvBN", args=(200, 40, 1, 1, 0), x=(2, 200, 9, 10)),
+    "relu_conv_bn_3x3_s2": dict(kind="ReLUConvBN", args=(24, 48, 3, 2, 1), x=(1, 24, 11, 14)),
+    "factorized_reduce_even": dict(kind="FactorizedReduce", args=(128, 40), x=(2, 128, 12, 16)),
+    "factorized_reduce_odd": dict(kind="FactorizedReduce", args=(64, 80), x=(1, 64, 13, 9)),
+    "double_factorized_reduce": dict(kind="DoubleFactorizedReduce", args=(40, 80), x=(1, 40, 14, 19)),
+}
+ASPP_CASE = dict(C=40, out=32, depth=32, mult=0.5, x=(2, 40, 12, 20))
+NET_CASES = {
+    "searched-dense-C2": dict(network="searched-dense", C=2, F=20, sizes=[(33, 65), (48, 80)], dynamic=True),
+    "autodeeplab-dense-C2": dict(network="autodeeplab-dense", C=2, F=20, sizes=[(33, 65)], dynamic=False),
+    "searched-dense-C3": dict(network="searched-dense", C=3, F=20, sizes=[(33, 65)], dynamic=False),
+    "searched-dense-C4": dict(network="searched-dense", C=4, F=20, sizes=[(48, 80)], dynamic=False),
+}
+
+
+def weight_checksum(sd) -> float:
+    return float(sum(v.double().abs().sum().item() for k, v in sorted(sd.items()) if v.dtype.is_floating_point))
+
+
+def _randomized(module, seed):
+    sd = orc.randomize_bn_({k: v.clone() for k, v in module.state_dict().items()}, seed)
+    module.load_state_dict(sd, strict=True)
+    return module.eval()
+
+
+def make_op(name):
+    spec = OP_CASES[name]
+    torch.manual_seed(100 + sorted(OP_CASES).index(name))
+    kind, args = spec["kind"], spec["args"]
+    if kind == "OPS":
+        m = add_b200.OPS[args[0]](args[1], 1, BN, 1e-5, 0.1, True)
+    else:
+        m = getattr(add_b200, kind)(*args, BN)
+    return _randomized(m, 11)
+
+
+def make_op_case(name):
+    m = make_op(name)
+    g = torch.Generator().manual_seed(500 + sorted(OP_CASES).index(name))
+    x = torch.randn(*OP_CASES[name]["x"], generator=g)
+    return m, x
+
+
+def make_aspp_case():
+    torch.manual_seed(201)
+    m = add_b200.ASPP_train(ASPP_CASE["C"], ASPP_CASE["out"], BN, depth=ASPP_CASE["depth"], mult=ASPP_CASE["mult"])
+    m = _randomized(m, 12)
+    x = torch.randn(*ASPP_CASE["x"], generator=torch.Generator().manual_seed(601))
+    return m, x
+
+
+def make_decoder_case():
+    torch.manual_seed(202)
+    m = _randomized(add_b200.Decoder(19, BN), 13)
+    g = torch.Generator().manual_seed(602)
+    x = torch.randn(1, 256, 5, 7, generator=g)
+    low = torch.randn(1, 48, 9, 13, generator=g)
+    return m, x, low, (33, 49)
+
+
+def make_edm():
+    torch.manual_seed(203)
+    return add_b200.EDM().eval()
+
+
+def make_edm_case():
+    m = make_edm()
+    x = torch.randn(2, 400, 9, 12, generator=torch.Generator().manual_seed(603))
+    return m, x
+
+
+def make_logits_case():
+    return torch.randn(1, 19, 21, 33, generator=torch.Generator().manual_seed(604)) * 3.0
+
+
+def make_evaluator_cases():
+    g = torch.Generator().manual_seed(605)
+    cases = {}
+    gt = torch.randint(0, 19, (2, 37, 53), generator=g)
+    gt[torch.rand(2, 37, 53, generator=g) < 0.1] = 255
+    cases["ragged"] = (gt, torch.randint(0, 19, (2, 37, 53), generator=g))
+    cases["all_ignored"] = (torch.full((1, 8, 8), 255, dtype=torch.int64), torch.randint(0, 19, (1, 8, 8), generator=g))
+    cases["single_pixel"] = (torch.tensor([[[3]]]), torch.tensor([[[5]]]))
+    gt = torch.randint(0, 19, (1, 64, 129), generator=g)
+    gt[0, :3] = -1
+    cases["negative_gt"] = (gt, torch.randint(0, 19, (1, 64, 129), generator=g))
+    cases["one_class"] = (torch.full((1, 16, 16), 7, dtype=torch.int64), torch.full((1, 16, 16), 7, dtype=torch.int64))
+    return cases
+
+
+def cell_arch():
+    return add_b200.AUTODEEPLAB_CELL.copy()
+
+
+def net_arch(spec):
+    return add_b200.NETWORKS[spec["network"]][spec["C"]]
+
+
+def make_net(spec, randomize_bn: bool = True):
+    m = add_b200.build_add(spec["network"], spec["C"], spec["F"], seed=1)
+    return _randomized(m, 21) if randomize_bn else m
+
+
+def make_input(n, h, w, seed=1234):
+    return orc.synthetic_batch(n, h, w, seed)
+
+
+def oracle_arch(spec) -> "orc.Arch":
+    na, ci, low = net_arch(spec)
+    return orc.Arch(na, ci, cell_arch(), 19, spec["F"], 5, low)
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max|a-b| / max|b| — the parity metric of BASELINE.json (max-norm relative)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
