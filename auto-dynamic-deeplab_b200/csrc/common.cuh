@@ -53,10 +53,20 @@ static inline bool tensor_vec4_ok(const add_tensor_t* t) {
   return (t->c % 4 == 0) && (t->pix_stride % 4 == 0) && ((uintptr_t)t->ptr % a == 0);
 }
 
+// Output extent `out` is acceptable for a conv over `in` pixels when the last output's window
+// [(out-1)*stride - pad, ... + dil*(k-1)] starts less than one stride past the image (the reference's
+// FactorizedReduce pads one zero row/column on the far side, operations.py:98) and ends at or after 0.
+static inline bool conv_extent_ok(int in, int out, int k, int stride, int pad, int dil) {
+  if (out <= 0) return false;
+  long long first = (long long)(out - 1) * stride - pad;
+  return first < (long long)in + stride && first + (long long)dil * (k - 1) >= 0;
+}
+
 // PyTorch's area_pixel_compute_source_index (align_corners=False, bilinear) in fp32.
 __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1,
                                              float& l0, float& l1) {
-  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  // explicit rn ops: no FMA contraction, so the source index is bit-identical to the CPU reference's
+  float src = __fsub_rn(__fmul_rn(scale, static_cast<float>(dst) + 0.5f), 0.5f);
   src = src < 0.f ? 0.f : src;
   i0 = static_cast<int>(src);
   if (i0 > in_size - 1) i0 = in_size - 1;

@@ -276,9 +276,10 @@ extern "C" int add_conv2d_fwd(const add_tensor_t* x, const add_tensor_t* y, cons
   ADD_CHECK_ARG(tensor_ok(x) && tensor_ok(y) && w);
   ADD_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && dil > 0);
   ADD_CHECK_ARG(x->n == y->n);
-  int ho = (x->h + 2 * pad - dil * (kh - 1) - 1) / stride + 1;
-  int wo = (x->w + 2 * pad - dil * (kw - 1) - 1) / stride + 1;
-  ADD_CHECK_ARG(ho == y->h && wo == y->w);
+  // `pad` is the top/left padding (may be negative); the output extent is the caller's: taps that
+  // fall outside the image read zero, so bottom/right padding is implicit.  Only require that the
+  // last output's tap window still touches the image.
+  ADD_CHECK_ARG(conv_extent_ok(x->h, y->h, kh, stride, pad, dil) && conv_extent_ok(x->w, y->w, kw, stride, pad, dil));
   // 4-channel vector loads on the input side
   ADD_CHECK_SUP(tensor_vec4_ok(x));
   ADD_CHECK_SUP((long long)y->n * y->h * y->w < (1ll << 31));
