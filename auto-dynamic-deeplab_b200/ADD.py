@@ -255,8 +255,8 @@ class ADD(AddModule):
         """Emit stems (if first == 0) and cells first..last inclusive, updating the trunk state `st`
         (mirrors ADD.py:283-308)."""
         self._ensure_prepared()
-        n, _, H, W = x_nchw.shape
         if first == 0:
+            n, _, H, W = x_nchw.shape
             img = b.alloc(n, H, W, 4)
             b.nchw_to_nhwc(x_nchw, 3, img, "ADD.input")
             h1, w1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
@@ -366,12 +366,26 @@ class ADD(AddModule):
         toc = time.perf_counter()
         return ys[0], int(exits[0]), toc - tic, confs[0]
 
-    def dynamic_inference_batch(self, x: torch.Tensor, threshold=1.0, confidence='edm', edm=False):
+    def dynamic_inference_batch(self, x: torch.Tensor, threshold=1.0, confidence='edm', edm=False,
+                                exit_mode: str = "reference"):
         """Per-image early-exit gating for a batch: each image follows exactly the reference's
-        batch-1 control flow.  Returns (list of [1,nc,H,W] logits, list of exit flags, list of
-        confidence values)."""
+        batch-1 control flow; with the EDM gate, exited images are compacted out of the batch so they
+        stop consuming later layers.  Returns (list of [1,nc,H,W] logits, list of exit flags, list
+        of confidence values).  exit_mode='forward' is a labelled deviation (see dynamic.py)."""
         from .dynamic import run_dynamic
-        return run_dynamic(self, x, threshold, confidence, edm)
+        self._check_eval()
+        rt.require_cuda(x)
+        return run_dynamic(self, x, threshold, confidence, edm, exit_mode)
+
+    def dynamic_evaluate(self, x: torch.Tensor, target: torch.Tensor, threshold=1.0, edm=False,
+                         exit_mode: str = "reference"):
+        """eval.py:195-221 fused for a batch: EDM-gated early exit → argmax → per-image int64
+        confusion matrix [N,nc,nc] (no full-resolution logits are materialised).
+        Returns (cm, exit flags, confidence values)."""
+        from .dynamic import run_dynamic_evaluate
+        self._check_eval()
+        rt.require_cuda(x)
+        return run_dynamic_evaluate(self, x, target, threshold, edm, exit_mode)
 
 
 class _NetPlan:

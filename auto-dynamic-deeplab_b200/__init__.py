@@ -15,6 +15,6 @@ from .aspp_train import ASPP_train
 from .decoder import Decoder
 from .ADD import ADD, Cell, EDM
 from .metrics import Evaluator
-from .factory import build_add, Args
+from .factory import build_add, Args, synthetic_batch
 
 __version__ = "0.1.0"

@@ -65,8 +65,9 @@ static inline bool conv_extent_ok(int in, int out, int k, int stride, int pad, i
 // PyTorch's area_pixel_compute_source_index (align_corners=False, bilinear) in fp32.
 __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1,
                                              float& l0, float& l1) {
-  // explicit rn ops: no FMA contraction, so the source index is bit-identical to the CPU reference's
-  float src = __fsub_rn(__fmul_rn(scale, static_cast<float>(dst) + 0.5f), 0.5f);
+  // one fused multiply-add, like the reference's own builds: ATen's CPU kernels are compiled with FP
+  // contraction on (and nvcc contracts the CUDA ones), so `scale*(dst+0.5)-0.5` is a single FMA there.
+  float src = fmaf(scale, static_cast<float>(dst) + 0.5f, -0.5f);
   src = src < 0.f ? 0.f : src;
   i0 = static_cast<int>(src);
   if (i0 > in_size - 1) i0 = in_size - 1;

@@ -185,3 +185,38 @@ extern "C" int add_edm_mlp_fwd(const float* pooled, int n, const float* w0, cons
   edm_mlp_kernel<<<n, 128, 0, static_cast<cudaStream_t>(stream)>>>(pooled, w0, b0, w1, b1, w2, b2, out);
   ADD_RETURN_LAUNCH();
 }
+
+// ---- image gather: dst[j] = src[idx[j]] for whole per-image slabs (early-exit batch compaction) ----
+namespace {
+template <typename V>
+__global__ void __launch_bounds__(256)
+gather_images_kernel(const V* __restrict__ src, V* __restrict__ dst, const int* __restrict__ idx,
+                     long long vec_per_image) {
+  const int j = blockIdx.y;
+  const V* s = src + (size_t)idx[j] * vec_per_image;
+  V* d = dst + (size_t)j * vec_per_image;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < vec_per_image; i += (long long)gridDim.x * 256)
+    d[i] = __ldg(s + i);
+}
+template <typename V>
+void launch_gather(const void* src, void* dst, const int32_t* idx, int count, int64_t bytes, cudaStream_t s) {
+  long long vec = bytes / (long long)sizeof(V);
+  long long bx = (vec + 255) / 256;
+  if (bx > 148 * 4) bx = 148 * 4;
+  dim3 grid((unsigned)bx, (unsigned)count);
+  gather_images_kernel<V><<<grid, 256, 0, s>>>((const V*)src, (V*)dst, idx, vec);
+}
+}  // namespace
+
+extern "C" int add_gather_images(const void* src, void* dst, const int32_t* idx_dev, int count,
+                                 int64_t bytes_per_image, void* stream) {
+  ADD_CHECK_ARG(src && dst && idx_dev && count > 0 && bytes_per_image > 0);
+  ADD_CHECK_SUP(count < 65536);
+  uintptr_t a = (uintptr_t)src | (uintptr_t)dst | (uintptr_t)bytes_per_image;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a % 16 == 0) launch_gather<uint4>(src, dst, idx_dev, count, bytes_per_image, s);
+  else if (a % 8 == 0) launch_gather<uint2>(src, dst, idx_dev, count, bytes_per_image, s);
+  else if (a % 4 == 0) launch_gather<uint32_t>(src, dst, idx_dev, count, bytes_per_image, s);
+  else return ADD_ERR_UNSUPPORTED;
+  ADD_RETURN_LAUNCH();
+}

@@ -1,15 +1,21 @@
 """Early-exit inference (reference ADD.py:379-488) as segmented launch plans.
 
-The reference decides per image on the host (`if confidence_value > threshold`, a device sync).
-Here the network is recorded once per input shape as segments — trunk up to each exit (+ the EDM
-gate), one early-exit head per exit, the final head — and the host replays only the segments the
-gate selects.  Quirks reproduced (SURVEY Q3–Q5): the early exit uses the 2^-L `aspp_size` (the
-feature is bilinearly up-sampled ×4 before ASPP), EDM's in-place ReLU is visible to the exit's
-resize and to later cells, the last exit never resizes, EDM exits when value <= threshold.
+The reference decides per image on the host (`if confidence_value > threshold`, a device sync) and
+is batch-1 only.  Here the network is recorded as *segments* — trunk up to each exit (+ the EDM
+gate), one early-exit head per exit, the final trunk + head — and the host replays only what the
+gate selects.  For the EDM gate a whole batch is gated per image: after each gate the exiting
+images are gathered into an early-exit head plan, the continuing images are compacted (whole-image
+slab gather, `add_gather_images`) into the next segment's plan, so exited images stop consuming
+later layers.  Plans are keyed by (segment, image count) and built lazily.
+
+Quirks reproduced (SURVEY Q3–Q5): the early exit uses the 2^-L `aspp_size` (the feature is
+bilinearly up-sampled ×4 before ASPP), EDM's in-place ReLU is visible to the exit's resize and to
+later cells, the last exit never resizes, EDM exits when value <= threshold.  `exit_mode='forward'`
+is a labelled DEVIATION that sizes the early exit like `ADD.forward` does (2^-(L+2)).
 """
 from __future__ import annotations
 
-from typing import Dict, List
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -18,8 +24,250 @@ from .runtime import Builder, Plan, View, RELU_IN
 from .operations import _confidence
 
 
-class _DynPlan:
-    def __init__(self, net, shape, device, precision: str, confidence: str, edm):
+# ------------------------------------------------------------------------------------------------
+# trunk state transfer between plans
+# ------------------------------------------------------------------------------------------------
+
+def _state_items(st: dict) -> List[Tuple[str, View]]:
+    """Deterministic list of the trunk-state tensors later cells / heads read (ADD.py:388-412)."""
+    items = [(f"two{i}", v) for i, v in enumerate(st["two"]) if v is not None]
+    items += [(f"dense{i}", v) for i, v in enumerate(st["dense"])]
+    if st.get("cur") is not None:
+        items.append(("cur", st["cur"]))
+    if st.get("low_cat") is not None:
+        items.append(("low_cat", st["low_cat"]))
+    return items
+
+
+def _alloc_state_like(b: Builder, st: dict, m: int, need_two: bool) -> dict:
+    """Fresh buffers for `m` images mirroring state `st`; aliasing between entries is preserved.
+    `two_last_inputs` is only carried while cells < 3 remain (ADD.py:395-400)."""
+    made: Dict[int, View] = {}
+
+    def like(v: View) -> View:
+        key = id(v.buf)
+        if key not in made:
+            made[key] = View(b.raw((m,) + tuple(v.buf.shape[1:]), v.buf.dtype))
+        return View(made[key].buf, v.c_off, v.c)
+
+    new = dict(two=[like(v) if need_two else None for v in st["two"]], dense=[like(v) for v in st["dense"]],
+               cur=like(st["cur"]) if st.get("cur") is not None else None,
+               low_cat=like(st["low_cat"]) if st.get("low_cat") is not None else None, size=st["size"])
+    return new
+
+
+def _emit_state_gather(b: Builder, src: dict, dst: dict, idx: torch.Tensor) -> None:
+    done = set()
+    for (name, s), (_, d) in zip(_state_items(src), _state_items(dst)):
+        if id(d.buf) in done:
+            continue
+        done.add(id(d.buf))
+        b.gather_images(s.buf, d.buf, idx, "dynamic.gather." + name)
+
+
+class _Segment:
+    """Trunk cells (after exit k-1) .. exit k, plus the EDM gate when exit k is not the last layer.
+    For the last segment the final head is part of the plan."""
+
+    def __init__(self, runner: "_EdmRunner", k: int, m: int, prev: Optional["_Segment"]):
+        net = runner.net
+        self.k, self.m = k, m
+        b = Builder(runner.device, runner.dtype, record=True)
+        self.builder = b
+        H, W = runner.H, runner.W
+        first = 0 if k == 0 else runner.exits[k - 1] + 1
+        is_last = k == len(runner.exits)
+        last = net.num_net - 1 if is_last else runner.exits[k]
+        self.idx = b.raw((m,), torch.int32, zero=True)   # valid ids even before the host fills them
+        self.gather: Optional[Plan] = None
+        if k == 0:
+            self.x_static = b.raw((m, 3, H, W), torch.float32)
+            st: dict = {}
+        else:
+            st = _alloc_state_like(b, prev.state, m, need_two=first <= 2)
+            start = len(b.launches)
+            src = dict(prev.state)
+            if first > 2:
+                src["two"] = [None, None]
+            _emit_state_gather(b, src, st, self.idx)
+            self.gather_range = (start, len(b.launches))
+        start = len(b.launches)
+        net._emit_trunk(b, self.x_static if k == 0 else None, first, last, st)
+        y = net._feature(st, last)
+        self.conf = None
+        self.out = None
+        if not is_last:
+            self.conf = runner.edm.emit_edm(b, y)
+            # EDM.forward's in-place ReLU (ADD.py:516-519) mutates the feature every later reader sees (Q4)
+            yr = b.alloc(y.n, y.h, y.w, y.c)
+            b.bilinear(y, yr, RELU_IN, "EDM.inplace_relu")
+            if last > 2:
+                st["cur"] = yr
+            else:
+                st["two"][1] = yr
+                if last == 2:
+                    st["cur"] = yr     # x aliases two_last_inputs[1] at i == 2 (ADD.py:399-400)
+        else:
+            # last exit: never resized in the EDM path (ADD.py:433-435)
+            logits = net._emit_exit_lowres(b, y, st, last, runner.aspp_size, 0, resize=False)
+            self.out = runner.emit_head_output(b, logits, m, self)
+        self.state = st
+        self.main = Plan(b, start, len(b.launches))
+        if k > 0:
+            self.gather = Plan(b, *self.gather_range)
+        if net.use_cuda_graph:
+            self.main.capture()
+            if self.gather is not None:
+                self.gather.capture()
+
+    @property
+    def n_launches(self) -> int:
+        return self.main.n_launches + (self.gather.n_launches if self.gather is not None else 0)
+
+
+class _Head:
+    """Early-exit head k for `m` gathered images: [resize →] [conv_aspp →] ASPP → decoder → output."""
+
+    def __init__(self, runner: "_EdmRunner", k: int, m: int, seg: _Segment):
+        net = runner.net
+        b = Builder(runner.device, runner.dtype, record=True)
+        self.builder = b
+        self.idx = b.raw((m,), torch.int32, zero=True)   # valid ids even before the host fills them
+        i = runner.exits[k]
+        y_src = net._feature(seg.state, i)
+        y = View(b.raw((m,) + tuple(y_src.buf.shape[1:]), y_src.buf.dtype))
+        low_src = seg.state["low_cat"]
+        low = View(b.raw((m,) + tuple(low_src.buf.shape[1:]), low_src.buf.dtype))
+        b.gather_images(y_src.buf, y.buf, self.idx, "dynamic.gather.exit_feature")
+        b.gather_images(low_src.buf, low.buf, self.idx, "dynamic.gather.low_cat")
+        # conv_aspp_iter == k: every earlier exit was skipped (ADD.py:422)
+        logits = net._emit_exit_lowres(b, y, dict(low_cat=low), i, runner.early_aspp_size, k, True, True)
+        self.out = runner.emit_head_output(b, logits, m, self)
+        self.main = Plan(b)
+        if net.use_cuda_graph:
+            self.main.capture()
+
+    @property
+    def n_launches(self) -> int:
+        return self.main.n_launches
+
+
+class _EdmRunner:
+    """Batched, per-image EDM-gated inference for one (input shape, precision, output mode)."""
+
+    def __init__(self, net, shape, device, precision: str, edm, mode: str, exit_mode: str):
+        self.generation = rt.generation()
+        self.net, self.edm, self.mode = net, edm, mode
+        self.device, self.dtype = device, rt.act_dtype(precision)
+        self.n, _, self.H, self.W = shape
+        self.nc = net._num_classes
+        self.aspp_size = net._aspp_size((self.H, self.W), net.network_arch[-1])          # ADD.py:383-384
+        if exit_mode == "reference":
+            self.early_aspp_size = self.aspp_size
+        elif exit_mode == "forward":     # DEVIATION: size the early exit like ADD.forward (ADD.py:279-280)
+            self.early_aspp_size = net._aspp_size((self.H, self.W), net.network_arch[-1] + 2)
+        else:
+            raise ValueError(exit_mode)
+        self.exits = [i for i in range(net.num_net) if i in net.C_index and i != net.num_net - 1]
+        self.segments: Dict[Tuple[int, int], _Segment] = {}
+        self.heads: Dict[Tuple[int, int], _Head] = {}
+        self.gt_full: Optional[torch.Tensor] = None
+        if mode == "evaluate":
+            self.gt_full = torch.empty((self.n, self.H, self.W), dtype=torch.int64, device=device)
+        self.last_launches = 0
+
+    # ---- per-plan output tail -------------------------------------------------------------------
+    def emit_head_output(self, b: Builder, logits: View, m: int, owner) -> torch.Tensor:
+        if self.mode == "logits":
+            out = b.raw((m, self.nc, self.H, self.W), torch.float32)
+            b.upsample_logits(logits, out, self.H, self.W, "ADD.upsample_logits")
+            return out
+        gt = b.raw((m, self.H, self.W), torch.int64)
+        owner.idx_gt = b.raw((m,), torch.int32, zero=True)          # ORIGINAL image ids of this plan's rows
+        b.gather_images(self.gt_full, gt, owner.idx_gt, "dynamic.gather.gt")
+        cm = b.raw((m, self.nc, self.nc), torch.int64)
+        b.upsample_argmax(logits, self.H, self.W, gt, None, cm, None, "ADD.upsample_argmax_cm")
+        return cm
+
+    def segment(self, k: int, m: int, prev: Optional[_Segment]) -> _Segment:
+        key = (k, m, prev.m if prev is not None else 0)
+        if key not in self.segments:
+            self.segments[key] = _Segment(self, k, m, prev)
+        return self.segments[key]
+
+    def head(self, k: int, m: int, seg: _Segment) -> _Head:
+        key = (k, m, seg.m)
+        if key not in self.heads:
+            self.heads[key] = _Head(self, k, m, seg)
+        return self.heads[key]
+
+    # ---- one batch ------------------------------------------------------------------------------
+    def run(self, x: torch.Tensor, threshold: float, target: Optional[torch.Tensor] = None):
+        """Returns (outputs per image, exit flag per image, confidence per image).  outputs[j] is a
+        [1,nc,H,W] fp32 logits tensor ('logits') or an int64 [nc,nc] confusion matrix ('evaluate');
+        they alias plan buffers that the next call overwrites."""
+        n = self.n
+        outs: List[Optional[torch.Tensor]] = [None] * n
+        flags = [0] * n
+        confs: List[Optional[torch.Tensor]] = [None] * n
+        launches = 0
+        if self.mode == "evaluate":
+            self.gt_full.copy_(target, non_blocking=True)
+        active = list(range(n))
+        seg = self.segment(0, n, None)
+        seg.x_static.copy_(x, non_blocking=True)
+        for k in range(len(self.exits) + 1):
+            if k > 0:
+                seg.gather.run()
+            if k == len(self.exits) and self.mode == "evaluate":
+                seg.idx_gt.copy_(torch.tensor(active, dtype=torch.int32), non_blocking=True)
+            seg.main.run()
+            launches += seg.n_launches
+            if k == len(self.exits):
+                for j, img in enumerate(active):
+                    outs[img] = seg.out[j:j + 1] if self.mode == "logits" else seg.out[j]
+                break
+            conf = seg.conf.cpu()                      # host decision = the reference's implicit sync (ADD.py:421)
+            ex = [j for j in range(len(active)) if not (float(conf[j]) > threshold)]
+            co = [j for j in range(len(active)) if float(conf[j]) > threshold]
+            for j, img in enumerate(active):
+                confs[img] = conf[j].view(1, 1)
+            if ex:
+                head = self.head(k, len(ex), seg)
+                head.idx.copy_(torch.tensor(ex, dtype=torch.int32), non_blocking=True)
+                if self.mode == "evaluate":
+                    head.idx_gt.copy_(torch.tensor([active[j] for j in ex], dtype=torch.int32), non_blocking=True)
+                head.main.run()
+                launches += head.n_launches
+                for jj, j in enumerate(ex):
+                    outs[active[j]] = head.out[jj:jj + 1] if self.mode == "logits" else head.out[jj]
+                    flags[active[j]] = 1
+            if not co:
+                break
+            nxt = self.segment(k + 1, len(co), seg)
+            nxt.idx.copy_(torch.tensor(co, dtype=torch.int32), non_blocking=True)
+            active = [active[j] for j in co]
+            seg = nxt
+        self.last_launches = launches
+        return outs, flags, confs
+
+
+def _get_runner(net, x: torch.Tensor, edm, mode: str, exit_mode: str) -> _EdmRunner:
+    prec = net.precision or rt.default_precision()
+    key = ("edm", tuple(x.shape), str(x.device), prec, id(edm), mode, exit_mode, bool(net.use_cuda_graph))
+    r = net._plans.get(key)
+    if r is None or r.generation != rt.generation():
+        r = _EdmRunner(net, tuple(x.shape), x.device, prec, edm, mode, exit_mode)
+        net._plans[key] = r
+    return r
+
+
+# ------------------------------------------------------------------------------------------------
+# entropy / max gates: the exit head is evaluated first, then scored (ADD.py:440-488) — batch 1
+# ------------------------------------------------------------------------------------------------
+
+class _ScorePlan:
+    def __init__(self, net, shape, device, precision: str):
         self.generation = rt.generation()
         n, _, H, W = shape
         assert n == 1
@@ -27,119 +275,86 @@ class _DynPlan:
         b = Builder(device, rt.act_dtype(precision), record=True)
         self.builder = b
         self.x_static = b.raw(shape, torch.float32)
-        aspp_size = net._aspp_size((H, W), net.network_arch[-1])          # ADD.py:383-384
+        aspp_size = net._aspp_size((H, W), net.network_arch[-1])          # ADD.py:442-443
         st: dict = {}
-        self.trunks: List[Plan] = []
-        self.heads: List[Plan] = []
-        self.conf: List[torch.Tensor] = []
+        self.stages: List[Plan] = []
         self.outs: List[torch.Tensor] = []
-        exits = [i for i in range(net.num_net) if i in net.C_index and i != net.num_net - 1]
-        self.exits = exits
+        exits = [i for i in range(net.num_net) if i in net.C_index or i == net.num_net - 1]
         done = -1
         for k, i in enumerate(exits):
             start = len(b.launches)
             net._emit_trunk(b, self.x_static, done + 1, i, st)
             done = i
             y = net._feature(st, i)
-            relu_feature = False
-            if confidence == 'edm':
-                self.conf.append(edm.emit_edm(b, y))
-                # EDM.forward's in-place ReLU (ADD.py:516-519) mutates the feature every later reader sees
-                yr = b.alloc(y.n, y.h, y.w, y.c)
-                b.bilinear(y, yr, RELU_IN, "EDM.inplace_relu")
-                if i > 2:
-                    st["cur"] = yr
-                else:
-                    st["two"][1] = yr
-                y = yr
-                relu_feature = True
-            self.trunks.append(Plan(b, start, len(b.launches)))
-            # early-exit head k (conv_aspp_iter == k: every earlier exit was skipped, ADD.py:422)
-            start = len(b.launches)
-            if confidence != 'edm' and not (y.h < aspp_size[0] or y.w < aspp_size[1]):
+            if not (y.h < aspp_size[0] or y.w < aspp_size[1]):
                 raise NotImplementedError("non-EDM gate with a feature not smaller than aspp_size: the reference "
                                           "skips the head and scores the raw feature map (ADD.py:465-476)")
-            logits = net._emit_exit_lowres(b, y, st, i, aspp_size, k, True, relu_feature)
+            logits = net._emit_exit_lowres(b, y, st, i, aspp_size, k, True, False)
             out = b.raw((1, nc, H, W), torch.float32)
             b.upsample_logits(logits, out, H, W, "ADD.upsample_logits")
             self.outs.append(out)
-            self.heads.append(Plan(b, start, len(b.launches)))
-        # remaining cells + last exit (never resized in the EDM path: ADD.py:433-435)
-        start = len(b.launches)
-        last = net.num_net - 1
-        net._emit_trunk(b, self.x_static, done + 1, last, st)
-        y = net._feature(st, last)
-        logits = net._emit_exit_lowres(b, y, st, last, aspp_size, 0, resize=(confidence != 'edm'))
-        out = b.raw((1, nc, H, W), torch.float32)
-        b.upsample_logits(logits, out, H, W, "ADD.upsample_logits")
-        self.outs.append(out)
-        self.tail = Plan(b, start, len(b.launches))
+            self.stages.append(Plan(b, start, len(b.launches)))
         if net.use_cuda_graph:
-            for p in self.trunks + self.heads + [self.tail]:
+            for p in self.stages:
                 p.capture()
 
-    @property
-    def n_launches(self):
-        return len(self.builder.launches)
 
-
-def _get_dyn_plan(net, x1: torch.Tensor, confidence: str, edm) -> _DynPlan:
+def _run_scored(net, x: torch.Tensor, threshold, confidence):
     prec = net.precision or rt.default_precision()
-    key = ("dynamic", tuple(x1.shape), str(x1.device), prec, confidence, id(edm), bool(net.use_cuda_graph))
-    p = net._plans.get(key)
-    if p is None or p.generation != rt.generation():
-        p = _DynPlan(net, tuple(x1.shape), x1.device, prec, confidence, edm)
-        net._plans[key] = p
-    return p
-
-
-def run_dynamic(net, x: torch.Tensor, threshold, confidence, edm):
-    if confidence not in ('edm', 'entropy', 'max'):
-        raise ValueError(confidence)
-    if confidence == 'edm' and (edm is False or edm is None):
-        raise ValueError("confidence='edm' needs an EDM module (eval.py:110-112)")
-    ys, flags, confs = [], [], []
-    launches = 0
+    ys, flags, confs, launches = [], [], [], 0
     for n in range(x.shape[0]):
         x1 = x[n:n + 1]
-        plan = _get_dyn_plan(net, x1, confidence, edm)
+        key = ("scored", tuple(x1.shape), str(x1.device), prec, bool(net.use_cuda_graph))
+        plan = net._plans.get(key)
+        if plan is None or plan.generation != rt.generation():
+            plan = _ScorePlan(net, tuple(x1.shape), x1.device, prec)
+            net._plans[key] = plan
         plan.x_static.copy_(x1)
-        taken = None
-        conf_val = None
-        for k, _ in enumerate(plan.exits):
-            plan.trunks[k].run()
-            launches += plan.trunks[k].n_launches
-            if confidence == 'edm':
-                conf_t = plan.conf[k]
-                conf_val = conf_t.view(1, 1).clone()
-                if float(conf_t.item()) > threshold:      # host decision = the reference's implicit sync
-                    continue
-                plan.heads[k].run()
-                launches += plan.heads[k].n_launches
+        conf_val, taken = None, len(plan.stages) - 1
+        for k, stage in enumerate(plan.stages):
+            stage.run()
+            launches += stage.n_launches
+            if k == len(plan.stages) - 1:
+                break
+            s = _confidence(plan.outs[k], threshold if confidence == 'max' else 2.0, net._num_classes)
+            if confidence == 'entropy':
+                conf_val = s[0].item()
+                hit = conf_val < threshold
+            else:
+                conf_val = s[1].item()
+                hit = conf_val > threshold
+            if hit:
                 taken = k
                 break
-            else:
-                plan.heads[k].run()
-                launches += plan.heads[k].n_launches
-                s = _confidence(plan.outs[k], threshold if confidence == 'max' else 2.0, net._num_classes)
-                if confidence == 'entropy':
-                    conf_val = s[0].item()
-                    if conf_val < threshold:
-                        taken = k
-                        break
-                else:
-                    conf_val = s[1].item()
-                    if conf_val > threshold:
-                        taken = k
-                        break
-        if taken is None:
-            plan.tail.run()
-            launches += plan.tail.n_launches
-            ys.append(plan.outs[-1].clone() if x.shape[0] > 1 else plan.outs[-1])
-            flags.append(0)
-        else:
-            ys.append(plan.outs[taken].clone() if x.shape[0] > 1 else plan.outs[taken])
-            flags.append(1)
+        out = plan.outs[taken]
+        ys.append(out.clone() if x.shape[0] > 1 else out)
+        flags.append(0 if taken == len(plan.stages) - 1 else 1)
         confs.append(conf_val)
     net.last_dynamic_launches = launches
     return ys, flags, confs
+
+
+# ------------------------------------------------------------------------------------------------
+# entry points used by ADD
+# ------------------------------------------------------------------------------------------------
+
+def run_dynamic(net, x: torch.Tensor, threshold, confidence, edm, exit_mode: str = "reference"):
+    if confidence not in ('edm', 'entropy', 'max'):
+        raise ValueError(confidence)
+    if confidence != 'edm':
+        return _run_scored(net, x, threshold, confidence)
+    if edm is False or edm is None:
+        raise ValueError("confidence='edm' needs an EDM module (eval.py:110-112)")
+    r = _get_runner(net, x, edm, "logits", exit_mode)
+    outs, flags, confs = r.run(x, float(threshold))
+    net.last_dynamic_launches = r.last_launches
+    return outs, flags, confs
+
+
+def run_dynamic_evaluate(net, x: torch.Tensor, target: torch.Tensor, threshold, edm, exit_mode: str = "reference"):
+    """eval.py:195-221 for a batch, fused: per-image EDM gate → exit head → argmax → int64 confusion
+    matrix, without materialising full-resolution logits.  Returns (cm int64 [N,nc,nc], flags, confs)."""
+    r = _get_runner(net, x, edm, "evaluate", exit_mode)
+    outs, flags, confs = r.run(x, float(threshold), target)
+    net.last_dynamic_launches = r.last_launches
+    return torch.stack(outs), flags, confs

@@ -23,3 +23,15 @@ def build_add(network: str = 'searched-dense', C: int = 2, F: int = 20, B: int =
         torch.manual_seed(seed)
     model = ADD(na, ci, AUTODEEPLAB_CELL.copy(), num_classes, Args(F, B), low)
     return model.eval()
+
+
+def synthetic_batch(n: int, h: int, w: int, seed: int = 1234, num_class: int = 19, pin: bool = False):
+    """SURVEY §8d synthetic Cityscapes-shaped batch on the HOST: image ~ N(0,1) fp32 NCHW (normalised
+    Cityscapes images are ≈N(0,1), cityscapes.py:53-54); labels randint(0,19) int64 with 10 % = 255."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 3, h, w, generator=g)
+    gt = torch.randint(0, num_class, (n, h, w), generator=g, dtype=torch.int64)
+    gt[torch.rand(n, h, w, generator=g) < 0.1] = 255
+    if pin:
+        x, gt = x.pin_memory(), gt.pin_memory()
+    return x, gt

@@ -161,7 +161,7 @@ class Builder:
         self.device = device
         self.dtype = dtype
         self.record = record
-        self.launches: List[Tuple[Callable, tuple, str]] = []
+        self.launches: List[Tuple[Callable, tuple, str, dict]] = []
         self.keep: List[object] = []
         self._pool: Dict[tuple, List[torch.Tensor]] = {}
         self.bytes_allocated = 0
@@ -184,16 +184,18 @@ class Builder:
         b = v.buf
         self._pool.setdefault((b.shape[0], b.shape[1], b.shape[2], b.shape[3], b.dtype), []).append(b)
 
-    def raw(self, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
-        t = torch.empty(tuple(shape), device=self.device, dtype=dtype)
+    def raw(self, shape: Sequence[int], dtype: torch.dtype, zero: bool = False) -> torch.Tensor:
+        t = (torch.zeros if zero else torch.empty)(tuple(shape), device=self.device, dtype=dtype)
         self.bytes_allocated += t.numel() * t.element_size()
         self.keep.append(t)
         return t
 
     # ---- launch plumbing ------------------------------------------------------------------
-    def _emit(self, fn, args: tuple, tag: str) -> None:
+    def _emit(self, fn, args: tuple, tag: str, meta: Optional[dict] = None) -> None:
+        """meta = {"kernel": name, "flops": algorithmic FLOPs, "bytes": algorithmic HBM bytes} of this
+        launch (SURVEY §8d formulas) — what bench.py's roofline is computed from."""
         if self.record:
-            self.launches.append((fn, args, tag))
+            self.launches.append((fn, args, tag, meta or {"kernel": tag, "flops": 0, "bytes": 0}))
         else:
             s = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             check(fn(*args, s), tag)
@@ -209,43 +211,70 @@ class Builder:
         assert x.c == cw.cin and y.c == cw.cout, (x.c, cw.cin, y.c, cw.cout, tag)
         self.keep.append(cw)
         use_tc = (x.dtype == torch.bfloat16 and tc_available())
+        p_out = y.n * y.h * y.w
+        # strided 1x1 convs only touch the sampled lattice (SURVEY §8d FactorizedReduce row)
+        p_in = p_out if (cw.kh == 1 and cw.kw == 1) else x.n * x.h * x.w
+        ex, ey = x.buf.element_size(), y.buf.element_size()
+        meta = dict(flops=2 * p_out * cw.cin * cw.cout * cw.kh * cw.kw,
+                    bytes=p_in * cw.cin * ex + p_out * cw.cout * ey * (2 if flags & ACCUMULATE else 1)
+                    + cw.cin * cw.cout * cw.kh * cw.kw * (2 if use_tc else 4))
         if use_tc:
             self._emit(lib.add_conv2d_tc_fwd,
                        (self._d(x), self._d(y), cw.packed_tc().data_ptr(), _ptr(cw.bias), cw.kh, cw.kw,
-                        stride, pad, dil, flags), tag + ":tc")
+                        stride, pad, dil, flags), tag + ":tc", dict(kernel="conv2d_tc", **meta))
         else:
             self._emit(lib.add_conv2d_fwd,
                        (self._d(x), self._d(y), cw.w.data_ptr(), _ptr(cw.bias), cw.kh, cw.kw,
-                        stride, pad, dil, flags), tag)
+                        stride, pad, dil, flags), tag, dict(kernel="conv2d_ffma", **meta))
 
     def sepconv_half(self, x: View, y: View, w_dw: torch.Tensor, pw: ConvWeights, k: int, flags: int,
                      tag: str = "sephalf") -> None:
         self.keep.extend((w_dw, pw))
+        p = x.n * x.h * x.w
+        ex = x.buf.element_size()
+        meta = dict(kernel="sepconv_half", flops=2 * p * (x.c * k * k + x.c * y.c),
+                    bytes=p * x.c * ex + p * y.c * ex * (2 if flags & ACCUMULATE else 1) + 4 * (x.c * k * k + x.c * y.c))
         self._emit(lib.add_sepconv_half_fwd,
-                   (self._d(x), self._d(y), w_dw.data_ptr(), pw.w.data_ptr(), _ptr(pw.bias), k, flags), tag)
+                   (self._d(x), self._d(y), w_dw.data_ptr(), pw.w.data_ptr(), _ptr(pw.bias), k, flags), tag, meta)
 
     def bilinear(self, x: View, y: View, flags: int = 0, tag: str = "bilinear") -> None:
-        self._emit(lib.add_bilinear_fwd, (self._d(x), self._d(y), flags), tag)
+        meta = dict(kernel="bilinear", flops=8 * y.n * y.h * y.w * y.c,
+                    bytes=(x.n * x.h * x.w * x.buf.element_size() + y.n * y.h * y.w * y.buf.element_size()) * x.c)
+        self._emit(lib.add_bilinear_fwd, (self._d(x), self._d(y), flags), tag, meta)
+
+    def gather_images(self, src: torch.Tensor, dst: torch.Tensor, idx: torch.Tensor, tag: str = "gather_images") -> None:
+        """dst[j] = src[idx[j]] over whole per-image slabs (dim 0 = image)."""
+        assert src.shape[1:] == dst.shape[1:] and src.dtype == dst.dtype and idx.dtype == torch.int32
+        per = src[0].numel() * src.element_size()
+        self.keep.extend((src, dst, idx))
+        self._emit(lib.add_gather_images, (src.data_ptr(), dst.data_ptr(), idx.data_ptr(), dst.shape[0], per), tag,
+                   dict(kernel="gather_images", flops=0, bytes=2 * per * dst.shape[0]))
 
     def gap(self, x: View, out: torch.Tensor, flags: int = 0, tag: str = "gap") -> None:
-        self._emit(lib.add_global_avgpool_fwd, (self._d(x), out.data_ptr(), flags), tag)
+        self._emit(lib.add_global_avgpool_fwd, (self._d(x), out.data_ptr(), flags), tag,
+                   dict(kernel="global_avgpool", flops=x.n * x.h * x.w * x.c, bytes=x.n * x.h * x.w * x.c * x.buf.element_size()))
 
     def nchw_to_nhwc(self, src: torch.Tensor, c_src: int, y: View, tag: str = "nchw2nhwc") -> None:
         self.keep.append(src)
-        self._emit(lib.add_nchw_to_nhwc, (src.data_ptr(), c_src, self._d(y)), tag)
+        self._emit(lib.add_nchw_to_nhwc, (src.data_ptr(), c_src, self._d(y)), tag,
+                   dict(kernel="nchw_to_nhwc", flops=0, bytes=src.numel() * 4 + y.n * y.h * y.w * y.c * y.buf.element_size()))
 
     def nhwc_to_nchw(self, x: View, dst: torch.Tensor, tag: str = "nhwc2nchw") -> None:
-        self._emit(lib.add_nhwc_to_nchw, (self._d(x), dst.data_ptr()), tag)
+        self._emit(lib.add_nhwc_to_nchw, (self._d(x), dst.data_ptr()), tag,
+                   dict(kernel="nhwc_to_nchw", flops=0, bytes=dst.numel() * 4 + x.n * x.h * x.w * x.c * x.buf.element_size()))
 
     def upsample_logits(self, x: View, dst: torch.Tensor, H: int, W: int, tag: str = "upsample_logits") -> None:
-        self._emit(lib.add_upsample_logits_nchw, (self._d(x), dst.data_ptr(), H, W), tag)
+        self._emit(lib.add_upsample_logits_nchw, (self._d(x), dst.data_ptr(), H, W), tag,
+                   dict(kernel="upsample_logits_nchw", flops=8 * dst.numel(), bytes=4 * (x.n * x.h * x.w * x.c + dst.numel())))
 
     def upsample_argmax(self, x: View, H: int, W: int, gt: Optional[torch.Tensor], pred: Optional[torch.Tensor],
                         cm: Optional[torch.Tensor], ent: Optional[torch.Tensor], tag: str = "upsample_argmax") -> None:
         nbytes = lib.add_head_workspace_bytes(x.n, H, W, x.c)
         ws = self.raw((nbytes,), torch.uint8)
         self._emit(lib.add_upsample_argmax_fwd,
-                   (self._d(x), H, W, _ptr(gt), _ptr(pred), _ptr(cm), _ptr(ent), ws.data_ptr(), nbytes), tag)
+                   (self._d(x), H, W, _ptr(gt), _ptr(pred), _ptr(cm), _ptr(ent), ws.data_ptr(), nbytes), tag,
+                   dict(kernel="upsample_argmax", flops=8 * x.n * H * W * x.c,
+                        bytes=4 * x.n * x.h * x.w * x.c + x.n * H * W * (8 * (gt is not None) + 8 * (pred is not None))))
 
     def edm_mlp(self, pooled: torch.Tensor, n: int, ws: Sequence[torch.Tensor], out: torch.Tensor,
                 tag: str = "edm_mlp") -> None:
@@ -270,10 +299,25 @@ class Plan:
 
     def run_eager(self) -> None:
         s = ctypes.c_void_p(torch.cuda.current_stream(self.builder.device).cuda_stream)
-        for fn, args, tag in self.launches:
+        for fn, args, tag, _ in self.launches:
             rc = fn(*args, s)
             if rc != 0:
                 check(rc, tag)
+
+    def profile(self) -> List[dict]:
+        """Replay eagerly with a CUDA-event pair around every launch (on the launching stream) and
+        return [{tag, kernel, flops, bytes, ms}] — per-launch device times for the roofline report."""
+        stream = torch.cuda.current_stream(self.builder.device)
+        s = ctypes.c_void_p(stream.cuda_stream)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in self.launches]
+        for (fn, args, tag, _), (e0, e1) in zip(self.launches, evs):
+            e0.record(stream)
+            rc = fn(*args, s)
+            e1.record(stream)
+            if rc != 0:
+                check(rc, tag)
+        stream.synchronize()
+        return [dict(tag=tag, ms=e0.elapsed_time(e1), **meta) for (_, _, tag, meta), (e0, e1) in zip(self.launches, evs)]
 
     def capture(self) -> None:
         self.run_eager()  # warm-up: cudaFuncSetAttribute calls must not happen inside capture

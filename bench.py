@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — ADD 1024x2048 inference images/sec on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libadd_b200, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # reference's CPU path (oracle port), host cores
+
+One step = one pass of the hot path over one batch: BASELINE config 2 — searched-dense ADD (C=2,
+F=20), 8 synthetic 3x1024x2048 images per GPU, bf16, EDM-gated early exit applied per image
+(threshold at the batch median ⇒ 4 of 8 images exit early; reference/parity exit semantics), each
+image's exit → argmax → int64 confusion matrix (what eval.py:195-221 does per image).
+`value`: inputs already resident in HBM.  `e2e`: the public API call with HOST (pinned) buffers —
+H2D of images+labels and D2H of the confusion matrices inside the timed region.
+Multi-GPU: batch sharding, one process per GPU, no data-path collective (weak scaling).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "ADD 1024x2048 inference images/sec"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=2048)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--exit-mode", default="reference", choices=["reference", "forward"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-images", type=int, default=2, help="images in the bounded CPU-baseline sample")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel launch table (JSON) here")
+    return ap.parse_args()
+
+
+def workload_name(a) -> dict:
+    return {"workload": f"searched-dense ADD C=2 F=20, {a.batch}x3x{a.height}x{a.width} per GPU, "
+                        f"EDM-gated early exit per image (threshold = batch median, {a.exit_mode} exit semantics), "
+                        "argmax + confusion matrix per exit taken",
+            "network": "searched-dense", "C": 2, "F": 20, "batch_per_gpu": a.batch,
+            "height": a.height, "width": a.width, "exit_mode": a.exit_mode,
+            "weights": "random init, seed 1 (kaiming conv, BN identity stats)",
+            "l2": "inputs per step (%.0f MB) exceed the 126 MB L2" % (a.batch * 3 * a.height * a.width * 4 / 1e6)}
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference's CPU path, all host threads
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_setup(a):
+    import torch
+    import add_b200  # only for the deterministic weight construction (same state_dict as the GPU arm)
+    from oracle import add_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = add_b200.build_add("searched-dense", 2, 20, seed=1)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    torch.manual_seed(203)
+    edm_sd = {k: v.detach() for k, v in add_b200.EDM().state_dict().items()}
+    na, ci, low = add_b200.NETWORKS["searched-dense"][2]
+    arch = orc.Arch(na, ci, low_level_layer=low)
+    return orc, sd, edm_sd, arch
+
+
+def cpu_reference_image(orc, sd, edm_sd, arch, x1, gt1, threshold):
+    """One image through the reference's dynamic_inference + argmax + confusion matrix on the CPU."""
+    import torch
+    with torch.no_grad():
+        y, ee, conf = orc.add_dynamic_inference(sd, arch, x1, threshold, 'edm', edm_sd)
+        pred = torch.argmax(y, 1)
+    return orc.generate_matrix(gt1.numpy(), pred.numpy()), ee
+
+
+def run_cpu_sample(a, n_images: int, exits: list) -> dict:
+    """Time `n_images` images, image j forced to exit early iff exits[j] (same 50 % mix as the GPU arm)."""
+    import add_b200
+    orc, sd, edm_sd, arch = cpu_reference_setup(a)
+    x, gt = add_b200.synthetic_batch(max(n_images, 1), a.height, a.width)
+    xs, gs = add_b200.synthetic_batch(1, 128, 256, seed=5)
+    cpu_reference_image(orc, sd, edm_sd, arch, xs, gs, 1e30)       # thread-pool / allocator warm-up (small)
+    t0 = time.perf_counter()
+    for j in range(n_images):
+        thr = 1e30 if exits[j % len(exits)] else -1e30
+        cpu_reference_image(orc, sd, edm_sd, arch, x[j:j + 1], gt[j:j + 1], thr)
+    dt = time.perf_counter() - t0
+    return {"value": n_images / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{n_images} image(s) {a.height}x{a.width} fp32, oracle/add_oracle.py add_dynamic_inference + argmax + "
+                      f"confusion matrix, early-exit pattern {[int(e) for e in exits[:n_images]]}, {dt:.1f} s",
+            "seconds": dt}
+
+
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import add_b200
+    orc, sd, edm_sd, arch = cpu_reference_setup(a)
+    x, gt = add_b200.synthetic_batch(2, a.height, a.width)
+    xs, gs = add_b200.synthetic_batch(1, 128, 256, seed=5)
+    cpu_reference_image(orc, sd, edm_sd, arch, xs, gs, 1e30)
+    # one step = ONE image (bounded sample of the 8-image batch); even steps exit early, odd steps do not
+    times = []
+    for s in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        cpu_reference_image(orc, sd, edm_sd, arch, x[s % 2:s % 2 + 1], gt[s % 2:s % 2 + 1], 1e30 if s % 2 == 0 else -1e30)
+        if s >= a.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    val = len(times) / total
+    cores = os.cpu_count() or 1
+    sample = (f"1 image {a.height}x{a.width} per step (bounded sample of the {a.batch}-image batch), alternating "
+              "early-exit / full-depth, oracle port of ADD.dynamic_inference + argmax + confusion matrix, fp32")
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_name(a),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def main_b200(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — add_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    import add_b200
+    from add_b200 import runtime as rt
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    net = add_b200.build_add("searched-dense", 2, 20, seed=1).to(dev)
+    net.set_precision(a.precision)
+    net.use_cuda_graph = not a.no_graph
+    torch.manual_seed(203)
+    edm = add_b200.EDM().eval().to(dev)
+    B, H, W = a.batch, a.height, a.width
+    x_host, gt_host = add_b200.synthetic_batch(B, H, W, seed=1234 + rank, pin=True)
+    x_dev, gt_dev = x_host.to(dev), gt_host.to(dev)
+
+    # gate values for this batch → threshold between the two middle values (half the images exit early)
+    _, _, confs = net.dynamic_evaluate(x_dev, gt_dev, -1e30, edm, a.exit_mode)
+    vals = sorted(float(c) for c in confs)
+    thr = 0.5 * (vals[B // 2 - 1] + vals[B // 2]) if B > 1 else vals[0] + 1.0
+    cm0, flags0, _ = net.dynamic_evaluate(x_dev, gt_dev, thr, edm, a.exit_mode)
+    cm0 = cm0.clone()
+    launches_per_step = net.last_dynamic_launches + 0
+
+    def step_resident():
+        return net.dynamic_evaluate(x_dev, gt_dev, thr, edm, a.exit_mode)
+
+    cm_host = torch.empty((B, 19, 19), dtype=torch.int64).pin_memory()
+    xd2, gd2 = torch.empty_like(x_dev), torch.empty_like(gt_dev)
+
+    def step_e2e():
+        xd2.copy_(x_host, non_blocking=True)
+        gd2.copy_(gt_host, non_blocking=True)
+        cm, flags, _ = net.dynamic_evaluate(xd2, gd2, thr, edm, a.exit_mode)
+        cm_host.copy_(cm, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return cm_host
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    ms_res, clocks = timed(step_resident, a.steps, max(a.warmup, 3), sample_clocks=True)
+    ms_e2e, _ = timed(step_e2e, a.steps, 1)
+    assert torch.equal(cm_host, cm0.cpu()), "e2e result differs from the resident-input result"
+    value = world * B * a.steps / (ms_res / 1e3)
+    e2e = world * B * a.steps / (ms_e2e / 1e3)
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel: per-launch CUDA-event times over one full step ----
+        runner = next(v for k, v in net._plans.items() if k[0] == "edm" and k[5] == "evaluate")
+        rows = []
+        for plan_owner in list(runner.segments.values()) + list(runner.heads.values()):
+            rows += plan_owner.main.profile()
+        agg = {}
+        for r in rows:
+            d = agg.setdefault(r["kernel"], dict(ms=0.0, flops=0, bytes=0, launches=0))
+            d["ms"] += r["ms"]; d["flops"] += r["flops"]; d["bytes"] += r["bytes"]; d["launches"] += 1
+        total_ms = sum(d["ms"] for d in agg.values())
+        top = max(agg, key=lambda k: agg[k]["ms"])
+        t = agg[top]
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        hbm_peak, tc_peak = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
+        src = "MEASURED_PEAKS.json" if pk.exists() else "fallback (B200_PROFILING.md)"
+        ai = t["flops"] / max(t["bytes"], 1)
+        if top.startswith("conv2d") and ai > 100:
+            ach = t["flops"] / (t["ms"] / 1e3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak}
+        else:
+            ach = t["bytes"] / (t["ms"] / 1e3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
+        roof.update({"kernel": top, "traffic": None, "peak_source": src, "launches": t["launches"],
+                     "avg_launch_ms": t["ms"] / t["launches"], "share_of_step": t["ms"] / total_ms,
+                     "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                     "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
+                                     "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in
+                                 sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}})
+        if a.profile_out:
+            Path(a.profile_out).write_text(json.dumps(rows, indent=0))
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            cpu = run_cpu_sample(a, a.cpu_images, [True, False])   # same 50 % early-exit mix as the GPU arm
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": ms_res / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": a.precision, "data": "synthetic", "config": dict(workload_name(a), parallelism=f"batch-shard dp{world}",
+                                                                           early_exit_flags=flags0, edm_threshold=thr,
+                                                                           cuda_graph=not a.no_graph,
+                                                                           tensor_core_path=bool(rt.tc_available())),
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + gt_host.numel() * 8,
+                        "d2h_bytes_per_step": cm_host.numel() * 8 + B * 4, "ms_per_step": ms_e2e / a.steps},
+                "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    args = parse()
+    sys.exit(main_reference(args) if args.impl == "reference" else main_b200(args))

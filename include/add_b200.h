@@ -93,6 +93,11 @@ int add_sepconv_half_fwd(const add_tensor_t* x, const add_tensor_t* y, const flo
 /* ---- bilinear resize, align_corners=False (F.interpolate: ADD.py:76,84,89,317; decoder.py:24) */
 int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, uint32_t flags, void* stream);
 
+/* ---- batch compaction for per-image early exit (ADD.py:421-432 applied to a batch): whole-image
+ * slabs dst[j] = src[idx[j]], j < count; idx lives on the device so the launch is graph-replayable. */
+int add_gather_images(const void* src, void* dst, const int32_t* idx_dev, int count,
+                      int64_t bytes_per_image, void* stream);
+
 /* ---- global average pool (aspp_train.py:49, ADD.py:522): out[n][c] fp32 = mean_hw relu?(x) */
 int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_t flags, void* stream);
 

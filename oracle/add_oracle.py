@@ -335,6 +335,8 @@ def _trunk(sd: SD, arch: Arch, x: torch.Tensor, relu_after_exit_feature=None):
                 cur = F.relu(cur)
             else:
                 two[1] = F.relu(two[1])
+                if i == 2:
+                    cur = two[1]   # x IS two_last_inputs[1] at i == 2 (ADD.py:399-400): same storage
 
 
 def add_forward(sd: SD, arch: Arch, x: torch.Tensor) -> List[torch.Tensor]:
@@ -476,7 +478,10 @@ def np_bilinear_nchw(x: np.ndarray, out_hw: Tuple[int, int]) -> np.ndarray:
     def axis(n_in, n_out):
         scale = np.float32(n_in) / np.float32(n_out)
         dst = np.arange(n_out, dtype=np.float32)
-        src = np.maximum(np.float32(0), scale * (dst + np.float32(0.5)) - np.float32(0.5)).astype(np.float32)
+        # ATen evaluates scale*(dst+0.5)-0.5 as ONE fused multiply-add (its CPU kernels are built with FP
+        # contraction on): emulate the single rounding through float64 (24x24-bit product is exact there).
+        fma = (scale.astype(np.float64) * (dst + np.float32(0.5)).astype(np.float64) - 0.5).astype(np.float32)
+        src = np.maximum(np.float32(0), fma).astype(np.float32)
         i0 = np.floor(src).astype(np.int64)
         i0 = np.minimum(i0, n_in - 1)
         i1 = np.minimum(i0 + 1, n_in - 1)

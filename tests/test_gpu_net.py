@@ -97,3 +97,36 @@ def test_entropy_gate_runs_and_matches_oracle():
     assert ee == ee_ref
     assert cv == pytest.approx(cv_ref, rel=1e-3, abs=1e-4)
     assert util.rel_err(y, y_ref) < 1e-3
+
+
+def test_batched_edm_gating_matches_per_image():
+    """Per-image gating of a batch (compaction) == the batch-1 reference control flow per image."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec).to(DEV)
+    edm = util.make_edm().to(DEV)
+    x, gt = util.make_input(5, 33, 65, seed=99)
+    xd, gtd = x.to(DEV), gt.to(DEV)
+    singles = []
+    for i in range(5):
+        y, ee, _, cv = net.dynamic_inference(xd[i:i + 1], threshold=-1e30, confidence='edm', edm=edm)  # never exit
+        singles.append(float(cv))
+    srt = sorted(singles)
+    thr = 0.5 * (srt[1] + srt[2])            # 2 images exit early, 3 continue
+    ref = []
+    for i in range(5):
+        y, ee, _, cv = net.dynamic_inference(xd[i:i + 1], threshold=thr, confidence='edm', edm=edm)
+        ref.append((y.clone(), ee))
+    ys, flags, confs = net.dynamic_inference_batch(xd, thr, 'edm', edm)
+    assert flags == [r[1] for r in ref] and sum(flags) == 2
+    for i in range(5):
+        assert util.rel_err(ys[i], ref[i][0]) < 1e-6
+        assert float(confs[i]) == pytest.approx(singles[i], rel=1e-5, abs=1e-6)
+    cms, flags2, _ = net.dynamic_evaluate(xd, gtd, thr, edm)
+    assert flags2 == flags
+    for i in range(5):
+        want = orc.generate_matrix(gt[i].numpy(), ref[i][0].argmax(1).cpu().numpy())
+        assert np.array_equal(cms[i].cpu().numpy(), want)
+    # all exit / none exit extremes
+    _, f_all, _ = net.dynamic_inference_batch(xd, 1e30, 'edm', edm)
+    _, f_none, _ = net.dynamic_inference_batch(xd, -1e30, 'edm', edm)
+    assert f_all == [1] * 5 and f_none == [0] * 5
