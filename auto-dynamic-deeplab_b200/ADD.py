@@ -236,7 +236,7 @@ class ADD(AddModule):
         rt.bump_generation()
 
     def _prepare(self):
-        self.cw_stem0 = ConvWeights(self.stem0[0].weight, self.stem0[1], cin_pad=4)
+        self.cw_stem0 = ConvWeights(self.stem0[0].weight, self.stem0[1], cin_pad=8)   # 16 B/pixel in bf16: TMA-able
         self.cw_stem1 = ConvWeights(self.stem1[0].weight, self.stem1[1])
         self.cw_stem2 = ConvWeights(self.stem2[1].weight, self.stem2[2])
         self.cw_low = ConvWeights(self.low_level_conv[1].weight, self.low_level_conv[2])
@@ -257,7 +257,7 @@ class ADD(AddModule):
         self._ensure_prepared()
         if first == 0:
             n, _, H, W = x_nchw.shape
-            img = b.alloc(n, H, W, 4)
+            img = b.alloc(n, H, W, 8)
             b.nchw_to_nhwc(x_nchw, 3, img, "ADD.input")
             h1, w1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             t0 = b.alloc(n, h1, w1, 64)

@@ -36,6 +36,7 @@ lib = _load()
 TP = POINTER(AddTensor)
 _SIGS = {
     "add_status_string": (c_char_p, [c_int]),
+    "add_last_cuda_error": (c_char_p, []),
     "add_version": (c_int, []),
     "add_device_sm_count": (c_int, []),
     "add_nchw_to_nhwc": (c_int, [c_void_p, c_int, TP, c_void_p]),
@@ -69,4 +70,6 @@ for _name, (_res, _args) in _SIGS.items():
 def check(status: int, what: str = "") -> None:
     if status != 0:
         msg = lib.add_status_string(int(status)).decode()
+        if int(status) == -3:
+            msg += " [" + lib.add_last_cuda_error().decode() + "]"
         raise AddError(f"libadd_b200 {what}: {msg} (status {status})")

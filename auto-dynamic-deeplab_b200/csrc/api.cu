@@ -12,6 +12,12 @@ extern "C" const char* add_status_string(int status) {
   }
 }
 
+thread_local int g_add_last_cuda_error = 0;
+
+extern "C" const char* add_last_cuda_error(void) {
+  return g_add_last_cuda_error == 0 ? "none" : cudaGetErrorString((cudaError_t)g_add_last_cuda_error);
+}
+
 extern "C" int add_version(void) { return 100; }  // 0.1.0
 
 extern "C" int add_device_sm_count(void) {

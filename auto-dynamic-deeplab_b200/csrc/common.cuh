@@ -7,7 +7,10 @@
 
 #define ADD_CHECK_ARG(cond) do { if (!(cond)) return ADD_ERR_BAD_ARG; } while (0)
 #define ADD_CHECK_SUP(cond) do { if (!(cond)) return ADD_ERR_UNSUPPORTED; } while (0)
-#define ADD_RETURN_LAUNCH() do { return cudaGetLastError() == cudaSuccess ? ADD_OK : ADD_ERR_CUDA; } while (0)
+// last CUDA runtime/driver error seen by this thread's launches (api.cu); add_last_cuda_error() reports it
+extern thread_local int g_add_last_cuda_error;
+#define ADD_RETURN_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ == cudaSuccess) return ADD_OK; \
+    g_add_last_cuda_error = (int)e_; return ADD_ERR_CUDA; } while (0)
 
 typedef __nv_bfloat16 bf16;
 

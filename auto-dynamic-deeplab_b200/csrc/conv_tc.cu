@@ -1,22 +1,417 @@
-// conv_tc.cu — tcgen05 / TMEM implicit-GEMM convolution for bf16 activations (sm_100a).
-// PLACEHOLDER until the tensor-core kernel lands: the entry points exist (the C ABI is stable) and
-// report ADD_ERR_UNSUPPORTED so callers fail loudly instead of silently taking another path.
+// conv_tc.cu — tcgen05 / TMEM implicit-GEMM convolution for bf16 NHWC activations (sm_100a).
+//
+//   y[n,oy,ox,co] (+)= act( bias[co] + sum_{ky,kx,ci} W[ky][kx][ci][co] *
+//                           relu?(x[n, oy*s - pad + ky*dil, ox*s - pad + kx*dil, ci]) )
+//
+// GEMM view: M = output pixels, N = Cout (padded to 16, one N tile: Cout <= 256), K = taps x Cin.
+// One CTA computes a 128-pixel spatial patch (BH x BW, BW a power of two) of one image.
+//  * A (activations): for every tap the 128 x 64-channel operand tile is ONE 4-D TMA box
+//    {64 ch, BW, BH, 1} of the NHWC tensor at the tap-shifted coordinate; out-of-image pixels and
+//    channels past Cin are zero-filled by the TMA unit (= the conv's zero padding, for free), the
+//    box lands in shared memory already in the UMMA K-major SWIZZLE_128B layout.  Strided convs
+//    use the tensor map's element strides.
+//  * B (weights): pre-packed bf16 [tap*kchunk][N_pad][64] (K-major), one 3-D TMA box per K chunk.
+//  * D: fp32 accumulator in TMEM (N_pad columns x 128 lanes), tcgen05.mma issued by one thread.
+//  * ReLU-on-load (the reference's ReLU -> conv order) is an in-place pass over the landed A tile
+//    by the four otherwise idle epilogue warps, fenced to the async proxy before the MMA reads it.
+//  * Epilogue: tcgen05.ld -> +bias (folded BN shift) -> (+= y, cell node sum) -> ReLU -> bf16/fp32
+//    stores into the (possibly channel-sliced) NHWC output view.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2..5 = ReLU pass + epilogue.  mbarrier ring of `stages` {A,B} slots; two CTAs per SM
+// overlap one tile's epilogue with the other's main loop.
 #include "common.cuh"
+#include <cuda.h>
+#include <cstring>
+#include <mutex>
 
-extern "C" int64_t add_conv2d_tc_packed_bytes(int cin, int cout, int kh, int kw) {
-  (void)cin; (void)cout; (void)kh; (void)kw;
-  return ADD_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int TC_BM = 128;                 // pixels per CTA tile (UMMA M)
+constexpr int TC_BK = 64;                  // channels per K chunk (128 B of bf16 = one swizzle row)
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 6;
+
+struct TcParams {
+  void* y; const float* bias;
+  int Ho, Wo, Cout, ys, y_is_f32;
+  int tiles_x, tiles_y;                    // spatial tiles per image
+  int bw_log2;                             // BW = 1 << bw_log2, BH = 128 >> bw_log2
+  int taps_w, taps, kchunks, Cin;
+  int stride, pad, dil;
+  int n_pad;                               // UMMA N
+  int tmem_cols;
+  int stages;
+  uint32_t b_bytes;                        // n_pad * 128
+  uint32_t flags;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
 }
 
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): 128-byte rows, 8-row groups
+// 1024 B apart (SBO), LBO unused for swizzled K-major layouts.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+  d |= (uint64_t)1 << 16;                          // leading byte offset (ignored) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS)
+conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 1];   // full[s], empty[s], relu[s], accum
+  __shared__ uint32_t tmem_base_smem;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles: 1024-B aligned
+  const uint32_t stage_bytes = TC_A_BYTES + p.b_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool relu_in = (p.flags & ADD_RELU_IN) != 0;
+
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[TC_MAX_STAGES]);
+  const uint32_t bar_relu = smem_u32(&bars[2 * TC_MAX_STAGES]);
+  const uint32_t bar_accum = smem_u32(&bars[3 * TC_MAX_STAGES]);
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y; const int n = t / p.tiles_y;
+  const int BW = 1 << p.bw_log2;
+  const int x0 = tx * BW, y0 = ty * (TC_BM >> p.bw_log2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_relu + 8 * s, 128);
+    }
+    mbar_init(bar_accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int iters = p.taps * p.kchunks;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+        const int ky = tap / p.taps_w, kx = tap - ky * p.taps_w;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t a_dst = smem_base + s * stage_bytes, b_dst = a_dst + TC_A_BYTES;
+        mbar_expect_tx(bar_full + 8 * s, stage_bytes);
+        tma_load_4d(a_dst, &map_x, bar_full + 8 * s, kc * TC_BK, x0 * p.stride - p.pad + kx * p.dil,
+                    y0 * p.stride - p.pad + ky * p.dil, n);
+        tma_load_3d(b_dst, &map_w, bar_full + 8 * s, 0, 0, it);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int kc = it % p.kchunks;
+        const int krem = p.Cin - kc * TC_BK;
+        const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
+        mbar_wait((relu_in ? bar_relu : bar_full) + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_src = smem_base + s * stage_bytes, b_src = a_src + TC_A_BYTES;
+        const uint64_t adesc = make_kmajor_sw128_desc(a_src), bdesc = make_kmajor_sw128_desc(b_src);
+        for (int k = 0; k < ksteps; ++k)   // +32 B along K inside the swizzle row = +2 in the address field
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_empty + 8 * s);     // frees the slot when these MMAs have read it
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(bar_accum);               // accumulator complete
+    }
+  } else {
+    // ===== ReLU pass (optional) + epilogue: warps 2..5 =====
+    const int et = threadIdx.x - 64;        // 0..127
+    if (relu_in) {
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(bar_full + 8 * s, ph);
+        const uint32_t a_src = smem_base + s * stage_bytes;
+#pragma unroll
+        for (int j = 0; j < TC_A_BYTES / (128 * 16); ++j) {
+          const uint32_t addr = a_src + (j * 128 + et) * 16;
+          uint32_t v0, v1, v2, v3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
+          asm("max.bf16x2 %0, %0, %1;" : "+r"(v0) : "r"(0u));
+          asm("max.bf16x2 %0, %0, %1;" : "+r"(v1) : "r"(0u));
+          asm("max.bf16x2 %0, %0, %1;" : "+r"(v2) : "r"(0u));
+          asm("max.bf16x2 %0, %0, %1;" : "+r"(v3) : "r"(0u));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+        mbar_arrive(bar_relu + 8 * s);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+    // ---- epilogue ----
+    mbar_wait(bar_accum, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;            // tile row = pixel
+    const int oy = y0 + (r >> p.bw_log2), ox = x0 + (r & (BW - 1));
+    const bool valid = (oy < p.Ho) && (ox < p.Wo);
+    const size_t pix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
+    const bool relu_out = p.flags & ADD_RELU_OUT, accum = p.flags & ADD_ACCUMULATE;
+    for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!valid) continue;
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int co = c0 + j;
+        f[j] = __uint_as_float(v[j]) + ((p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.f);
+      }
+      if (p.y_is_f32) {
+        float* dst = static_cast<float*>(p.y) + pix * p.ys + c0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (c0 + 4 * g + 4 <= p.Cout) {
+            float4 o = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+            if (accum) { float4 old = *reinterpret_cast<const float4*>(dst + 4 * g); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+            if (relu_out) o = relu4(o);
+            *reinterpret_cast<float4*>(dst + 4 * g) = o;
+          } else {
+            for (int j = 4 * g; j < 4 * g + 4; ++j)
+              if (c0 + j < p.Cout) {
+                float o = f[j];
+                if (accum) o += dst[j];
+                if (relu_out) o = fmaxf(o, 0.f);
+                dst[j] = o;
+              }
+          }
+        }
+      } else {
+        bf16* dst = static_cast<bf16*>(p.y) + pix * p.ys + c0;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c0 + 8 * g + 8 <= p.Cout) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = f[8 * g + j];
+            if (accum) {
+              uint4 old = *reinterpret_cast<const uint4*>(dst + 8 * g);
+              const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { float2 t2 = __bfloat1622float2(ob[j]); o[2 * j] += t2.x; o[2 * j + 1] += t2.y; }
+            }
+            if (relu_out) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            uint4 pk;
+            __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pb[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+            *reinterpret_cast<uint4*>(dst + 8 * g) = pk;
+          } else {
+            for (int j = 8 * g; j < 8 * g + 8; ++j)
+              if (c0 + j < p.Cout) {
+                float o = f[j];
+                if (accum) o += __bfloat162float(dst[j]);
+                if (relu_out) o = fmaxf(o, 0.f);
+                dst[j] = __float2bfloat16_rn(o);
+              }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline int kchunks_of(int cin) { return (cin + TC_BK - 1) / TC_BK; }
+inline int npad_of(int cout) { return round_up(cout, 16); }
+
+}  // namespace
+
+extern "C" int64_t add_conv2d_tc_packed_bytes(int cin, int cout, int kh, int kw) {
+  if (cin <= 0 || cout <= 0 || kh <= 0 || kw <= 0) return ADD_ERR_BAD_ARG;
+  if (cout > 256) return ADD_ERR_UNSUPPORTED;
+  return (int64_t)kh * kw * kchunks_of(cin) * npad_of(cout) * TC_BK * 2;
+}
+
+// w_hwio: fp32 [kh][kw][cin][cout] (BN scale folded) -> bf16 [kh*kw*kchunks][n_pad][64], zero padded.
 extern "C" int add_conv2d_tc_pack(const float* w_hwio, int cin, int cout, int kh, int kw, void* packed_host) {
-  (void)w_hwio; (void)cin; (void)cout; (void)kh; (void)kw; (void)packed_host;
-  return ADD_ERR_UNSUPPORTED;
+  ADD_CHECK_ARG(w_hwio && packed_host && cin > 0 && cout > 0 && kh > 0 && kw > 0);
+  ADD_CHECK_SUP(cout <= 256);
+  const int kc_n = kchunks_of(cin), n_pad = npad_of(cout);
+  uint16_t* out = static_cast<uint16_t*>(packed_host);
+  std::memset(out, 0, (size_t)kh * kw * kc_n * n_pad * TC_BK * 2);
+  for (int tap = 0; tap < kh * kw; ++tap)
+    for (int ci = 0; ci < cin; ++ci) {
+      const int kc = ci / TC_BK, k = ci % TC_BK;
+      const float* src = w_hwio + ((size_t)tap * cin + ci) * cout;
+      uint16_t* dst = out + ((size_t)(tap * kc_n + kc) * n_pad) * TC_BK + k;
+      for (int co = 0; co < cout; ++co) {
+        uint32_t u; std::memcpy(&u, &src[co], 4);
+        uint32_t rnd = 0x7FFFu + ((u >> 16) & 1u);           // round to nearest even
+        dst[(size_t)co * TC_BK] = (uint16_t)((u + rnd) >> 16);
+      }
+    }
+  return ADD_OK;
 }
 
 extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, const void* w_packed,
                                  const float* bias, int kh, int kw, int stride, int pad, int dil,
                                  uint32_t flags, void* stream) {
-  (void)x; (void)y; (void)w_packed; (void)bias; (void)kh; (void)kw; (void)stride; (void)pad; (void)dil;
-  (void)flags; (void)stream;
-  return ADD_ERR_UNSUPPORTED;
+  ADD_CHECK_ARG(tensor_ok(x) && tensor_ok(y) && w_packed);
+  ADD_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && dil > 0 && x->n == y->n);
+  ADD_CHECK_ARG(conv_extent_ok(x->h, y->h, kh, stride, pad, dil) && conv_extent_ok(x->w, y->w, kw, stride, pad, dil));
+  ADD_CHECK_SUP(x->dtype == ADD_BF16 && y->c <= 256 && stride <= 2);
+  // TMA: 16-byte aligned base and strides
+  ADD_CHECK_SUP(x->pix_stride % 8 == 0 && ((uintptr_t)x->ptr % 16) == 0 && ((uintptr_t)w_packed % 16) == 0);
+  if (y->dtype == ADD_BF16) ADD_CHECK_SUP(y->pix_stride % 8 == 0 && ((uintptr_t)y->ptr % 16) == 0);
+  else ADD_CHECK_SUP(y->pix_stride % 4 == 0 && ((uintptr_t)y->ptr % 16) == 0);
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) { g_add_last_cuda_error = (int)cudaErrorSymbolNotFound; return ADD_ERR_CUDA; }
+
+  TcParams p;
+  p.y = y->ptr; p.bias = bias; p.Ho = y->h; p.Wo = y->w; p.Cout = y->c; p.ys = y->pix_stride;
+  p.y_is_f32 = (y->dtype == ADD_F32);
+  int bw_log2 = 3;                                   // BW = smallest power of two >= Wo, clamped to [8, 128]
+  while ((1 << bw_log2) < y->w && bw_log2 < 7) ++bw_log2;
+  p.bw_log2 = bw_log2;
+  const int BW = 1 << bw_log2, BH = TC_BM / BW;
+  p.tiles_x = ceil_div(y->w, BW); p.tiles_y = ceil_div(y->h, BH);
+  p.taps_w = kw; p.taps = kh * kw; p.kchunks = kchunks_of(x->c); p.Cin = x->c;
+  p.stride = stride; p.pad = pad; p.dil = dil;
+  p.n_pad = npad_of(y->c);
+  p.tmem_cols = 32; while (p.tmem_cols < p.n_pad) p.tmem_cols <<= 1;
+  p.b_bytes = (uint32_t)p.n_pad * 128u;
+  const uint32_t stage_bytes = TC_A_BYTES + p.b_bytes;
+  int stages = (int)((100u * 1024u) / stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages < 2) stages = 2;
+  if (stages > p.taps * p.kchunks) stages = p.taps * p.kchunks;
+  if (stages < 1) stages = 1;
+  p.stages = stages; p.flags = flags;
+
+  CUtensorMap map_x, map_w;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)x->c, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
+    cuuint64_t strides[3] = {(cuuint64_t)x->pix_stride * 2, (cuuint64_t)x->w * x->pix_stride * 2,
+                             (cuuint64_t)x->h * x->w * x->pix_stride * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(BW * stride), (cuuint32_t)(BH * stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    if (encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ADD_ERR_UNSUPPORTED;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)TC_BK, (cuuint64_t)p.n_pad, (cuuint64_t)(p.taps * p.kchunks)};
+    cuuint64_t strides[2] = {(cuuint64_t)TC_BK * 2, (cuuint64_t)p.n_pad * TC_BK * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)p.n_pad, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ADD_ERR_UNSUPPORTED;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 1024;     // + alignment slack
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // + static < 227 KB
+  });
+  const long long grid = (long long)p.tiles_x * p.tiles_y * y->n;
+  ADD_CHECK_SUP(grid < (1ll << 31));
+  conv2d_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, p);
+  ADD_RETURN_LAUNCH();
 }

@@ -210,7 +210,11 @@ class Builder:
              flags: int = 0, tag: str = "conv") -> None:
         assert x.c == cw.cin and y.c == cw.cout, (x.c, cw.cin, y.c, cw.cout, tag)
         self.keep.append(cw)
-        use_tc = (x.dtype == torch.bfloat16 and tc_available())
+        # tcgen05 path: bf16 NHWC input whose base/stride are 16-byte multiples (TMA), Cout <= 256
+        use_tc = (x.dtype == torch.bfloat16 and tc_available() and cw.cout <= 256 and stride <= 2
+                  and x.buf.shape[3] % 8 == 0 and x.c_off % 8 == 0
+                  and ((y.dtype == torch.bfloat16 and y.buf.shape[3] % 8 == 0 and y.c_off % 8 == 0)
+                       or (y.dtype == torch.float32 and y.buf.shape[3] % 4 == 0 and y.c_off % 4 == 0)))
         p_out = y.n * y.h * y.w
         # strided 1x1 convs only touch the sampled lattice (SURVEY §8d FactorizedReduce row)
         p_in = p_out if (cw.kh == 1 and cw.kw == 1) else x.n * x.h * x.w

@@ -51,6 +51,7 @@ typedef struct {
 #define ADD_ACCUMULATE 4u    /* y += result instead of y = result (cell node sum, ADD.py:108)     */
 
 const char* add_status_string(int status);
+const char* add_last_cuda_error(void); /* text of the last CUDA error behind an ADD_ERR_CUDA on this thread */
 int  add_version(void);               /* 10000*major + 100*minor + patch                       */
 int  add_device_sm_count(void);       /* SMs of the current device, <0 on error                */
 

@@ -1,0 +1,119 @@
+"""GPU: the tcgen05/TMEM implicit-GEMM convolution against the CUDA-core fp32 kernel on identical
+bf16 inputs and bf16-representable weights, so both compute the same products with fp32
+accumulation: the only difference is summation order.  Tolerance 2e-5 max-norm relative for fp32
+outputs; 1 bf16 ulp (2^-8 relative) for bf16 outputs."""
+import numpy as np
+import pytest
+import torch
+
+import util
+import add_b200
+from add_b200 import runtime as rt
+from add_b200.runtime import Builder, ConvWeights, View, RELU_IN, RELU_OUT, ACCUMULATE
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _bf16_exact(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _run(x_buf, c_off, cin, w, bias, stride, pad, dil, flags, out_hw, out_dtype, y_ctot, y_off, tc, y_init):
+    rt.set_tc_enabled(tc)
+    b = Builder(DEV, torch.bfloat16)
+    xv = View(x_buf, c_off, cin)
+    ybuf = y_init.clone()
+    yv = View(ybuf, y_off, w.shape[0])
+    cw = ConvWeights(w)
+    cw.bias = bias
+    b.conv(xv, yv, cw, stride, pad, dil, flags)
+    torch.cuda.synchronize()
+    rt.set_tc_enabled(True)
+    return ybuf
+
+
+CASES = [
+    # cin, cout, k, stride, pad, dil, H, W, flags
+    (64, 64, 1, 1, 0, 1, 16, 128, 0),
+    (40, 40, 1, 1, 0, 1, 13, 17, RELU_IN),
+    (200, 40, 1, 1, 0, 1, 31, 64, RELU_IN),
+    (400, 80, 1, 1, 0, 1, 9, 130, RELU_IN | RELU_OUT),
+    (800, 80, 1, 1, 0, 1, 7, 33, RELU_IN),
+    (256, 19, 1, 1, 0, 1, 16, 40, 0),
+    (40, 40, 3, 1, 2, 2, 20, 37, RELU_IN),
+    (40, 40, 5, 1, 4, 2, 20, 37, RELU_IN | ACCUMULATE),
+    (80, 80, 5, 1, 4, 2, 11, 64, RELU_IN),
+    (160, 160, 3, 1, 2, 2, 8, 16, RELU_IN | ACCUMULATE),
+    (304, 256, 3, 1, 1, 1, 12, 24, RELU_IN | RELU_OUT),
+    (400, 256, 3, 1, 6, 6, 16, 32, RELU_IN | RELU_OUT),
+    (400, 256, 3, 1, 18, 18, 16, 32, RELU_OUT),
+    (8, 64, 3, 2, 1, 1, 32, 64, RELU_OUT),
+    (64, 128, 3, 2, 1, 1, 17, 33, RELU_IN),
+    (128, 24, 1, 2, 0, 1, 12, 16, RELU_IN),
+    (128, 24, 1, 2, -1, 1, 13, 9, RELU_IN),
+    (400, 128, 3, 2, 1, 1, 16, 32, RELU_IN | RELU_OUT),
+    (64, 64, 3, 1, 1, 1, 5, 300, RELU_OUT),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"c{c[0]}-{c[1]}_k{c[2]}s{c[3]}p{c[4]}d{c[5]}_{c[6]}x{c[7]}_f{c[8]}" for c in CASES])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_tc_matches_ffma(case, out_dtype):
+    cin, cout, k, stride, pad, dil, H, W, flags = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    n = 2
+    # input is a channel slice of a wider buffer (concat-slice reads)
+    x_ctot, c_off = cin + 16, 8
+    x_buf = torch.randn(n, H, W, x_ctot, generator=g).to(torch.bfloat16).to(DEV)
+    w = _bf16_exact(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    if pad >= 0:
+        ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    else:
+        ho, wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    step = 8 if out_dtype == torch.bfloat16 else 4
+    y_ctot, y_off = (cout + step - 1) // step * step + 2 * step, step
+    y_init = torch.randn(n, ho, wo, y_ctot, generator=g).to(out_dtype).to(DEV)
+    ref = _run(x_buf, c_off, cin, w, bias, stride, pad, dil, flags, (ho, wo), out_dtype, y_ctot, y_off, False, y_init)
+    got = _run(x_buf, c_off, cin, w, bias, stride, pad, dil, flags, (ho, wo), out_dtype, y_ctot, y_off, True, y_init)
+    # untouched channels stay untouched
+    assert torch.equal(got[..., :y_off], y_init[..., :y_off])
+    assert torch.equal(got[..., y_off + cout:], y_init[..., y_off + cout:])
+    a, r = got[..., y_off:y_off + cout].float(), ref[..., y_off:y_off + cout].float()
+    tol = 2e-5 if out_dtype == torch.float32 else 2 ** -7
+    assert util.rel_err(a, r) < tol
+
+
+def test_tc_is_the_bf16_conv_path():
+    assert rt.tc_available()
+    m, x = util.make_op_case("dil_conv_5x5_c40")
+    m = m.to(DEV)
+    b = Builder(DEV, torch.bfloat16, record=True)
+    xv = rt.as_nhwc_view(x.to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last), b, torch.bfloat16)
+    yv = b.alloc(xv.n, xv.h, xv.w, 40)
+    m.emit(b, xv, yv, 0)
+    assert [l[3]["kernel"] for l in b.launches] == ["conv2d_tc"]
+
+
+def test_network_bf16_vs_fp32():
+    """Whole network in bf16 (tensor-core path) against the fp32 golden.  Stated per-exit tolerance
+    (max-norm relative, BN-randomised weights): exit 1 (6 cells deep) 3e-2, last exit (12 cells deep)
+    1e-1 — every activation is rounded to bf16 (2^-8) at each of ~50 sequential layers; argmax
+    agreement >= 95 %."""
+    NETS = np.load(util.ROOT / "tests/golden/nets.npz")
+    cname = "searched-dense-C2"
+    spec = util.NET_CASES[cname]
+    net = util.make_net(spec).to(DEV)
+    net.set_precision("bf16")
+    for (h, w) in spec["sizes"]:
+        x, _ = util.make_input(1, h, w)
+        outs = net(x.to(DEV))
+        for e, o in enumerate(outs):
+            ref = torch.from_numpy(NETS[f"{cname}/{h}x{w}/forward/{e}"])
+            err = util.rel_err(o, ref)
+            agree = float((o.cpu().argmax(1) == ref.argmax(1)).float().mean())
+            print(f"bf16 {h}x{w} exit {e}: rel_err={err:.3e} argmax_agree={agree:.4f}")
+            assert err < (3e-2 if e < len(outs) - 1 else 1e-1)
+            assert agree > 0.95
