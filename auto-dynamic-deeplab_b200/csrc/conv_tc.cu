@@ -44,6 +44,10 @@ struct TcParams {
   int stages;
   uint32_t b_bytes;                        // n_pad * 128
   uint32_t flags;
+  // halo-resident mode (stride 1, 128-pixel row tiles)
+  int halo_pitch;                          // pixels per halo row in smem (multiple of 8)
+  int halo_bufs;                           // 1 or 2 halo buffers
+  int base_off_mode;                       // descriptor base_offset: 0 = always 0, 1 = (addr >> 7) & 7
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -105,6 +109,101 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
   d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
   return d;
+}
+
+// ---- shared pieces of the two kernels -----------------------------------------------------------
+// In-place ReLU over `bytes` of bf16 in shared memory by the 128 ReLU/epilogue threads (et = 0..127).
+__device__ __forceinline__ void relu_sweep(uint32_t base, uint32_t bytes, int et) {
+  for (uint32_t off = et * 16; off < bytes; off += 128 * 16) {
+    const uint32_t addr = base + off;
+    uint32_t v0, v1, v2, v3;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(v0) : "r"(0u));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(v1) : "r"(0u));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(v2) : "r"(0u));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(v3) : "r"(0u));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+}
+
+// TMEM accumulator -> +bias -> (+= y) -> ReLU -> bf16/fp32 stores.  Called by the four epilogue warps
+// after the accumulator-complete barrier.
+__device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_base, int warp, int lane, int n, int y0, int x0) {
+  const int BW = 1 << p.bw_log2;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+  const int r = q * 32 + lane;            // tile row = pixel
+  const int oy = y0 + (r >> p.bw_log2), ox = x0 + (r & (BW - 1));
+  const bool valid = (oy < p.Ho) && (ox < p.Wo);
+  const size_t pix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
+  const bool relu_out = p.flags & ADD_RELU_OUT, accum = p.flags & ADD_ACCUMULATE;
+  for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (!valid) continue;
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int co = c0 + j;
+      f[j] = __uint_as_float(v[j]) + ((p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.f);
+    }
+    if (p.y_is_f32) {
+      float* dst = static_cast<float*>(p.y) + pix * p.ys + c0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (c0 + 4 * g + 4 <= p.Cout) {
+          float4 o = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+          if (accum) { float4 old = *reinterpret_cast<const float4*>(dst + 4 * g); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          if (relu_out) o = relu4(o);
+          *reinterpret_cast<float4*>(dst + 4 * g) = o;
+        } else {
+          for (int j = 4 * g; j < 4 * g + 4; ++j)
+            if (c0 + j < p.Cout) {
+              float o = f[j];
+              if (accum) o += dst[j];
+              if (relu_out) o = fmaxf(o, 0.f);
+              dst[j] = o;
+            }
+        }
+      }
+    } else {
+      bf16* dst = static_cast<bf16*>(p.y) + pix * p.ys + c0;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (c0 + 8 * g + 8 <= p.Cout) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = f[8 * g + j];
+          if (accum) {
+            uint4 old = *reinterpret_cast<const uint4*>(dst + 8 * g);
+            const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float2 t2 = __bfloat1622float2(ob[j]); o[2 * j] += t2.x; o[2 * j + 1] += t2.y; }
+          }
+          if (relu_out) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+          }
+          uint4 pk;
+          __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pb[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+          *reinterpret_cast<uint4*>(dst + 8 * g) = pk;
+        } else {
+          for (int j = 8 * g; j < 8 * g + 8; ++j)
+            if (c0 + j < p.Cout) {
+              float o = f[j];
+              if (accum) o += __bfloat162float(dst[j]);
+              if (relu_out) o = fmaxf(o, 0.f);
+              dst[j] = __float2bfloat16_rn(o);
+            }
+        }
+      }
+    }
+  }
+  
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
@@ -198,99 +297,162 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       for (int it = 0; it < iters; ++it) {
         mbar_wait(bar_full + 8 * s, ph);
         const uint32_t a_src = smem_base + s * stage_bytes;
-#pragma unroll
-        for (int j = 0; j < TC_A_BYTES / (128 * 16); ++j) {
-          const uint32_t addr = a_src + (j * 128 + et) * 16;
-          uint32_t v0, v1, v2, v3;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
-          asm("max.bf16x2 %0, %0, %1;" : "+r"(v0) : "r"(0u));
-          asm("max.bf16x2 %0, %0, %1;" : "+r"(v1) : "r"(0u));
-          asm("max.bf16x2 %0, %0, %1;" : "+r"(v2) : "r"(0u));
-          asm("max.bf16x2 %0, %0, %1;" : "+r"(v3) : "r"(0u));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+        relu_sweep(a_src, TC_A_BYTES, et);
         mbar_arrive(bar_relu + 8 * s);
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
     // ---- epilogue ----
     mbar_wait(bar_accum, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int r = q * 32 + lane;            // tile row = pixel
-    const int oy = y0 + (r >> p.bw_log2), ox = x0 + (r & (BW - 1));
-    const bool valid = (oy < p.Ho) && (ox < p.Wo);
-    const size_t pix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
-    const bool relu_out = p.flags & ADD_RELU_OUT, accum = p.flags & ADD_ACCUMULATE;
-    for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (!valid) continue;
-      float f[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int co = c0 + j;
-        f[j] = __uint_as_float(v[j]) + ((p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.f);
-      }
-      if (p.y_is_f32) {
-        float* dst = static_cast<float*>(p.y) + pix * p.ys + c0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (c0 + 4 * g + 4 <= p.Cout) {
-            float4 o = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
-            if (accum) { float4 old = *reinterpret_cast<const float4*>(dst + 4 * g); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-            if (relu_out) o = relu4(o);
-            *reinterpret_cast<float4*>(dst + 4 * g) = o;
-          } else {
-            for (int j = 4 * g; j < 4 * g + 4; ++j)
-              if (c0 + j < p.Cout) {
-                float o = f[j];
-                if (accum) o += dst[j];
-                if (relu_out) o = fmaxf(o, 0.f);
-                dst[j] = o;
-              }
-          }
-        }
-      } else {
-        bf16* dst = static_cast<bf16*>(p.y) + pix * p.ys + c0;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (c0 + 8 * g + 8 <= p.Cout) {
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = f[8 * g + j];
-            if (accum) {
-              uint4 old = *reinterpret_cast<const uint4*>(dst + 8 * g);
-              const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) { float2 t2 = __bfloat1622float2(ob[j]); o[2 * j] += t2.x; o[2 * j + 1] += t2.y; }
-            }
-            if (relu_out) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-            }
-            uint4 pk;
-            __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) pb[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
-            *reinterpret_cast<uint4*>(dst + 8 * g) = pk;
-          } else {
-            for (int j = 8 * g; j < 8 * g + 8; ++j)
-              if (c0 + j < p.Cout) {
-                float o = f[j];
-                if (accum) o += __bfloat162float(dst[j]);
-                if (relu_out) o = fmaxf(o, 0.f);
-                dst[j] = __float2bfloat16_rn(o);
-              }
-          }
-        }
-      }
-    }
+    epilogue_store(p, tmem_base, warp, lane, n, y0, x0);
   }
 
   // ---- teardown ----
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---- halo-resident kernel (stride 1, BW = 128, BH = 1) ---------------------------------------------
+// The per-tap kernel above re-fetches the 128 x 64 A tile from L2 once per tap (9x / 25x).  Here the
+// kh halo rows of the current 64-channel chunk are brought into shared memory ONCE (one TMA box per
+// row, zero-filled outside the image = the conv padding) and every tap's A operand is the same
+// buffer addressed through a shifted UMMA descriptor: tap (ky,kx) starts (ky*pitch + kx*dil) pixels
+// (128 B each) into the buffer.  TMA's SWIZZLE_128B is a function of the shared-memory address bits,
+// which is also what the UMMA read side applies, so a 128-byte-granular shift stays consistent.
+// ReLU-on-load is one in-place sweep per halo chunk instead of one per tap.
+// Warps (224 threads): 0 = halo producer, 1 = MMA issuer (+TMEM alloc), 2 = weight producer,
+// 3..6 = ReLU sweep + epilogue.
+constexpr int TCH_THREADS = 224;
+
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_shifted(uint32_t saddr, int mode) {
+  uint64_t d = make_kmajor_sw128_desc(saddr);
+  if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7u) << 49;    // base_offset: phase of the 1024-B swizzle pattern
+  return d;
+}
+
+__global__ void __launch_bounds__(TCH_THREADS)
+conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[6 + 2 * TC_MAX_STAGES + 1];   // halo full/empty/relu [2], b_full[s], b_empty[s], accum
+  __shared__ uint32_t tmem_base_smem;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t halo_bytes = (uint32_t)(p.taps / p.taps_w) * p.halo_pitch * 128u;    // kh rows
+  const uint32_t b_base = smem_base + p.halo_bufs * halo_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool relu_in = (p.flags & ADD_RELU_IN) != 0;
+  const int kh = p.taps / p.taps_w;
+
+  const uint32_t bar_hfull = smem_u32(&bars[0]);
+  const uint32_t bar_hempty = smem_u32(&bars[2]);
+  const uint32_t bar_hrelu = smem_u32(&bars[4]);
+  const uint32_t bar_bfull = smem_u32(&bars[6]);
+  const uint32_t bar_bempty = smem_u32(&bars[6 + TC_MAX_STAGES]);
+  const uint32_t bar_accum = smem_u32(&bars[6 + 2 * TC_MAX_STAGES]);
+
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y; const int n = t / p.tiles_y;
+  const int x0 = tx * TC_BM, y0 = ty;
+
+  if (threadIdx.x == 0) {
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar_hfull + 8 * h, 1);
+      mbar_init(bar_hempty + 8 * h, 1);
+      mbar_init(bar_hrelu + 8 * h, 128);
+    }
+    for (int s2 = 0; s2 < p.stages; ++s2) {
+      mbar_init(bar_bfull + 8 * s2, 1);
+      mbar_init(bar_bempty + 8 * s2, 1);
+    }
+    mbar_init(bar_accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== halo producer: kh row boxes per 64-channel chunk =====
+    if (lane == 0) {
+      int hb = 0; uint32_t ph = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(bar_hempty + 8 * hb, ph ^ 1);
+        mbar_expect_tx(bar_hfull + 8 * hb, halo_bytes);
+        const uint32_t dst = smem_base + hb * halo_bytes;
+        for (int ky = 0; ky < kh; ++ky)
+          tma_load_4d(dst + ky * p.halo_pitch * 128, &map_x, bar_hfull + 8 * hb, kc * TC_BK, x0 - p.pad,
+                      y0 - p.pad + ky * p.dil, n);
+        if (++hb == p.halo_bufs) { hb = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== weight producer: one [n_pad x 64] K-major tile per (chunk, tap) =====
+    if (lane == 0) {
+      int s2 = 0; uint32_t ph = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc)
+        for (int tap = 0; tap < p.taps; ++tap) {
+          mbar_wait(bar_bempty + 8 * s2, ph ^ 1);
+          mbar_expect_tx(bar_bfull + 8 * s2, p.b_bytes);
+          tma_load_3d(b_base + s2 * p.b_bytes, &map_w, bar_bfull + 8 * s2, 0, 0, tap * p.kchunks + kc);
+          if (++s2 == p.stages) { s2 = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int hb = 0; uint32_t hph = 0; int s2 = 0; uint32_t bph = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        const int krem = p.Cin - kc * TC_BK;
+        const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
+        mbar_wait((relu_in ? bar_hrelu : bar_hfull) + 8 * hb, hph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t halo = smem_base + hb * halo_bytes;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int ky = tap / p.taps_w, kx = tap - ky * p.taps_w;
+          mbar_wait(bar_bfull + 8 * s2, bph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_src = halo + (uint32_t)(ky * p.halo_pitch + kx * p.dil) * 128u;
+          const uint64_t adesc = make_kmajor_sw128_desc_shifted(a_src, p.base_off_mode);
+          const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s2 * p.b_bytes);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+          umma_commit(bar_bempty + 8 * s2);
+          if (++s2 == p.stages) { s2 = 0; bph ^= 1; }
+        }
+        umma_commit(bar_hempty + 8 * hb);     // halo buffer free once this chunk's MMAs have read it
+        if (++hb == p.halo_bufs) { hb = 0; hph ^= 1; }
+      }
+      umma_commit(bar_accum);
+    }
+  } else if (warp >= 3) {
+    // ===== ReLU sweep (one per halo chunk) + epilogue: warps 3..6 =====
+    const int et = threadIdx.x - 96;        // 0..127
+    if (relu_in) {
+      int hb = 0; uint32_t ph = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(bar_hfull + 8 * hb, ph);
+        relu_sweep(smem_base + hb * halo_bytes, halo_bytes, et);
+        mbar_arrive(bar_hrelu + 8 * hb);
+        if (++hb == p.halo_bufs) { hb = 0; ph ^= 1; }
+      }
+    }
+    mbar_wait(bar_accum, 0);
+    epilogue_store(p, tmem_base, warp, lane, n, y0, x0);
+  }
+
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -315,6 +477,10 @@ EncodeTiledFn get_encode_fn() {
   });
   return fn;
 }
+
+int g_halo_mode = 1;   // 0 = per-tap A tiles only, 1 = halo-resident A (measured on B200: base_offset must stay 0 — the
+                       // swizzle is applied on absolute shared-memory address bits; mode 2 (base_offset = phase) is WRONG
+                       // and kept only as the recorded experiment)
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 inline int kchunks_of(int cin) { return (cin + TC_BK - 1) / TC_BK; }
@@ -384,12 +550,33 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
   if (stages < 1) stages = 1;
   p.stages = stages; p.flags = flags;
 
+  // halo-resident mode: stride-1 multi-tap convs on 128-pixel row tiles (the large feature maps)
+  int halo_mode = g_halo_mode;
+  // (N_pad > 160: the per-tap pipeline is already MMA-bound and keeps two CTAs per SM)
+  const bool halo = halo_mode > 0 && stride == 1 && p.taps > 1 && bw_log2 == 7 && p.n_pad <= 160;
+  p.halo_pitch = 0; p.halo_bufs = 0; p.base_off_mode = halo_mode == 2 ? 1 : 0;
+  size_t smem = 0;
+  if (halo) {
+    p.halo_pitch = round_up(TC_BM + (kw - 1) * dil, 8);
+    const uint32_t halo_bytes = (uint32_t)kh * p.halo_pitch * 128u;
+    p.halo_bufs = (p.kchunks > 1 && 2 * halo_bytes + 2 * p.b_bytes <= 110u * 1024u) ? 2 : 1;
+    int sb = (int)((110u * 1024u - (uint32_t)p.halo_bufs * halo_bytes) / p.b_bytes);
+    if (sb > TC_MAX_STAGES) sb = TC_MAX_STAGES;
+    if (sb < 2) sb = 2;
+    p.stages = sb;
+    smem = (size_t)p.halo_bufs * halo_bytes + (size_t)sb * p.b_bytes + 1024;
+    if (p.halo_pitch > 256 || smem > 200u * 1024u) return ADD_ERR_UNSUPPORTED;
+  } else {
+    smem = (size_t)stages * stage_bytes + 1024;     // + alignment slack
+  }
+
   CUtensorMap map_x, map_w;
   {
     cuuint64_t dims[4] = {(cuuint64_t)x->c, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
     cuuint64_t strides[3] = {(cuuint64_t)x->pix_stride * 2, (cuuint64_t)x->w * x->pix_stride * 2,
                              (cuuint64_t)x->h * x->w * x->pix_stride * 2};
     cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(BW * stride), (cuuint32_t)(BH * stride), 1};
+    if (halo) { box[1] = (cuuint32_t)p.halo_pitch; box[2] = 1; }
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     if (encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -405,13 +592,23 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return ADD_ERR_UNSUPPORTED;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024;     // + alignment slack
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
     cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // + static < 227 KB
+    cudaFuncSetAttribute(conv2d_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   });
   const long long grid = (long long)p.tiles_x * p.tiles_y * y->n;
   ADD_CHECK_SUP(grid < (1ll << 31));
-  conv2d_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, p);
+  if (halo)
+    conv2d_tc_halo_kernel<<<(unsigned)grid, TCH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, p);
+  else
+    conv2d_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, p);
   ADD_RETURN_LAUNCH();
+}
+
+/* Tuning / experiment switch for the halo-resident A path (see conv2d_tc_halo_kernel). */
+extern "C" int add_conv2d_tc_set_halo_mode(int mode) {
+  if (mode < 0 || mode > 2) return ADD_ERR_BAD_ARG;
+  g_halo_mode = mode;
+  return ADD_OK;
 }

@@ -68,28 +68,54 @@ nhwc_to_nchw_kernel(const TI* __restrict__ src, float* __restrict__ dst, int C, 
   }
 }
 
-// ---- global average pool: one block per (image, 32-channel group) -----------------------------
+// ---- global average pool: two deterministic stages ------------------------------------------------
+// stage 1: grid (splits, n); each block sums a contiguous pixel range for ALL channels with 4-channel
+// vector loads (thread = channel vector x pixel lane), block-reduces over pixel lanes in smem and
+// writes partial[n][split][C].  stage 2: one block per image sums the splits in fixed order.
+constexpr int GAP_THREADS = 256;
+__host__ __device__ inline int gap_splits(int HW) {
+  int s = (HW + 1023) / 1024;
+  return s < 1 ? 1 : (s > 148 * 2 ? 148 * 2 : s);
+}
+
 template <typename TI>
-__global__ void __launch_bounds__(256)
-gap_kernel(const TI* __restrict__ x, float* __restrict__ out, int HW, int C, int xs, uint32_t flags) {
-  __shared__ float red[8][33];
-  int n = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), row = threadIdx.x >> 5;
-  float s = 0.f;
-  if (c < C) {
-    const TI* xn = x + (size_t)n * HW * xs + c;
-    for (int p = row; p < HW; p += 8) {
-      float v = ld1(xn + (size_t)p * xs);
-      if (flags & ADD_RELU_IN) v = fmaxf(v, 0.f);
-      s += v;
+__global__ void __launch_bounds__(GAP_THREADS)
+gap_partial_kernel(const TI* __restrict__ x, float* __restrict__ part, int HW, int C, int xs, uint32_t flags) {
+  extern __shared__ float4 gap_red[];                // [lanes][cv]
+  const int cv = C >> 2;
+  const int lanes = GAP_THREADS / cv;                // pixel lanes (>= 1: host checks cv <= 256)
+  const int n = blockIdx.y, S = gridDim.x;
+  const int per = (HW + S - 1) / S;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  const int v = threadIdx.x % cv, l = threadIdx.x / cv;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (l < lanes) {
+    const TI* xn = x + (size_t)n * HW * xs + v * 4;
+    for (int p = p0 + l; p < p1; p += lanes) {
+      float4 t = ld4(xn + (size_t)p * xs);
+      if (flags & ADD_RELU_IN) t = relu4(t);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
+    gap_red[l * cv + v] = acc;
   }
-  red[row][threadIdx.x & 31] = s;
   __syncthreads();
-  if (row == 0 && c < C) {
-    float tot = 0.f;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) tot += red[r][threadIdx.x];
-    out[(size_t)n * C + c] = tot / (float)HW;
+  if (threadIdx.x < cv) {
+    float4 tot = gap_red[threadIdx.x];
+    for (int r = 1; r < lanes; ++r) {
+      float4 t = gap_red[r * cv + threadIdx.x];
+      tot.x += t.x; tot.y += t.y; tot.z += t.z; tot.w += t.w;
+    }
+    *reinterpret_cast<float4*>(part + ((size_t)n * S + blockIdx.x) * C + threadIdx.x * 4) = tot;
+  }
+}
+
+__global__ void __launch_bounds__(GAP_THREADS)
+gap_finalize_kernel(const float* __restrict__ part, float* __restrict__ out, int S, int C, float inv_hw) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += GAP_THREADS) {
+    float s = 0.f;
+    for (int i = 0; i < S; ++i) s += part[((size_t)n * S + i) * C + c];
+    out[(size_t)n * C + c] = s * inv_hw;
   }
 }
 
@@ -168,14 +194,25 @@ extern "C" int add_nhwc_to_nchw(const add_tensor_t* x, float* dst, void* stream)
   ADD_RETURN_LAUNCH();
 }
 
-extern "C" int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_t flags, void* stream) {
-  ADD_CHECK_ARG(tensor_ok(x) && out);
-  dim3 grid(ceil_div(x->c, 32), x->n);
+extern "C" int64_t add_global_avgpool_workspace_bytes(int n, int h, int w, int c) {
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0) return ADD_ERR_BAD_ARG;
+  return (int64_t)n * gap_splits(h * w) * c * sizeof(float);
+}
+
+extern "C" int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_t flags, void* workspace,
+                                      int64_t workspace_bytes, void* stream) {
+  ADD_CHECK_ARG(tensor_ok(x) && out && workspace);
+  ADD_CHECK_SUP(tensor_vec4_ok(x) && x->c / 4 <= GAP_THREADS);
+  if (workspace_bytes < add_global_avgpool_workspace_bytes(x->n, x->h, x->w, x->c)) return ADD_ERR_WORKSPACE;
+  const int HW = x->h * x->w, S = gap_splits(HW), cv = x->c / 4;
+  dim3 grid(S, x->n);
+  size_t smem = (size_t)(GAP_THREADS / cv) * cv * sizeof(float4);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (x->dtype == ADD_F32)
-    gap_kernel<float><<<grid, 256, 0, s>>>((const float*)x->ptr, out, x->h * x->w, x->c, x->pix_stride, flags);
+    gap_partial_kernel<float><<<grid, GAP_THREADS, smem, s>>>((const float*)x->ptr, (float*)workspace, HW, x->c, x->pix_stride, flags);
   else
-    gap_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x->ptr, out, x->h * x->w, x->c, x->pix_stride, flags);
+    gap_partial_kernel<bf16><<<grid, GAP_THREADS, smem, s>>>((const bf16*)x->ptr, (float*)workspace, HW, x->c, x->pix_stride, flags);
+  gap_finalize_kernel<<<x->n, GAP_THREADS, 0, s>>>((const float*)workspace, out, S, x->c, 1.f / (float)HW);
   ADD_RETURN_LAUNCH();
 }
 

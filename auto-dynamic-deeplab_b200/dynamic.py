@@ -211,6 +211,7 @@ class _EdmRunner:
         flags = [0] * n
         confs: List[Optional[torch.Tensor]] = [None] * n
         launches = 0
+        self.last_plans: List[Plan] = []
         if self.mode == "evaluate":
             self.gt_full.copy_(target, non_blocking=True)
         active = list(range(n))
@@ -219,9 +220,11 @@ class _EdmRunner:
         for k in range(len(self.exits) + 1):
             if k > 0:
                 seg.gather.run()
+                self.last_plans.append(seg.gather)
             if k == len(self.exits) and self.mode == "evaluate":
                 seg.idx_gt.copy_(torch.tensor(active, dtype=torch.int32), non_blocking=True)
             seg.main.run()
+            self.last_plans.append(seg.main)
             launches += seg.n_launches
             if k == len(self.exits):
                 for j, img in enumerate(active):
@@ -238,6 +241,7 @@ class _EdmRunner:
                 if self.mode == "evaluate":
                     head.idx_gt.copy_(torch.tensor([active[j] for j in ex], dtype=torch.int32), non_blocking=True)
                 head.main.run()
+                self.last_plans.append(head.main)
                 launches += head.n_launches
                 for jj, j in enumerate(ex):
                     outs[active[j]] = head.out[jj:jj + 1] if self.mode == "logits" else head.out[jj]

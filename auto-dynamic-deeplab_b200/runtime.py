@@ -142,6 +142,17 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 _TC_STATE = {"enabled": True, "probed": None}
 
 
+def set_tc_halo_mode(mode: int) -> None:
+    """0 = per-tap A tiles, 1 = halo-resident A (default), 2 = halo-resident with descriptor base_offset."""
+    check(lib.add_conv2d_tc_set_halo_mode(int(mode)), "conv2d_tc_set_halo_mode")
+    bump_generation()
+
+
+import os as _os
+if _os.environ.get("ADD_TC_HALO_MODE"):
+    set_tc_halo_mode(int(_os.environ["ADD_TC_HALO_MODE"]))
+
+
 def tc_available() -> bool:
     if _TC_STATE["probed"] is None:
         _TC_STATE["probed"] = lib.add_conv2d_tc_packed_bytes(64, 64, 1, 1) > 0
@@ -255,7 +266,9 @@ class Builder:
                    dict(kernel="gather_images", flops=0, bytes=2 * per * dst.shape[0]))
 
     def gap(self, x: View, out: torch.Tensor, flags: int = 0, tag: str = "gap") -> None:
-        self._emit(lib.add_global_avgpool_fwd, (self._d(x), out.data_ptr(), flags), tag,
+        nbytes = lib.add_global_avgpool_workspace_bytes(x.n, x.h, x.w, x.c)
+        ws = self.raw((max(int(nbytes), 16),), torch.uint8)
+        self._emit(lib.add_global_avgpool_fwd, (self._d(x), out.data_ptr(), flags, ws.data_ptr(), nbytes), tag,
                    dict(kernel="global_avgpool", flops=x.n * x.h * x.w * x.c, bytes=x.n * x.h * x.w * x.c * x.buf.element_size()))
 
     def nchw_to_nhwc(self, src: torch.Tensor, c_src: int, y: View, tag: str = "nchw2nhwc") -> None:

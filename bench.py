@@ -271,8 +271,8 @@ def main_b200(a):
         # ---- roofline of the dominant kernel: per-launch CUDA-event times over one full step ----
         runner = next(v for k, v in net._plans.items() if k[0] == "edm" and k[5] == "evaluate")
         rows = []
-        for plan_owner in list(runner.segments.values()) + list(runner.heads.values()):
-            rows += plan_owner.main.profile()
+        for plan in runner.last_plans:                 # exactly the plans the timed step replays
+            rows += plan.profile()
         agg = {}
         for r in rows:
             d = agg.setdefault(r["kernel"], dict(ms=0.0, flops=0, bytes=0, launches=0))

@@ -85,6 +85,10 @@ int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, const void* 
                       const float* bias, int kh, int kw, int stride, int pad, int dil,
                       uint32_t flags, void* stream);
 
+/* A-operand strategy of add_conv2d_tc_fwd: 0 = one TMA tile per tap; 1 = halo rows resident in shared
+ * memory, taps addressed through shifted UMMA descriptors (default); 2 = as 1 with descriptor base_offset. */
+int add_conv2d_tc_set_halo_mode(int mode);
+
 /* ---- SepConv half: ReLU → depthwise k×k → pointwise 1×1 → folded BN ---------------------- */
 /* Replaces operations.py:51-54 and :55-58 (two calls make one SepConv, operations.py:46-62).
  * w_dw: fp32 [k][k][C]; w_pw: fp32 [Cin][Cout] (BN scale folded); bias fp32[Cout]. Stride 1, pad k/2. */
@@ -99,8 +103,11 @@ int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, uint32_t flag
 int add_gather_images(const void* src, void* dst, const int32_t* idx_dev, int count,
                       int64_t bytes_per_image, void* stream);
 
-/* ---- global average pool (aspp_train.py:49, ADD.py:522): out[n][c] fp32 = mean_hw relu?(x) */
-int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_t flags, void* stream);
+/* ---- global average pool (aspp_train.py:49, ADD.py:522): out[n][c] fp32 = mean_hw relu?(x).
+ * Two deterministic stages (per-split partial sums in the workspace, fixed-order final sum). */
+int64_t add_global_avgpool_workspace_bytes(int n, int h, int w, int c);
+int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_t flags, void* workspace,
+                           int64_t workspace_bytes, void* stream);
 
 /* ---- EDM tail (ADD.py:509-513,523-525): pooled[n][128] → Linear/ReLU ×2 → Linear → out[n] */
 int add_edm_mlp_fwd(const float* pooled, int n, const float* w0, const float* b0, const float* w1,

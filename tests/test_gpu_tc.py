@@ -54,6 +54,14 @@ CASES = [
     (128, 24, 1, 2, -1, 1, 13, 9, RELU_IN),
     (400, 128, 3, 2, 1, 1, 16, 32, RELU_IN | RELU_OUT),
     (64, 64, 3, 1, 1, 1, 5, 300, RELU_OUT),
+    # halo-resident path (stride 1, Wo > 64, Cout <= 160): shifted-descriptor taps
+    (40, 40, 5, 1, 4, 2, 9, 253, RELU_IN | ACCUMULATE),
+    (40, 40, 3, 1, 2, 2, 7, 127, RELU_IN),
+    (80, 80, 5, 1, 4, 2, 6, 128, RELU_IN | RELU_OUT),
+    (160, 160, 3, 1, 2, 2, 5, 100, RELU_IN | ACCUMULATE),
+    (200, 48, 3, 1, 1, 1, 4, 65, 0),
+    (64, 64, 3, 1, 1, 1, 3, 1024, RELU_OUT),
+    (40, 40, 5, 1, 2, 1, 11, 256, RELU_IN),
 ]
 
 
