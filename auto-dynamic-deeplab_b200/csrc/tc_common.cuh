@@ -1,0 +1,214 @@
+// tc_common.cuh — shared pieces of the tcgen05/TMEM kernels (conv_tc.cu, sepconv_tc.cu): PTX wrappers
+// (mbarrier, TMA, tcgen05.mma/commit/ld), UMMA descriptors, the fused epilogue, tensor-map encoding.
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+#include <cstring>
+#include <mutex>
+
+namespace {
+
+
+constexpr int TC_BM = 128;                 // pixels per CTA tile (UMMA M)
+constexpr int TC_BK = 64;                  // channels per K chunk (128 B of bf16 = one swizzle row)
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 6;
+
+struct TcParams {
+  void* y; const float* bias;
+  int Ho, Wo, Cout, ys, y_is_f32;
+  int tiles_x, tiles_y;                    // spatial tiles per image
+  int bw_log2;                             // BW = 1 << bw_log2, BH = 128 >> bw_log2
+  int taps_w, taps, kchunks, Cin;
+  int stride, pad, dil;
+  int n_pad;                               // UMMA N
+  int tmem_cols;
+  int stages;
+  uint32_t b_bytes;                        // n_pad * 128
+  uint32_t flags;
+  // halo-resident mode (stride 1, 128-pixel row tiles)
+  int halo_pitch;                          // pixels per halo row in smem (multiple of 8)
+  int halo_bufs;                           // 1 or 2 halo buffers
+  int base_off_mode;                       // descriptor base_offset: 0 = always 0, 1 = (addr >> 7) & 7
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): 128-byte rows, 8-row groups
+// 1024 B apart (SBO), LBO unused for swizzled K-major layouts.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+  d |= (uint64_t)1 << 16;                          // leading byte offset (ignored) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+// ---- shared pieces of the two kernels -----------------------------------------------------------
+// In-place ReLU over `bytes` of bf16 in shared memory by the 128 ReLU/epilogue threads (et = 0..127).
+__device__ __forceinline__ void relu_sweep(uint32_t base, uint32_t bytes, int et) {
+  for (uint32_t off = et * 16; off < bytes; off += 128 * 16) {
+    const uint32_t addr = base + off;
+    uint32_t v0, v1, v2, v3;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(v0) : "r"(0u));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(v1) : "r"(0u));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(v2) : "r"(0u));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(v3) : "r"(0u));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+}
+
+// TMEM accumulator -> +bias -> (+= y) -> ReLU -> bf16/fp32 stores.  Called by the four epilogue warps
+// after the accumulator-complete barrier.
+__device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_base, int warp, int lane, int n, int y0, int x0) {
+  const int BW = 1 << p.bw_log2;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+  const int r = q * 32 + lane;            // tile row = pixel
+  const int oy = y0 + (r >> p.bw_log2), ox = x0 + (r & (BW - 1));
+  const bool valid = (oy < p.Ho) && (ox < p.Wo);
+  const size_t pix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
+  const bool relu_out = p.flags & ADD_RELU_OUT, accum = p.flags & ADD_ACCUMULATE;
+  for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (!valid) continue;
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int co = c0 + j;
+      f[j] = __uint_as_float(v[j]) + ((p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.f);
+    }
+    if (p.y_is_f32) {
+      float* dst = static_cast<float*>(p.y) + pix * p.ys + c0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (c0 + 4 * g + 4 <= p.Cout) {
+          float4 o = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+          if (accum) { float4 old = *reinterpret_cast<const float4*>(dst + 4 * g); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          if (relu_out) o = relu4(o);
+          *reinterpret_cast<float4*>(dst + 4 * g) = o;
+        } else {
+          for (int j = 4 * g; j < 4 * g + 4; ++j)
+            if (c0 + j < p.Cout) {
+              float o = f[j];
+              if (accum) o += dst[j];
+              if (relu_out) o = fmaxf(o, 0.f);
+              dst[j] = o;
+            }
+        }
+      }
+    } else {
+      bf16* dst = static_cast<bf16*>(p.y) + pix * p.ys + c0;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (c0 + 8 * g + 8 <= p.Cout) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = f[8 * g + j];
+          if (accum) {
+            uint4 old = *reinterpret_cast<const uint4*>(dst + 8 * g);
+            const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float2 t2 = __bfloat1622float2(ob[j]); o[2 * j] += t2.x; o[2 * j + 1] += t2.y; }
+          }
+          if (relu_out) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+          }
+          uint4 pk;
+          __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pb[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+          *reinterpret_cast<uint4*>(dst + 8 * g) = pk;
+        } else {
+          for (int j = 8 * g; j < 8 * g + 8; ++j)
+            if (c0 + j < p.Cout) {
+              float o = f[j];
+              if (accum) o += __bfloat162float(dst[j]);
+              if (relu_out) o = fmaxf(o, 0.f);
+              dst[j] = __float2bfloat16_rn(o);
+            }
+        }
+      }
+    }
+  }
+  
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline int kchunks_of(int cin) { return (cin + TC_BK - 1) / TC_BK; }
+inline int npad_of(int cout) { return round_up(cout, 16); }
+
+}  // namespace
