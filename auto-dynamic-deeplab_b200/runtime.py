@@ -247,10 +247,22 @@ class Builder:
         self.keep.extend((w_dw, pw))
         p = x.n * x.h * x.w
         ex = x.buf.element_size()
-        meta = dict(kernel="sepconv_half", flops=2 * p * (x.c * k * k + x.c * y.c),
-                    bytes=p * x.c * ex + p * y.c * ex * (2 if flags & ACCUMULATE else 1) + 4 * (x.c * k * k + x.c * y.c))
-        self._emit(lib.add_sepconv_half_fwd,
-                   (self._d(x), self._d(y), w_dw.data_ptr(), pw.w.data_ptr(), _ptr(pw.bias), k, flags), tag, meta)
+        # tensor-core path: bf16 NHWC input (TMA halo box), pointwise GEMM on tcgen05
+        use_tc = (x.dtype == torch.bfloat16 and tc_available() and x.c % 8 == 0 and x.c <= 256 and y.c <= 256
+                  and x.buf.shape[3] % 8 == 0 and x.c_off % 8 == 0
+                  and ((y.dtype == torch.bfloat16 and y.buf.shape[3] % 8 == 0 and y.c_off % 8 == 0)
+                       or (y.dtype == torch.float32 and y.buf.shape[3] % 4 == 0 and y.c_off % 4 == 0)))
+        meta = dict(flops=2 * p * (x.c * k * k + x.c * y.c),
+                    bytes=p * x.c * ex + p * y.c * y.buf.element_size() * (2 if flags & ACCUMULATE else 1)
+                    + 4 * x.c * k * k + (2 if use_tc else 4) * x.c * y.c)
+        if use_tc:
+            self._emit(lib.add_sepconv_half_tc_fwd,
+                       (self._d(x), self._d(y), w_dw.data_ptr(), pw.packed_tc().data_ptr(), _ptr(pw.bias), k, flags),
+                       tag + ":tc", dict(kernel="sepconv_half_tc", **meta))
+        else:
+            self._emit(lib.add_sepconv_half_fwd,
+                       (self._d(x), self._d(y), w_dw.data_ptr(), pw.w.data_ptr(), _ptr(pw.bias), k, flags), tag,
+                       dict(kernel="sepconv_half", **meta))
 
     def bilinear(self, x: View, y: View, flags: int = 0, tag: str = "bilinear") -> None:
         meta = dict(kernel="bilinear", flops=8 * y.n * y.h * y.w * y.c,

@@ -95,6 +95,14 @@ int add_conv2d_tc_set_halo_mode(int mode);
 int add_sepconv_half_fwd(const add_tensor_t* x, const add_tensor_t* y, const float* w_dw,
                          const float* w_pw, const float* bias, int k, uint32_t flags, void* stream);
 
+/* Same contract on the tensor-core path (bf16 activations): CUDA-core depthwise (packed fp32x2 FMA,
+ * TMA halo tile) whose bf16-rounded result is the A operand of a tcgen05 pointwise GEMM with a TMEM
+ * accumulator.  w_pw_packed: add_conv2d_tc_pack() image of the [1][1][Cin][Cout] pointwise weights.
+ * C % 8 == 0, C <= 256, Cout <= 256; y may be bf16 or fp32. */
+int add_sepconv_half_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, const float* w_dw,
+                            const void* w_pw_packed, const float* bias, int k, uint32_t flags,
+                            void* stream);
+
 /* ---- bilinear resize, align_corners=False (F.interpolate: ADD.py:76,84,89,317; decoder.py:24) */
 int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, uint32_t flags, void* stream);
 

@@ -125,3 +125,69 @@ def test_network_bf16_vs_fp32():
             print(f"bf16 {h}x{w} exit {e}: rel_err={err:.3e} argmax_agree={agree:.4f}")
             assert err < (3e-2 if e < len(outs) - 1 else 1e-1)
             assert agree > 0.95
+
+
+# ---- SepConv half on the tensor-core path (sepconv_tc.cu) vs a plain PyTorch fp32 reference ----------
+SEP_CASES = [
+    # C, Cout, k, H, W, flags
+    (40, 40, 3, 13, 17, RELU_IN | RELU_OUT),
+    (40, 40, 5, 13, 17, RELU_IN | RELU_OUT),
+    (40, 40, 5, 8, 16, 0),
+    (40, 40, 3, 21, 253, ACCUMULATE),
+    (80, 80, 3, 9, 20, RELU_IN | RELU_OUT),
+    (80, 80, 5, 17, 127, RELU_IN | ACCUMULATE),
+    (160, 160, 5, 6, 7, RELU_IN),
+    (160, 160, 3, 32, 64, ACCUMULATE | RELU_OUT),
+    (24, 24, 3, 7, 9, RELU_IN),
+    (64, 48, 5, 10, 33, RELU_IN | RELU_OUT),
+    (200, 40, 3, 5, 18, 0),
+]
+
+
+def _sep_reference(x, w_dw, w_pw, bias, k, flags, y_init):
+    """fp32 PyTorch: relu? -> depthwise (fp32) -> round to bf16 (the kernel's A operand) -> 1x1 -> +bias."""
+    import torch.nn.functional as F
+    xin = x.float().permute(0, 3, 1, 2)
+    if flags & RELU_IN:
+        xin = F.relu(xin)
+    C = xin.shape[1]
+    d = F.conv2d(xin, w_dw.permute(2, 0, 1).unsqueeze(1), padding=k // 2, groups=C)
+    d = d.to(torch.bfloat16).float()
+    o = F.conv2d(d, w_pw.t().reshape(w_pw.shape[1], C, 1, 1)) + bias.view(1, -1, 1, 1)
+    o = o.permute(0, 2, 3, 1)
+    if flags & ACCUMULATE:
+        o = o + y_init.float()
+    if flags & RELU_OUT:
+        o = F.relu(o)
+    return o
+
+
+@pytest.mark.parametrize("case", SEP_CASES, ids=[f"c{c[0]}-{c[1]}_k{c[2]}_{c[3]}x{c[4]}_f{c[5]}" for c in SEP_CASES])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_sepconv_half_tc_matches_torch(case, out_dtype):
+    """Tolerance: fp32 output 2e-3, bf16 output 2^-7 (max-norm relative).  The depthwise result is
+    rounded to bf16 before the pointwise GEMM in both; fp32 summation order may flip a rounding."""
+    C, Cout, k, H, W, flags = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    n = 2
+    x_ctot, c_off = C + 16, 8
+    x_buf = torch.randn(n, H, W, x_ctot, generator=g).to(torch.bfloat16).to(DEV)
+    w_dw = (torch.randn(k, k, C, generator=g) / k).to(DEV)
+    w_pw = _bf16_exact(torch.randn(C, Cout, generator=g) / C ** 0.5).to(DEV)     # [Cin][Cout]
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    step = 8 if out_dtype == torch.bfloat16 else 4
+    y_ctot, y_off = (Cout + step - 1) // step * step + 2 * step, step
+    y_init = torch.randn(n, H, W, y_ctot, generator=g).to(out_dtype).to(DEV)
+    cw = ConvWeights(w_pw.t().reshape(Cout, C, 1, 1).contiguous())
+    cw.bias = bias
+    b = Builder(DEV, torch.bfloat16, record=True)
+    ybuf = y_init.clone()
+    b.sepconv_half(View(x_buf, c_off, C), View(ybuf, y_off, Cout), w_dw.contiguous(), cw, k, flags)
+    assert [l[3]["kernel"] for l in b.launches] == ["sepconv_half_tc"]
+    rt.Plan(b).run_eager()
+    torch.cuda.synchronize()
+    ref = _sep_reference(x_buf[..., c_off:c_off + C], w_dw, w_pw, bias, k, flags, y_init[..., y_off:y_off + Cout])
+    assert torch.equal(ybuf[..., :y_off], y_init[..., :y_off])
+    assert torch.equal(ybuf[..., y_off + Cout:], y_init[..., y_off + Cout:])
+    tol = 2e-3 if out_dtype == torch.float32 else 2 ** -7
+    assert util.rel_err(ybuf[..., y_off:y_off + Cout].float(), ref) < tol
