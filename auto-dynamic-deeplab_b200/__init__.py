@@ -16,5 +16,6 @@ from .decoder import Decoder
 from .ADD import ADD, Cell, EDM
 from .metrics import Evaluator
 from .factory import build_add, Args, synthetic_batch
+from .parallel import shard_range, env_rank_world, all_reduce_confusion
 
 __version__ = "0.1.0"

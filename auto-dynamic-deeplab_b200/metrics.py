@@ -69,6 +69,14 @@ class Evaluator(object):
         self.confusion_matrix += cm_int64          # fp32 += int64, as in the reference (Q6)
         self.confusion_matrix_int64 += cm_int64
 
+    def all_reduce(self, group=None):
+        """Global confusion matrix over the batch shards of all ranks: one all-reduce of
+        the exact int64 matrix (2.9 KB); the fp32 accumulator is rebuilt from it.  No-op on one rank."""
+        from .parallel import all_reduce_confusion
+        all_reduce_confusion(self.confusion_matrix_int64, group)
+        self.confusion_matrix = self.confusion_matrix_int64.to(torch.float32)
+        return self
+
     def reset(self):
         self.confusion_matrix = torch.zeros((self.num_class,) * 2).cuda()
         self.confusion_matrix_int64 = torch.zeros((self.num_class,) * 2, dtype=torch.int64).cuda()

@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=2, help="images in the bounded CPU-baseline sample")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel launch table (JSON) here")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="for `ncu --profile-from-start off`: warm up, then run ONE step between cudaProfilerStart/Stop "
+                         "and exit (prints no bench line)")
     return ap.parse_args()
 
 
@@ -64,45 +67,62 @@ def workload_name(a) -> dict:
 # clocks sampler (B200_PROFILING.md recipe)
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """`nvidia-smi -lms 20` in the background.  It is started BEFORE the warm-up (the tool takes a few hundred ms
+    to produce its first line); `mark()` brackets the timed region and only samples that arrived inside it are
+    reported (falling back to the samples under load since start if the region was too short to catch one)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.lines, self.marks = gpu_index, None, [], []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [t.strip() for t in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def collect(lo, hi):
+            sm, smax, reasons = [], [], set()
+            for ts, ln in self.lines:
+                if not (lo <= ts <= hi):
+                    continue
+                f = [t.strip() for t in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, smax, reasons
+        lo, hi = (self.marks + [0.0, float("inf")])[:2] if len(self.marks) >= 2 else (0.0, float("inf"))
+        sm, smax, reasons = collect(lo, hi + 0.03)
+        window = "timed region"
+        if not sm:
+            sm, smax, reasons = collect(0.0, float("inf"))
+            window = "warm-up + timed region (timed region shorter than one sample)"
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -239,19 +259,33 @@ def main_b200(a):
         torch.cuda.current_stream().synchronize()
         return cm_host
 
+    if a.profile_step:
+        for _ in range(max(a.warmup, 3)):
+            step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return 0
+
     def timed(fn, steps, warmup, sample_clocks=False):
-        for _ in range(warmup):
-            fn()
-        barrier()
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
             sampler.start()
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if sampler:
+            sampler.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         barrier()
+        if sampler:
+            sampler.mark()
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)
         if world > 1:
