@@ -120,10 +120,8 @@ class Cell(AddModule):
             temps.append(cat)
             for i, src in enumerate(prev_prev):
                 if src.h != h:
-                    r = b.scratch(n, h, w, src.c)
-                    b.bilinear(src, r, 0, "Cell.resize_dense")
+                    r = b.resized(src, h, w, "Cell.resize_dense")
                     self.pre_preprocess[i].emit(b, r, cat.slice(i * C, C), 0)
-                    b.release(r)
                 else:
                     self.pre_preprocess[i].emit(b, src, cat.slice(i * C, C), 0)
             self.pre_preprocess_1x1.emit(b, cat, s0, 0)

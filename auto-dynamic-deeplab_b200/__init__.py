@@ -16,6 +16,7 @@ from .decoder import Decoder
 from .ADD import ADD, Cell, EDM
 from .metrics import Evaluator
 from .factory import build_add, Args, synthetic_batch
+from .pipeline import HostPipeline
 from .parallel import shard_range, env_rank_world, all_reduce_confusion
 
 __version__ = "0.1.0"

@@ -12,9 +12,11 @@ constexpr int HD_WARPS = HD_THREADS / 32;
 constexpr int MAX_CLASS = 32;               // num_class <= 32 (Cityscapes: 19)
 constexpr int MAX_BINS = 361 + 7;           // supports num_class <= 19 for the histogram
 
-__host__ __device__ inline int head_blocks_per_image(long long hw) {
+// blocks per image: enough 2048-pixel chunks to fill the GPU (n*B ~ 4 CTAs per SM), few enough that the
+// deterministic second-stage merge of the per-block histograms stays short
+__host__ __device__ inline int head_blocks_per_image(long long hw, int n) {
   long long b = (hw + 2047) / 2048;
-  long long cap = 148 * 8;
+  long long cap = (148 * 4 + n - 1) / n;
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
@@ -116,16 +118,129 @@ upsample_argmax_kernel(const HeadParams p) {
   }
 }
 
+// Fast path for a compile-time class count: a thread owns a run of 8 consecutive output pixels of one row,
+// [8r-4, 8r+4) — for the decoder's x8 upsample (decoder.py:28) the whole run interpolates between the SAME two
+// source columns, so the 4 x NC source logits are loaded once per run and kept in registers (reloaded whenever
+// the source columns change, so any size ratio is handled).  Same arithmetic order as upsample_logits_nchw.
+template <int NC, bool WANT_ENT>
+__global__ void __launch_bounds__(HD_THREADS)
+upsample_argmax_runs_kernel(const HeadParams p) {
+  __shared__ unsigned int hist[HD_WARPS][MAX_BINS];
+  __shared__ double ent_red[HD_WARPS];
+  const int n = blockIdx.y, b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool do_hist = p.part_hist != nullptr;
+  if (do_hist)
+    for (int i = threadIdx.x; i < HD_WARPS * MAX_BINS; i += HD_THREADS) (&hist[0][0])[i] = 0u;
+  __syncthreads();
+  const int runs_per_row = (p.W + 4 + 7) / 8;
+  const long long n_runs = (long long)p.H * runs_per_row;
+  const long long per = (n_runs + p.B - 1) / p.B;
+  const long long start = b * per, end = (start + per < n_runs) ? start + per : n_runs;
+  const long long HW = (long long)p.H * p.W;
+  const float* xn = p.x + (size_t)n * p.h * p.w * p.xs;
+  const float inv_logc = 1.f / logf((float)NC);
+  double ent = 0.0;
+  for (long long base = start + warp * 32; base < end; base += HD_THREADS) {      // uniform trip count per warp
+    const long long run = base + lane;
+    const bool live = run < end;
+    const int oy = live ? (int)(run / runs_per_row) : 0;
+    const int ox_first = live ? ((int)(run % runs_per_row) * 8 - 4) : 0;
+    int y0, y1; float hl0, hl1;
+    bilinear_src(oy, p.sh, p.h, y0, y1, hl0, hl1);
+    const float* row0 = xn + (size_t)y0 * p.w * p.xs;
+    const float* row1 = xn + (size_t)y1 * p.w * p.xs;
+    float v00[NC], v01[NC], v10[NC], v11[NC];
+    int cx0 = -1, cx1 = -1;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      const int ox = ox_first + j;
+      int bin = -1;
+      if (live && ox >= 0 && ox < p.W) {
+        int x0, x1; float wl0, wl1;
+        bilinear_src(ox, p.sw, p.w, x0, x1, wl0, wl1);
+        if (x0 != cx0 || x1 != cx1) {
+          const float* a0 = row0 + (size_t)x0 * p.xs; const float* a1 = row0 + (size_t)x1 * p.xs;
+          const float* b0 = row1 + (size_t)x0 * p.xs; const float* b1 = row1 + (size_t)x1 * p.xs;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) { v00[c] = __ldg(a0 + c); v01[c] = __ldg(a1 + c); v10[c] = __ldg(b0 + c); v11[c] = __ldg(b1 + c); }
+          cx0 = x0; cx1 = x1;
+        }
+        float v[NC];
+        float best = -INFINITY; int arg = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const float val = hl0 * (wl0 * v00[c] + wl1 * v01[c]) + hl1 * (wl0 * v10[c] + wl1 * v11[c]);
+          v[c] = val;
+          if (val > best) { best = val; arg = c; }    // first maximum wins, like torch.argmax
+        }
+        if (WANT_ENT) {
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) s += expf(v[c] - best);
+          const float logs = logf(s);
+          float e = 0.f;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) { const float lp = v[c] - best - logs; e += expf(lp) * lp; }
+          ent += (double)(-e * inv_logc);
+        }
+        const size_t pix = (size_t)n * HW + (size_t)oy * p.W + ox;
+        if (p.pred) p.pred[pix] = arg;
+        if (do_hist && p.gt) {
+          const long long g = __ldg(p.gt + pix);
+          if (g >= 0 && g < NC) bin = (int)g * NC + arg;
+        }
+      }
+      if (do_hist) warp_hist_add(hist[warp], bin, lane);
+    }
+  }
+  if (WANT_ENT) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ent += __shfl_xor_sync(0xffffffffu, ent, o);
+    if (lane == 0) ent_red[warp] = ent;
+  }
+  __syncthreads();
+  if (do_hist) {
+    unsigned int* out = p.part_hist + ((size_t)n * p.B + b) * p.bins;
+    for (int i = threadIdx.x; i < p.bins; i += HD_THREADS) {
+      unsigned int s = 0;
+#pragma unroll
+      for (int wv = 0; wv < HD_WARPS; ++wv) s += hist[wv][i];
+      out[i] = s;
+    }
+  }
+  if (WANT_ENT && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int wv = 0; wv < HD_WARPS; ++wv) s += ent_red[wv];
+    p.part_ent[(size_t)n * p.B + b] = s;
+  }
+}
+
 // deterministic second stage: one block per image
 __global__ void __launch_bounds__(HD_THREADS)
 head_finalize_kernel(const unsigned int* __restrict__ part_hist, const double* __restrict__ part_ent,
                      int B, int bins, long long* __restrict__ cm_out, float* __restrict__ ent_out,
                      double inv_hw) {
-  int n = blockIdx.x;
+  // warp w sums the per-block histograms b = w, w+8, ... (coalesced rows, independent loads), then the eight
+  // per-warp sums are added in fixed order: integer arithmetic, deterministic.
+  __shared__ long long red[HD_WARPS][MAX_BINS];
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (cm_out) {
+    for (int i0 = 0; i0 < bins; i0 += 32 * 4) {
+      long long s[4] = {0, 0, 0, 0};
+      for (int b = warp; b < B; b += HD_WARPS) {
+        const unsigned int* row = part_hist + ((size_t)n * B + b) * bins;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + lane; if (i < bins) s[u] += __ldg(row + i); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + lane; if (i < bins) red[warp][i] = s[u]; }
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < bins; i += HD_THREADS) {
       long long s = 0;
-      for (int b = 0; b < B; ++b) s += part_hist[((size_t)n * B + b) * bins + i];
+#pragma unroll
+      for (int wv = 0; wv < HD_WARPS; ++wv) s += red[wv][i];
       cm_out[(size_t)n * bins + i] = s;
     }
   }
@@ -278,7 +393,7 @@ extern "C" int add_upsample_logits_nchw(const add_tensor_t* x, float* dst, int H
 
 extern "C" int64_t add_head_workspace_bytes(int n, int H, int W, int num_class) {
   if (n <= 0 || H <= 0 || W <= 0 || num_class <= 0) return ADD_ERR_BAD_ARG;
-  int B = head_blocks_per_image((long long)H * W);
+  int B = head_blocks_per_image((long long)H * W, n);
   int64_t hist = (int64_t)n * B * num_class * num_class * sizeof(unsigned int);
   hist = (hist + 15) & ~15ll;
   return hist + (int64_t)n * B * sizeof(double);
@@ -296,14 +411,19 @@ extern "C" int add_upsample_argmax_fwd(const add_tensor_t* x, int H, int W, cons
   p.x = (const float*)x->ptr; p.n = x->n; p.h = x->h; p.w = x->w; p.c = x->c; p.xs = x->pix_stride;
   p.H = H; p.W = W; p.sh = (float)x->h / (float)H; p.sw = (float)x->w / (float)W;
   p.gt = (const long long*)gt; p.pred = (long long*)pred_out;
-  p.bins = x->c * x->c; p.B = head_blocks_per_image((long long)H * W);
+  p.bins = x->c * x->c; p.B = head_blocks_per_image((long long)H * W, x->n);
   int64_t hist_bytes = ((int64_t)x->n * p.B * p.bins * sizeof(unsigned int) + 15) & ~15ll;
   p.part_hist = cm_out ? (unsigned int*)workspace : nullptr;
   p.part_ent = (double*)((char*)workspace + hist_bytes);
   p.want_ent = entropy_out != nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dim3 grid(p.B, x->n);
-  upsample_argmax_kernel<<<grid, HD_THREADS, 0, s>>>(p);
+  if (x->c == 19) {            // Cityscapes: the specialised run kernel
+    if (p.want_ent) upsample_argmax_runs_kernel<19, true><<<grid, HD_THREADS, 0, s>>>(p);
+    else upsample_argmax_runs_kernel<19, false><<<grid, HD_THREADS, 0, s>>>(p);
+  } else {
+    upsample_argmax_kernel<<<grid, HD_THREADS, 0, s>>>(p);
+  }
   if (cm_out || entropy_out)
     head_finalize_kernel<<<x->n, HD_THREADS, 0, s>>>(p.part_hist, p.part_ent, p.B, p.bins,
                                                       (long long*)cm_out, entropy_out, 1.0 / ((double)H * W));

@@ -5,29 +5,60 @@
 namespace {
 
 // ---- bilinear, align_corners=False -----------------------------------------------------------
-template <typename TI, typename TO>
+// Thread = one output pixel x V consecutive channels (V = 8 for 16-byte-aligned bf16 views: four 16 B loads,
+// one 16 B store; V = 4 otherwise).  grid = (blocks over Ho*Wo*C/V, N); 32-bit index arithmetic.
+template <int V> struct VecIO;
+template <> struct VecIO<4> {
+  template <typename T> static __device__ __forceinline__ void load(const T* p, float (&v)[4]) {
+    float4 t = ld4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  template <typename T> static __device__ __forceinline__ void store(T* p, const float (&v)[4]) {
+    st4(p, make_float4(v[0], v[1], v[2], v[3]));
+  }
+};
+template <> struct VecIO<8> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+    uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+    uint4 r;
+    uint32_t* u = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); u[i] = *reinterpret_cast<uint32_t*>(&b); }
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+
+template <typename TI, typename TO, int V>
 __global__ void __launch_bounds__(256)
-bilinear_kernel(const TI* __restrict__ x, TO* __restrict__ y, int N, int H, int W, int C, int xs,
+bilinear_kernel(const TI* __restrict__ x, TO* __restrict__ y, int H, int W, int C, int xs,
                 int Ho, int Wo, int ys, float sh, float sw, uint32_t flags) {
-  const int cv = C >> 2;
-  long long total = (long long)N * Ho * Wo * cv;
-  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
-    int c = (int)(idx % cv) * 4; long long pix = idx / cv;
-    int ox = (int)(pix % Wo); long long tmp = pix / Wo; int oy = (int)(tmp % Ho); int n = (int)(tmp / Ho);
+  const unsigned cv = (unsigned)C / V, row = (unsigned)Wo * cv, total = (unsigned)Ho * row;
+  const int n = blockIdx.y;
+  const TI* xn = x + (size_t)n * H * W * xs;
+  TO* yn = y + (size_t)n * Ho * Wo * ys;
+  for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
+    const unsigned oy = idx / row, rem = idx - oy * row, ox = rem / cv, c = (rem - ox * cv) * V;
     int y0, y1, x0, x1; float hl0, hl1, wl0, wl1;
-    bilinear_src(oy, sh, H, y0, y1, hl0, hl1);
-    bilinear_src(ox, sw, W, x0, x1, wl0, wl1);
-    const TI* xn = x + (size_t)n * H * W * xs + c;
-    float4 v00 = ld4(xn + ((size_t)y0 * W + x0) * xs), v01 = ld4(xn + ((size_t)y0 * W + x1) * xs);
-    float4 v10 = ld4(xn + ((size_t)y1 * W + x0) * xs), v11 = ld4(xn + ((size_t)y1 * W + x1) * xs);
-    if (flags & ADD_RELU_IN) { v00 = relu4(v00); v01 = relu4(v01); v10 = relu4(v10); v11 = relu4(v11); }
-    float4 r;
-    r.x = hl0 * (wl0 * v00.x + wl1 * v01.x) + hl1 * (wl0 * v10.x + wl1 * v11.x);
-    r.y = hl0 * (wl0 * v00.y + wl1 * v01.y) + hl1 * (wl0 * v10.y + wl1 * v11.y);
-    r.z = hl0 * (wl0 * v00.z + wl1 * v01.z) + hl1 * (wl0 * v10.z + wl1 * v11.z);
-    r.w = hl0 * (wl0 * v00.w + wl1 * v01.w) + hl1 * (wl0 * v10.w + wl1 * v11.w);
-    if (flags & ADD_RELU_OUT) r = relu4(r);
-    st4(y + (size_t)pix * ys + c, r);
+    bilinear_src((int)oy, sh, H, y0, y1, hl0, hl1);
+    bilinear_src((int)ox, sw, W, x0, x1, wl0, wl1);
+    float v00[V], v01[V], v10[V], v11[V], r[V];
+    VecIO<V>::load(xn + ((size_t)y0 * W + x0) * xs + c, v00);
+    VecIO<V>::load(xn + ((size_t)y0 * W + x1) * xs + c, v01);
+    VecIO<V>::load(xn + ((size_t)y1 * W + x0) * xs + c, v10);
+    VecIO<V>::load(xn + ((size_t)y1 * W + x1) * xs + c, v11);
+    const bool relu_in = flags & ADD_RELU_IN, relu_out = flags & ADD_RELU_OUT;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float a = v00[i], b = v01[i], cc = v10[i], d = v11[i];
+      if (relu_in) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); cc = fmaxf(cc, 0.f); d = fmaxf(d, 0.f); }
+      float o = hl0 * (wl0 * a + wl1 * b) + hl1 * (wl0 * cc + wl1 * d);
+      r[i] = relu_out ? fmaxf(o, 0.f) : o;
+    }
+    VecIO<V>::store(yn + ((size_t)oy * Wo + ox) * ys + c, r);
   }
 }
 
@@ -154,15 +185,22 @@ extern "C" int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, ui
   ADD_CHECK_ARG(x->n == y->n && x->c == y->c);
   ADD_CHECK_SUP(tensor_vec4_ok(x) && tensor_vec4_ok(y));
   float sh = (float)x->h / (float)y->h, sw = (float)x->w / (float)y->w;
-  long long total = (long long)y->n * y->h * y->w * (y->c / 4);
-  int blocks = (int)((total + 255) / 256 < 148ll * 64 ? (total + 255) / 256 : 148ll * 64);
+  ADD_CHECK_SUP((long long)y->h * y->w * (y->c / 4) < (1ll << 31) && y->n < 65536);
+  const bool v8 = x->dtype == ADD_BF16 && y->dtype == ADD_BF16 && x->c % 8 == 0 && x->pix_stride % 8 == 0 &&
+                  y->pix_stride % 8 == 0 && ((uintptr_t)x->ptr % 16) == 0 && ((uintptr_t)y->ptr % 16) == 0;
+  const long long total = (long long)y->h * y->w * (y->c / (v8 ? 8 : 4));
+  long long bx = (total + 255) / 256;
+  const long long cap = (148ll * 32 + y->n - 1) / y->n;
+  if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, (unsigned)y->n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define BL(TI, TO) bilinear_kernel<TI, TO><<<blocks, 256, 0, s>>>((const TI*)x->ptr, (TO*)y->ptr, x->n, x->h, \
+#define BL(TI, TO, V) bilinear_kernel<TI, TO, V><<<grid, 256, 0, s>>>((const TI*)x->ptr, (TO*)y->ptr, x->h, \
     x->w, x->c, x->pix_stride, y->h, y->w, y->pix_stride, sh, sw, flags)
-  if (x->dtype == ADD_F32 && y->dtype == ADD_F32) BL(float, float);
-  else if (x->dtype == ADD_BF16 && y->dtype == ADD_BF16) BL(bf16, bf16);
-  else if (x->dtype == ADD_F32 && y->dtype == ADD_BF16) BL(float, bf16);
-  else if (x->dtype == ADD_BF16 && y->dtype == ADD_F32) BL(bf16, float);
+  if (v8) BL(bf16, bf16, 8);
+  else if (x->dtype == ADD_F32 && y->dtype == ADD_F32) BL(float, float, 4);
+  else if (x->dtype == ADD_BF16 && y->dtype == ADD_BF16) BL(bf16, bf16, 4);
+  else if (x->dtype == ADD_F32 && y->dtype == ADD_BF16) BL(float, bf16, 4);
+  else if (x->dtype == ADD_BF16 && y->dtype == ADD_F32) BL(bf16, float, 4);
   else return ADD_ERR_UNSUPPORTED;
 #undef BL
   ADD_RETURN_LAUNCH();

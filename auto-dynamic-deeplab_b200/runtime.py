@@ -175,6 +175,7 @@ class Builder:
         self.launches: List[Tuple[Callable, tuple, str, dict]] = []
         self.keep: List[object] = []
         self._pool: Dict[tuple, List[torch.Tensor]] = {}
+        self._resized: Dict[tuple, View] = {}
         self.bytes_allocated = 0
 
     # ---- memory ---------------------------------------------------------------------------
@@ -268,6 +269,17 @@ class Builder:
         meta = dict(kernel="bilinear", flops=8 * y.n * y.h * y.w * y.c,
                     bytes=(x.n * x.h * x.w * x.buf.element_size() + y.n * y.h * y.w * y.buf.element_size()) * x.c)
         self._emit(lib.add_bilinear_fwd, (self._d(x), self._d(y), flags), tag, meta)
+
+    def resized(self, x: View, h: int, w: int, tag: str = "bilinear") -> View:
+        """Bilinear resize of a write-once tensor, computed once per (source, size) and shared by every later
+        reader (the dense features of early cells are resized to the same few sizes by many cells, ADD.py:88-91)."""
+        key = (x.buf.data_ptr(), x.c_off, x.c, h, w)
+        v = self._resized.get(key)
+        if v is None:
+            v = self.alloc(x.n, h, w, x.c, x.dtype)
+            self.bilinear(x, v, 0, tag)
+            self._resized[key] = v
+        return v
 
     def gather_images(self, src: torch.Tensor, dst: torch.Tensor, idx: torch.Tensor, tag: str = "gather_images") -> None:
         """dst[j] = src[idx[j]] over whole per-image slabs (dim 0 = image)."""
