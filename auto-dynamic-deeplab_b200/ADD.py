@@ -235,6 +235,7 @@ class ADD(AddModule):
 
     def _prepare(self):
         self.cw_stem0 = ConvWeights(self.stem0[0].weight, self.stem0[1], cin_pad=8)   # 16 B/pixel in bf16: TMA-able
+        self._stem0_packed = None
         self.cw_stem1 = ConvWeights(self.stem1[0].weight, self.stem1[1])
         self.cw_stem2 = ConvWeights(self.stem2[1].weight, self.stem2[2])
         self.cw_low = ConvWeights(self.low_level_conv[1].weight, self.low_level_conv[2])
@@ -255,11 +256,17 @@ class ADD(AddModule):
         self._ensure_prepared()
         if first == 0:
             n, _, H, W = x_nchw.shape
-            img = b.alloc(n, H, W, 8)
-            b.nchw_to_nhwc(x_nchw, 3, img, "ADD.input")
             h1, w1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             t0 = b.alloc(n, h1, w1, 64)
-            b.conv(img, t0, self.cw_stem0, 2, 1, 1, RELU_OUT, "ADD.stem0")
+            if b.dtype == torch.bfloat16 and rt.tc_available():
+                # layout change + bf16 conversion + im2col fused into the tcgen05 stem kernel
+                if self._stem0_packed is None:
+                    self._stem0_packed = rt.pack_stem_tc(self.cw_stem0)
+                b.stem_nchw(x_nchw, t0, self._stem0_packed, self.cw_stem0.bias, RELU_OUT, "ADD.stem0")
+            else:
+                img = b.alloc(n, H, W, 8)
+                b.nchw_to_nhwc(x_nchw, 3, img, "ADD.input")
+                b.conv(img, t0, self.cw_stem0, 2, 1, 1, RELU_OUT, "ADD.stem0")
             # stem2's in-place ReLU mutates stem0 (Q7): every reader sees relu(stem1 output)
             stem0 = b.alloc(n, h1, w1, 64)
             b.conv(t0, stem0, self.cw_stem1, 1, 1, 1, RELU_OUT, "ADD.stem1")

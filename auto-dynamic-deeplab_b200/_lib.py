@@ -45,6 +45,9 @@ _SIGS = {
     "add_conv2d_tc_packed_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "add_conv2d_tc_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "add_conv2d_tc_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
+    "add_stem_tc_packed_bytes": (c_int64, []),
+    "add_stem_tc_pack": (c_int, [c_void_p, c_void_p]),
+    "add_stem_conv3x3s2_nchw_fwd": (c_int, [c_void_p, c_int, c_int, c_int, TP, c_void_p, c_void_p, c_uint32, c_void_p]),
     "add_conv2d_tc_set_halo_mode": (c_int, [c_int]),
     "add_sepconv_half_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_void_p]),
     "add_sepconv_half_tc_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_void_p]),

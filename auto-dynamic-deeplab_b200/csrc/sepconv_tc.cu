@@ -48,7 +48,7 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
 }
 
 template <int K>
-__global__ void __launch_bounds__(SC_MAX_CTHREADS + 32)
+__global__ void __launch_bounds__(SC_MAX_CTHREADS + 32, 2)
 sepconv_half_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ScParams p) {
   constexpr int HR = SC_TH + K - 1, HC = SC_TW + K - 1;
   extern __shared__ uint8_t smem_raw[];
@@ -201,6 +201,7 @@ int launch_sepconv_tc(const CUtensorMap& map_x, const CUtensorMap& map_w, const 
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(sepconv_half_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(sepconv_half_tc_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   });
   sepconv_half_tc_kernel<K><<<(unsigned)grid, p.n_cthreads + 32, smem, s>>>(map_x, map_w, p);
   ADD_RETURN_LAUNCH();

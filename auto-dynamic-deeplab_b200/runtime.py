@@ -123,6 +123,15 @@ class ConvWeights:
         return self._packed
 
 
+def pack_stem_tc(cw: "ConvWeights") -> torch.Tensor:
+    """bf16 [64][64] UMMA image of a folded 3->64 3x3 conv for add_stem_conv3x3s2_nchw_fwd (device tensor)."""
+    w_oihw = cw.w[:, :, :3, :].permute(3, 2, 0, 1).contiguous().cpu()        # [co][ci][ky][kx]
+    assert tuple(w_oihw.shape) == (64, 3, 3, 3)
+    host = torch.empty(int(lib.add_stem_tc_packed_bytes()), dtype=torch.uint8)
+    check(lib.add_stem_tc_pack(w_oihw.data_ptr(), host.data_ptr()), "stem_tc_pack")
+    return host.to(cw.w.device)
+
+
 def bn_scale_shift(bn) -> Tuple[torch.Tensor, torch.Tensor]:
     """Eval-mode BatchNorm as y = x*scale + shift (fp32)."""
     var = bn.running_var.detach().float()
@@ -242,6 +251,17 @@ class Builder:
             self._emit(lib.add_conv2d_fwd,
                        (self._d(x), self._d(y), cw.w.data_ptr(), _ptr(cw.bias), cw.kh, cw.kw,
                         stride, pad, dil, flags), tag, dict(kernel="conv2d_ffma", **meta))
+
+    def stem_nchw(self, src: torch.Tensor, y: View, w_packed: torch.Tensor, bias: torch.Tensor, flags: int,
+                  tag: str = "stem0") -> None:
+        """NCHW fp32 image -> 3x3 s2 conv 3->64 (+BN, ReLU) -> NHWC bf16, one launch (stem_tc.cu)."""
+        n, c, h, w = src.shape
+        assert c == 3 and src.dtype == torch.float32 and src.is_contiguous() and y.dtype == torch.bfloat16
+        self.keep.extend((src, w_packed, bias))
+        p_out = y.n * y.h * y.w
+        self._emit(lib.add_stem_conv3x3s2_nchw_fwd,
+                   (src.data_ptr(), n, h, w, self._d(y), w_packed.data_ptr(), bias.data_ptr(), flags), tag + ":tc",
+                   dict(kernel="stem_conv_tc", flops=2 * p_out * 27 * y.c, bytes=src.numel() * 4 + p_out * y.c * 2 + 64 * 64 * 2))
 
     def sepconv_half(self, x: View, y: View, w_dw: torch.Tensor, pw: ConvWeights, k: int, flags: int,
                      tag: str = "sephalf") -> None:

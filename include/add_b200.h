@@ -85,6 +85,15 @@ int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, const void* 
                       const float* bias, int kh, int kw, int stride, int pad, int dil,
                       uint32_t flags, void* stream);
 
+/* ---- first layer on the bf16 path: NCHW fp32 image -> 3x3 stride-2 conv 3->64 + folded BN (+ReLU) -> NHWC
+ * bf16 in one kernel (ADD.py:154-158 `stem0` applied to the loader's NCHW tensor, eval.py:175): the layout
+ * change, bf16 conversion and im2col happen on the way into shared memory; tcgen05 GEMM; TMA tile store.
+ * w_packed: add_stem_tc_pack() of the fp32 [64][3][3][3] weights (BN scale folded); y: [n,(h-1)/2+1,(w-1)/2+1,64]. */
+int64_t add_stem_tc_packed_bytes(void);
+int add_stem_tc_pack(const float* w_oihw, void* packed_host);
+int add_stem_conv3x3s2_nchw_fwd(const float* x_nchw, int n, int h, int w, const add_tensor_t* y,
+                                const void* w_packed, const float* bias, uint32_t flags, void* stream);
+
 /* A-operand strategy of add_conv2d_tc_fwd: 0 = one TMA tile per tap; 1 = halo rows resident in shared
  * memory, taps addressed through shifted UMMA descriptors (default); 2 = as 1 with descriptor base_offset. */
 int add_conv2d_tc_set_halo_mode(int mode);

@@ -191,3 +191,26 @@ def test_sepconv_half_tc_matches_torch(case, out_dtype):
     assert torch.equal(ybuf[..., y_off + Cout:], y_init[..., y_off + Cout:])
     tol = 2e-3 if out_dtype == torch.float32 else 2 ** -7
     assert util.rel_err(ybuf[..., y_off:y_off + Cout].float(), ref) < tol
+
+
+# ---- fused stem0 (stem_tc.cu): NCHW fp32 image -> conv3x3 s2 + bias + ReLU -> NHWC bf16 -------------------
+@pytest.mark.parametrize("hw", [(32, 64), (33, 65), (48, 300), (17, 513)])
+def test_stem_tc_matches_torch(hw):
+    """vs plain PyTorch fp32 conv on bf16-rounded image and weights (what the kernel multiplies); output is bf16:
+    tolerance 2^-7 max-norm relative."""
+    import torch.nn.functional as F
+    H, W = hw
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    x = torch.randn(2, 3, H, W, generator=g)
+    w = _bf16_exact(torch.randn(64, 3, 3, 3, generator=g) / 27 ** 0.5)
+    bias = torch.randn(64, generator=g)
+    cw = ConvWeights(w.to(DEV))
+    cw.bias = bias.to(DEV)
+    packed = rt.pack_stem_tc(cw)
+    b = Builder(DEV, torch.bfloat16)
+    y = b.alloc(2, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64)
+    y.buf.fill_(float("nan"))
+    b.stem_nchw(x.to(DEV), y, packed, cw.bias, RELU_OUT)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(_bf16_exact(x), w, bias, stride=2, padding=1)).permute(0, 2, 3, 1)
+    assert util.rel_err(y.buf.float(), ref) < 2 ** -7
