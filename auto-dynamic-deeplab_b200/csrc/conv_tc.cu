@@ -29,6 +29,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 1];   // full[s], empty[s], relu[s], accum
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
+  stage_bias(bias_s, p, threadIdx.x, TC_THREADS);
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles: 1024-B aligned
   const uint32_t stage_bytes = TC_A_BYTES + p.b_bytes;
@@ -121,7 +123,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     // ---- epilogue ----
     mbar_wait(bar_accum, 0);
-    epilogue_store(p, tmem_base, warp, lane, n, y0, x0);
+    epilogue_store(p, tmem_base, bias_s, warp, lane, n, y0, x0);
   }
 
   // ---- teardown ----
@@ -155,6 +157,8 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[6 + 2 * TC_MAX_STAGES + 1];   // halo full/empty/relu [2], b_full[s], b_empty[s], accum
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
+  stage_bias(bias_s, p, threadIdx.x, TCH_THREADS);
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t halo_bytes = (uint32_t)(p.taps / p.taps_w) * p.halo_pitch * 128u;    // kh rows
@@ -267,7 +271,7 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       }
     }
     mbar_wait(bar_accum, 0);
-    epilogue_store(p, tmem_base, warp, lane, n, y0, x0);
+    epilogue_store(p, tmem_base, bias_s, warp, lane, n, y0, x0);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

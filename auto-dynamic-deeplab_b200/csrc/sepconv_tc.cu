@@ -29,6 +29,7 @@ struct ScParams {
   const float* w_dw;         // [K][K][C] fp32
   int C, kchunks, n_cthreads, n_items;
   uint32_t halo_bytes;
+  int merged;                // 1: map_x is the merged {W*C, H, N} map in 8-byte elements (contiguous input)
 };
 
 __device__ __forceinline__ float2 bf16x2_to_float2(uint32_t v) {
@@ -54,6 +55,8 @@ sepconv_half_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2];            // [0] TMA landed, [1] accumulator complete
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
+  stage_bias(bias_s, p.e, threadIdx.x, blockDim.x);
 
   const int C = p.C;
   const uint32_t a_base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // kchunks x 16 KB A tiles
@@ -92,7 +95,8 @@ sepconv_half_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   if (is_ctrl) {
     if (lane == 0) {
       mbar_expect_tx(bar_in, p.halo_bytes + (uint32_t)p.kchunks * p.e.b_bytes);
-      tma_load_4d(halo, &map_x, bar_in, 0, x0 - K / 2, y0 - K / 2, n);
+      if (p.merged) tma_load_3d(halo, &map_x, bar_in, (x0 - K / 2) * (C >> 2), y0 - K / 2, n);
+      else tma_load_4d(halo, &map_x, bar_in, 0, x0 - K / 2, y0 - K / 2, n);
       for (int kc = 0; kc < p.kchunks; ++kc) tma_load_3d(b_base + kc * p.e.b_bytes, &map_w, bar_in, 0, 0, kc);
     }
   } else {
@@ -186,7 +190,7 @@ sepconv_half_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     }
   } else if (warp < 4) {
     mbar_wait(bar_mma, 0);
-    epilogue_store(p.e, tmem_base, warp, lane, n, y0, x0);
+    epilogue_store(p.e, tmem_base, bias_s, warp, lane, n, y0, x0);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -195,6 +199,216 @@ sepconv_half_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.e.tmem_cols) : "memory");
   }
 }
+
+// ---- persistent, warp-specialised version (C <= 80) --------------------------------------------------
+// The one-tile-per-CTA kernel above spends most of a CTA's life in its latency chain (TMEM alloc -> TMA
+// round trip -> depthwise -> MMA -> epilogue: ~7 us for ~0.5 us of depthwise work, ncu r01d: issue-active
+// 27-32 %).  Here a CTA loops over tiles with every stage double-buffered, so the chain is paid once:
+//   warp 4      producer   TMA halo of tile i+1 / i+2 into a 2-slot ring (halo_full / halo_empty)
+//   warps 6..   depthwise  thread = (channel pair, column pair), weights live in REGISTERS for the whole
+//                          kernel; ReLU-on-load is a max.bf16x2 per loaded word; output -> A[i&1]
+//   warp 5      MMA        tcgen05.mma A[i&1] x Wpw -> TMEM[i&1]; commit frees A and publishes TMEM
+//   warps 0..3  epilogue   TMEM[i&1] -> +bias -> (+= y) -> ReLU -> global, overlapped with tile i+1's depthwise
+constexpr int SP_MAX_S = 6;                   // max halo ring depth (runtime p.stages <= this)
+constexpr int SP_FIRST_DW_WARP = 6;
+
+struct SpParams {
+  TcParams e;
+  const float* w_dw;
+  int C, kchunks, n_dw_warps, n_tiles;
+  uint32_t halo_bytes;
+  int merged;
+  int stages;                // halo ring depth: how many tiles ahead the TMA producer runs
+};
+
+template <int K, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const SpParams p) {
+  constexpr int HR = SC_TH + K - 1, HC = SC_TW + K - 1;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * SP_MAX_S + 8 + 1];
+  __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
+  stage_bias(bias_s, p.e, threadIdx.x, blockDim.x);
+  const int SP_S = p.stages;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int C = p.C;
+  const uint32_t a_bytes = (uint32_t)p.kchunks * TC_A_BYTES;
+  const uint32_t a_base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // 2 x kchunks x 16 KB
+  const uint32_t b_base = a_base + 2u * a_bytes;                            // kchunks x (n_pad x 128 B)
+  const uint32_t halo_base = b_base + (uint32_t)p.kchunks * p.e.b_bytes;    // SP_S x [HR][HC][C] bf16
+  const uint32_t halo_stride = (p.halo_bytes + 127u) & ~127u;
+  const uint32_t bar_hfull = smem_u32(&bars[0]), bar_hempty = smem_u32(&bars[SP_MAX_S]);
+  const uint32_t bar_afull = smem_u32(&bars[2 * SP_MAX_S]), bar_aempty = smem_u32(&bars[2 * SP_MAX_S + 2]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * SP_MAX_S + 4]), bar_tempty = smem_u32(&bars[2 * SP_MAX_S + 6]);
+  const uint32_t bar_b = smem_u32(&bars[2 * SP_MAX_S + 8]);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t tmem_cols = (uint32_t)p.e.tmem_cols;                        // per accumulator buffer
+
+  if (warp == 4 && lane == 0) {
+    for (int s = 0; s < SP_S; ++s) { mbar_init(bar_hfull + 8 * s, 1); mbar_init(bar_hempty + 8 * s, p.n_dw_warps); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_afull + 8 * b, p.n_dw_warps); mbar_init(bar_aempty + 8 * b, 1);
+      mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4);
+    }
+    mbar_init(bar_b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_smem)), "r"(2u * tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+  const int tiles_per_img = p.e.tiles_x * p.e.tiles_y;
+
+  if (warp == 4) {
+    // ===== producer =====
+    if (lane == 0) {
+      mbar_expect_tx(bar_b, (uint32_t)p.kchunks * p.e.b_bytes);
+      for (int kc = 0; kc < p.kchunks; ++kc) tma_load_3d(b_base + kc * p.e.b_bytes, &map_w, bar_b, 0, 0, kc);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % SP_S; const uint32_t ph = (uint32_t)(it / SP_S) & 1u;
+        const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+        const int ty = r / p.e.tiles_x, tx = r - ty * p.e.tiles_x;
+        mbar_wait_relaxed(bar_hempty + 8 * s, ph ^ 1u);
+        mbar_expect_tx(bar_hfull + 8 * s, p.halo_bytes);
+        if (p.merged) tma_load_3d(halo_base + s * halo_stride, &map_x, bar_hfull + 8 * s, (tx * SC_TW - K / 2) * (C >> 2), ty * SC_TH - K / 2, n);
+        else tma_load_4d(halo_base + s * halo_stride, &map_x, bar_hfull + 8 * s, 0, tx * SC_TW - K / 2, ty * SC_TH - K / 2, n);
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.e.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      mbar_wait(bar_b, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1; const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(bar_afull + 8 * b, ph);
+        mbar_wait(bar_tempty + 8 * b, ph ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          const int krem = C - kc * TC_BK;
+          const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
+          const uint64_t adesc = make_kmajor_sw128_desc(a_base + b * a_bytes + kc * TC_A_BYTES);
+          const uint64_t bdesc = make_kmajor_sw128_desc(b_base + kc * p.e.b_bytes);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base + b * tmem_cols, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_aempty + 8 * b);      // A[b] may be overwritten once these MMAs have read it
+        umma_commit(bar_tfull + 8 * b);       // accumulator b complete
+      }
+    }
+  } else if (warp < 4) {
+    // ===== epilogue =====
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1; const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+      const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+      const int ty = r / p.e.tiles_x, tx = r - ty * p.e.tiles_x;
+      mbar_wait_relaxed(bar_tfull + 8 * b, ph);
+      epilogue_store(p.e, tmem_base + b * tmem_cols, bias_s, warp, lane, n, ty * SC_TH, tx * SC_TW);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+    }
+  } else if (warp < SP_FIRST_DW_WARP + p.n_dw_warps) {
+    // ===== depthwise =====
+    const int dt = tid - SP_FIRST_DW_WARP * 32;
+    const int cpairs = C >> 1;
+    const int cp = dt % cpairs, xp = dt / cpairs;
+    const bool relu_in = (p.e.flags & ADD_RELU_IN) != 0;
+    float2 w[K * K];
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) w[i] = __ldg(reinterpret_cast<const float2*>(p.w_dw + (size_t)i * C) + cp);
+    {  // zero the K-padding columns of the last chunk of both A buffers (read by the MMA, never written below)
+      const int c_last = C - (p.kchunks - 1) * TC_BK;
+      const int u0 = c_last >> 3, u1 = ((c_last + 15) >> 4) << 1;
+      const int nthr = p.n_dw_warps * 32;
+      for (int i = dt; i < 2 * TC_BM * (u1 - u0); i += nthr) {
+        const int b = i / (TC_BM * (u1 - u0)), j = i - b * TC_BM * (u1 - u0);
+        const int m = j / (u1 - u0), u = u0 + j % (u1 - u0);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};"
+                     ::"r"(a_base + b * a_bytes + (uint32_t)(p.kchunks - 1) * TC_A_BYTES + m * 128 + ((u ^ (m & 7)) << 4)), "r"(0u) : "memory");
+      }
+    }
+    const uint32_t hoff = (uint32_t)((2 * xp) * C + 2 * cp) * 2u;
+    const uint32_t a_off = (uint32_t)(cp >> 5) * TC_A_BYTES;
+    const uint32_t cbyte = (uint32_t)(cp & 31) * 4u;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int s = it % SP_S; const uint32_t hph = (uint32_t)(it / SP_S) & 1u;
+      const int b = it & 1; const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(bar_hfull + 8 * s, hph);
+      mbar_wait(bar_aempty + 8 * b, aph ^ 1u);
+      const uint32_t hsrc = halo_base + s * halo_stride + hoff;
+      const uint32_t a_tile = a_base + b * a_bytes + a_off;
+      float2 acc0[K], acc1[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) acc0[i] = acc1[i] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < HR; ++r) {
+        float2 in[K + 1];
+#pragma unroll
+        for (int j = 0; j <= K; ++j) {
+          uint32_t v = lds32(hsrc + (uint32_t)((r * HC + j) * C) * 2u);
+          if (relu_in) asm("max.bf16x2 %0, %0, %1;" : "+r"(v) : "r"(0u));
+          in[j] = bf16x2_to_float2(v);
+        }
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          const int o = r - ky;
+          if (o < 0 || o >= SC_TH) continue;
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            acc0[o % K] = __ffma2_rn(w[ky * K + kx], in[kx], acc0[o % K]);
+            acc1[o % K] = __ffma2_rn(w[ky * K + kx], in[kx + 1], acc1[o % K]);
+          }
+        }
+        const int oc = r - (K - 1);
+        if (oc >= 0) {
+          const int m0 = oc * SC_TW + 2 * xp, m1 = m0 + 1;
+          sts32(a_tile + m0 * 128 + ((((cbyte >> 4) ^ (m0 & 7)) << 4) | (cbyte & 15u)), float2_to_bf16x2(acc0[oc % K]));
+          sts32(a_tile + m1 * 128 + ((((cbyte >> 4) ^ (m1 & 7)) << 4) | (cbyte & 15u)), float2_to_bf16x2(acc1[oc % K]));
+          acc0[oc % K] = acc1[oc % K] = make_float2(0.f, 0.f);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar_afull + 8 * b); mbar_arrive(bar_hempty + 8 * s); }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * tmem_cols) : "memory");
+  }
+}
+
+template <int K, int MAXT, int MINB>
+int launch_sepconv_tc_persistent(const CUtensorMap& map_x, const CUtensorMap& map_w, const SpParams& p, int grid, int threads,
+                                 size_t smem, cudaStream_t s) {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(sepconv_half_tc_persistent_kernel<K, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(sepconv_half_tc_persistent_kernel<K, MAXT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  });
+  sepconv_half_tc_persistent_kernel<K, MAXT, MINB><<<grid, threads, smem, s>>>(map_x, map_w, p);
+  ADD_RETURN_LAUNCH();
+}
+
+int g_sepconv_merged = 1;  // merged {W*C} halo tensor map for contiguous inputs (A/B switch: mode bit 1)
+int g_sepconv_stages = 0;  // 0 = auto
+int g_sepconv_mode = 1;    // 1 = persistent pipeline where it fits (default), 0 = one tile per CTA
 
 template <int K>
 int launch_sepconv_tc(const CUtensorMap& map_x, const CUtensorMap& map_w, const ScParams& p, long long grid, size_t smem, cudaStream_t s) {
@@ -246,7 +460,19 @@ extern "C" int add_sepconv_half_tc_fwd(const add_tensor_t* x, const add_tensor_t
   ADD_CHECK_SUP(smem <= 220u * 1024u);
 
   CUtensorMap map_x, map_w;
-  {
+  // Contiguous input (not a channel slice): merge W and C into one dimension of 8-byte elements, so a halo row is
+  // ONE contiguous box row (HC*C*2 bytes) instead of HC separate C*2-byte rows — the TMA unit's cost is per box row.
+  // Out-of-image columns/rows are still zero-filled (they are out of bounds of the merged dimension too).
+  p.merged = (g_sepconv_merged && x->pix_stride == C && HC * C / 4 <= 256) ? 1 : 0;
+  if (p.merged) {
+    cuuint64_t dims[3] = {(cuuint64_t)x->w * C / 4, (cuuint64_t)x->h, (cuuint64_t)x->n};
+    cuuint64_t strides[2] = {(cuuint64_t)x->w * C * 2, (cuuint64_t)x->h * x->w * C * 2};
+    cuuint32_t box[3] = {(cuuint32_t)(HC * C / 4), (cuuint32_t)HR, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, x->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return ADD_ERR_UNSUPPORTED;
+  } else {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
     cuuint64_t strides[3] = {(cuuint64_t)x->pix_stride * 2, (cuuint64_t)x->w * x->pix_stride * 2,
                              (cuuint64_t)x->h * x->w * x->pix_stride * 2};
@@ -269,5 +495,44 @@ extern "C" int add_sepconv_half_tc_fwd(const add_tensor_t* x, const add_tensor_t
   const long long grid = (long long)p.e.tiles_x * p.e.tiles_y * y->n;
   ADD_CHECK_SUP(grid < (1ll << 31));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (g_sepconv_mode == 1 && C <= 80) {
+    SpParams q;
+    std::memset(&q, 0, sizeof(q));
+    q.e = p.e; q.w_dw = w_dw; q.C = C; q.kchunks = p.kchunks; q.n_dw_warps = C / 8; q.n_tiles = (int)grid;
+    q.halo_bytes = p.halo_bytes; q.merged = p.merged;
+    const size_t hstride = (q.halo_bytes + 127u) & ~127u;
+    const size_t fixed = 2 * (size_t)q.kchunks * TC_A_BYTES + (size_t)q.kchunks * q.e.b_bytes + 1024;
+    const int threads = (SP_FIRST_DW_WARP + q.n_dw_warps) * 32;
+    // ring depth: as deep as fits two CTAs per SM (<= 110 KB each) when the CTA is small enough for that,
+    // else as deep as fits one CTA (<= 200 KB); at least 2
+    const bool small = threads <= 352 && 4 * q.e.tmem_cols <= 512;
+    const size_t budget = (small && fixed + 2 * hstride <= 110u * 1024u) ? 110u * 1024u : 200u * 1024u;
+    int stages = (int)((budget - fixed) / hstride);
+    if (g_sepconv_stages > 0) stages = g_sepconv_stages;
+    if (stages > SP_MAX_S) stages = SP_MAX_S;
+    if (stages < 2) stages = 2;
+    q.stages = stages;
+    const size_t psmem = fixed + (size_t)stages * hstride;
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    if (psmem <= 200u * 1024u && 2 * q.e.tmem_cols <= 512) {
+      const bool two = threads <= 352 && psmem <= 110u * 1024u && 4 * q.e.tmem_cols <= 512;
+      long long g = (long long)sms * (two ? 2 : 1);
+      if (g > grid) g = grid;
+      if (two) return k == 3 ? launch_sepconv_tc_persistent<3, 352, 2>(map_x, map_w, q, (int)g, threads, psmem, s)
+                             : launch_sepconv_tc_persistent<5, 352, 2>(map_x, map_w, q, (int)g, threads, psmem, s);
+      return k == 3 ? launch_sepconv_tc_persistent<3, 512, 1>(map_x, map_w, q, (int)g, threads, psmem, s)
+                    : launch_sepconv_tc_persistent<5, 512, 1>(map_x, map_w, q, (int)g, threads, psmem, s);
+    }
+  }
   return k == 3 ? launch_sepconv_tc<3>(map_x, map_w, p, grid, smem, s) : launch_sepconv_tc<5>(map_x, map_w, p, grid, smem, s);
+}
+
+/* 1 = persistent warp-specialised pipeline where it fits (default); 0 = one tile per CTA (kept for A/B runs). */
+extern "C" int add_sepconv_tc_set_mode(int mode) {
+  if (mode >= 16) { g_sepconv_stages = (mode >> 4) & 15; mode &= 15; }      // bits 4..7: forced halo ring depth (tuning)
+  if (mode < 0 || mode > 3) return ADD_ERR_BAD_ARG;
+  g_sepconv_mode = mode & 1;
+  g_sepconv_merged = (mode & 2) ? 0 : 1;      // bit 1 set = per-pixel halo rows even for contiguous inputs
+  return ADD_OK;
 }

@@ -110,9 +110,30 @@ __device__ __forceinline__ void relu_sweep(uint32_t base, uint32_t bytes, int et
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
 }
 
+// Folded-BN bias staged once per CTA in shared memory (zero past Cout up to n_pad), so the epilogue reads it with
+// broadcast 16-byte loads instead of one predicated global load per output element (ncu r01g: that single line
+// was 16 % of all warp instructions of the SepConv kernel — more than its FFMA2s).
+constexpr int TC_MAX_NPAD = 256;
+__device__ __forceinline__ void stage_bias(float* bias_s, const TcParams& p, int tid, int nthreads) {
+  for (int i = tid; i < p.n_pad; i += nthreads) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+}
+
+// spin on an mbarrier with a short sleep between polls: for waiters with slack (producers, epilogue warps), so
+// their polling does not take issue slots from the compute warps of the same SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
+
 // TMEM accumulator -> +bias -> (+= y) -> ReLU -> bf16/fp32 stores.  Called by the four epilogue warps
-// after the accumulator-complete barrier.
-__device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_base, int warp, int lane, int n, int y0, int x0) {
+// after the accumulator-complete barrier.  bias_s: shared-memory bias (stage_bias).
+__device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_base, const float* bias_s, int warp, int lane,
+                                               int n, int y0, int x0) {
   const int BW = 1 << p.bw_log2;
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int q = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -128,9 +149,10 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_
     if (!valid) continue;
     float f[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int co = c0 + j;
-      f[j] = __uint_as_float(v[j]) + ((p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.f);
+    for (int j = 0; j < 4; ++j) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
+      f[4 * j] = __uint_as_float(v[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+      f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
     }
     if (p.y_is_f32) {
       float* dst = static_cast<float*>(p.y) + pix * p.ys + c0;
@@ -156,24 +178,24 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         if (c0 + 8 * g + 8 <= p.Cout) {
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = f[8 * g + j];
           if (accum) {
-            uint4 old = *reinterpret_cast<const uint4*>(dst + 8 * g);
-            const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+            const uint4 old = *reinterpret_cast<const uint4*>(dst + 8 * g);
+            const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { float2 t2 = __bfloat1622float2(ob[j]); o[2 * j] += t2.x; o[2 * j + 1] += t2.y; }
+            for (int j = 0; j < 4; ++j) {
+              f[8 * g + 2 * j] += __uint_as_float(ow[j] << 16);
+              f[8 * g + 2 * j + 1] += __uint_as_float(ow[j] & 0xffff0000u);
+            }
           }
-          if (relu_out) {
+          uint32_t pk[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * g + 2 * j], f[8 * g + 2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            // ReLU on the rounded pair: rounding is monotonic and keeps the sign, so this equals round(relu(x))
+            if (relu_out) asm("max.bf16x2 %0, %0, %1;" : "+r"(pk[j]) : "r"(0u));
           }
-          uint4 pk;
-          __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pb[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
-          *reinterpret_cast<uint4*>(dst + 8 * g) = pk;
+          *reinterpret_cast<uint4*>(dst + 8 * g) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         } else {
           for (int j = 8 * g; j < 8 * g + 8; ++j)
             if (c0 + j < p.Cout) {
@@ -186,7 +208,6 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_
       }
     }
   }
-  
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

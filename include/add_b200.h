@@ -112,6 +112,9 @@ int add_sepconv_half_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, const 
                             const void* w_pw_packed, const float* bias, int k, uint32_t flags,
                             void* stream);
 
+/* add_sepconv_half_tc_fwd scheduling: 1 = persistent warp-specialised pipeline (default), 0 = one tile per CTA. */
+int add_sepconv_tc_set_mode(int mode);
+
 /* ---- bilinear resize, align_corners=False (F.interpolate: ADD.py:76,84,89,317; decoder.py:24) */
 int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, uint32_t flags, void* stream);
 

@@ -141,6 +141,11 @@ SEP_CASES = [
     (24, 24, 3, 7, 9, RELU_IN),
     (64, 48, 5, 10, 33, RELU_IN | RELU_OUT),
     (200, 40, 3, 5, 18, 0),
+    # more tiles than resident CTAs: the persistent kernel's multi-tile loop, ring wrap-around and phase flips
+    (40, 40, 5, 100, 253, RELU_IN | ACCUMULATE),
+    (40, 40, 3, 131, 250, RELU_IN | RELU_OUT),
+    (80, 80, 3, 90, 127, RELU_IN | RELU_OUT),
+    (80, 80, 5, 70, 130, ACCUMULATE),
 ]
 
 
@@ -163,14 +168,16 @@ def _sep_reference(x, w_dw, w_pw, bias, k, flags, y_init):
 
 
 @pytest.mark.parametrize("case", SEP_CASES, ids=[f"c{c[0]}-{c[1]}_k{c[2]}_{c[3]}x{c[4]}_f{c[5]}" for c in SEP_CASES])
+@pytest.mark.parametrize("mode", [1, 0, 3], ids=["persistent", "tile_per_cta", "persistent_unmerged"])
+@pytest.mark.parametrize("contig", [False, True], ids=["slice_in", "contig_in"])
 @pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
-def test_sepconv_half_tc_matches_torch(case, out_dtype):
+def test_sepconv_half_tc_matches_torch(case, out_dtype, mode, contig):
     """Tolerance: fp32 output 2e-3, bf16 output 2^-7 (max-norm relative).  The depthwise result is
     rounded to bf16 before the pointwise GEMM in both; fp32 summation order may flip a rounding."""
     C, Cout, k, H, W, flags = case
     g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
     n = 2
-    x_ctot, c_off = C + 16, 8
+    x_ctot, c_off = (C, 0) if contig else (C + 16, 8)     # contiguous input -> merged {W*C} halo tensor map
     x_buf = torch.randn(n, H, W, x_ctot, generator=g).to(torch.bfloat16).to(DEV)
     w_dw = (torch.randn(k, k, C, generator=g) / k).to(DEV)
     w_pw = _bf16_exact(torch.randn(C, Cout, generator=g) / C ** 0.5).to(DEV)     # [Cin][Cout]
@@ -184,8 +191,13 @@ def test_sepconv_half_tc_matches_torch(case, out_dtype):
     ybuf = y_init.clone()
     b.sepconv_half(View(x_buf, c_off, C), View(ybuf, y_off, Cout), w_dw.contiguous(), cw, k, flags)
     assert [l[3]["kernel"] for l in b.launches] == ["sepconv_half_tc"]
-    rt.Plan(b).run_eager()
-    torch.cuda.synchronize()
+    from add_b200._lib import lib as _lib
+    assert _lib.add_sepconv_tc_set_mode(mode) == 0
+    try:
+        rt.Plan(b).run_eager()
+        torch.cuda.synchronize()
+    finally:
+        _lib.add_sepconv_tc_set_mode(1)
     ref = _sep_reference(x_buf[..., c_off:c_off + C], w_dw, w_pw, bias, k, flags, y_init[..., y_off:y_off + Cout])
     assert torch.equal(ybuf[..., :y_off], y_init[..., :y_off])
     assert torch.equal(ybuf[..., y_off + Cout:], y_init[..., y_off + Cout:])
