@@ -126,7 +126,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
-    __nanosleep(64);
+    __nanosleep(128);
   }
 }
 
@@ -163,7 +163,7 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_
           if (accum) { float4 old = *reinterpret_cast<const float4*>(dst + 4 * g); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
           if (relu_out) o = relu4(o);
           *reinterpret_cast<float4*>(dst + 4 * g) = o;
-        } else {
+        } else if (c0 + 4 * g < p.Cout) {
           for (int j = 4 * g; j < 4 * g + 4; ++j)
             if (c0 + j < p.Cout) {
               float o = f[j];
@@ -196,7 +196,7 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_
             if (relu_out) asm("max.bf16x2 %0, %0, %1;" : "+r"(pk[j]) : "r"(0u));
           }
           *reinterpret_cast<uint4*>(dst + 8 * g) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        } else {
+        } else if (c0 + 8 * g < p.Cout) {
           for (int j = 8 * g; j < 8 * g + 8; ++j)
             if (c0 + j < p.Cout) {
               float o = f[j];

@@ -162,6 +162,19 @@ if _os.environ.get("ADD_TC_HALO_MODE"):
     set_tc_halo_mode(int(_os.environ["ADD_TC_HALO_MODE"]))
 
 
+_GRAPH_STREAMS = {"n": int(_os.environ.get("ADD_GRAPH_STREAMS", "4"))}
+
+
+def graph_streams() -> int:
+    return _GRAPH_STREAMS["n"]
+
+
+def set_graph_streams(n: int) -> None:
+    """How many streams a captured plan's launch DAG is spread over (1 = one serial chain)."""
+    _GRAPH_STREAMS["n"] = max(1, int(n))
+    bump_generation()
+
+
 def tc_available() -> bool:
     if _TC_STATE["probed"] is None:
         _TC_STATE["probed"] = lib.add_conv2d_tc_packed_bytes(64, 64, 1, 1) > 0
@@ -171,6 +184,20 @@ def tc_available() -> bool:
 def set_tc_enabled(flag: bool) -> None:
     _TC_STATE["enabled"] = bool(flag)
     bump_generation()
+
+
+def _res(obj) -> Optional[tuple]:
+    """Memory footprint of a launch operand for dependency tracking: (buffer base pointer, channel lo, channel hi).
+    A View is a channel range of its buffer; a raw tensor covers its whole allocation."""
+    if obj is None:
+        return None
+    if isinstance(obj, View):
+        return (obj.buf.data_ptr(), obj.c_off, obj.c_off + obj.c)
+    return (obj.data_ptr(), 0, 1 << 30)
+
+
+def _overlap(a: tuple, b: tuple) -> bool:
+    return a[0] == b[0] and a[1] < b[2] and b[1] < a[2]
 
 
 class Builder:
@@ -195,6 +222,10 @@ class Builder:
         return View(t)
 
     def scratch(self, n: int, h: int, w: int, c: int, dtype: Optional[torch.dtype] = None) -> View:
+        if self.record:
+            # recorded plans never recycle temporaries: a reused buffer is a false (write-after-read) dependency
+            # that would serialise otherwise independent launches of the captured graph; HBM is not the constraint
+            return self.alloc(n, h, w, c, dtype)
         key = (n, h, w, c, dtype or self.dtype)
         pool = self._pool.setdefault(key, [])
         if pool:
@@ -202,6 +233,8 @@ class Builder:
         return self.alloc(n, h, w, c, dtype)
 
     def release(self, v: View) -> None:
+        if self.record:
+            return
         b = v.buf
         self._pool.setdefault((b.shape[0], b.shape[1], b.shape[2], b.shape[3], b.dtype), []).append(b)
 
@@ -212,11 +245,15 @@ class Builder:
         return t
 
     # ---- launch plumbing ------------------------------------------------------------------
-    def _emit(self, fn, args: tuple, tag: str, meta: Optional[dict] = None) -> None:
+    def _emit(self, fn, args: tuple, tag: str, meta: Optional[dict] = None, reads=(), writes=()) -> None:
         """meta = {"kernel": name, "flops": algorithmic FLOPs, "bytes": algorithmic HBM bytes} of this
-        launch (SURVEY §8d formulas) — what bench.py's roofline is computed from."""
+        launch (SURVEY §8d formulas) — what bench.py's roofline is computed from.  reads / writes: the Views /
+        tensors the launch touches, from which `Plan` derives the launch DAG for multi-stream graph capture."""
         if self.record:
-            self.launches.append((fn, args, tag, meta or {"kernel": tag, "flops": 0, "bytes": 0}))
+            meta = dict(meta or {"kernel": tag, "flops": 0, "bytes": 0})
+            meta["reads"] = [r for r in map(_res, reads) if r is not None]
+            meta["writes"] = [r for r in map(_res, writes) if r is not None]
+            self.launches.append((fn, args, tag, meta))
         else:
             s = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             check(fn(*args, s), tag)
@@ -246,11 +283,13 @@ class Builder:
         if use_tc:
             self._emit(lib.add_conv2d_tc_fwd,
                        (self._d(x), self._d(y), cw.packed_tc().data_ptr(), _ptr(cw.bias), cw.kh, cw.kw,
-                        stride, pad, dil, flags), tag + ":tc", dict(kernel="conv2d_tc", **meta))
+                        stride, pad, dil, flags), tag + ":tc", dict(kernel="conv2d_tc", **meta),
+                       reads=(x, y) if flags & ACCUMULATE else (x,), writes=(y,))
         else:
             self._emit(lib.add_conv2d_fwd,
                        (self._d(x), self._d(y), cw.w.data_ptr(), _ptr(cw.bias), cw.kh, cw.kw,
-                        stride, pad, dil, flags), tag, dict(kernel="conv2d_ffma", **meta))
+                        stride, pad, dil, flags), tag, dict(kernel="conv2d_ffma", **meta),
+                       reads=(x, y) if flags & ACCUMULATE else (x,), writes=(y,))
 
     def stem_nchw(self, src: torch.Tensor, y: View, w_packed: torch.Tensor, bias: torch.Tensor, flags: int,
                   tag: str = "stem0") -> None:
@@ -261,7 +300,8 @@ class Builder:
         p_out = y.n * y.h * y.w
         self._emit(lib.add_stem_conv3x3s2_nchw_fwd,
                    (src.data_ptr(), n, h, w, self._d(y), w_packed.data_ptr(), bias.data_ptr(), flags), tag + ":tc",
-                   dict(kernel="stem_conv_tc", flops=2 * p_out * 27 * y.c, bytes=src.numel() * 4 + p_out * y.c * 2 + 64 * 64 * 2))
+                   dict(kernel="stem_conv_tc", flops=2 * p_out * 27 * y.c, bytes=src.numel() * 4 + p_out * y.c * 2 + 64 * 64 * 2),
+                   reads=(src,), writes=(y,))
 
     def sepconv_half(self, x: View, y: View, w_dw: torch.Tensor, pw: ConvWeights, k: int, flags: int,
                      tag: str = "sephalf") -> None:
@@ -279,16 +319,17 @@ class Builder:
         if use_tc:
             self._emit(lib.add_sepconv_half_tc_fwd,
                        (self._d(x), self._d(y), w_dw.data_ptr(), pw.packed_tc().data_ptr(), _ptr(pw.bias), k, flags),
-                       tag + ":tc", dict(kernel="sepconv_half_tc", **meta))
+                       tag + ":tc", dict(kernel="sepconv_half_tc", **meta),
+                       reads=(x, y) if flags & ACCUMULATE else (x,), writes=(y,))
         else:
             self._emit(lib.add_sepconv_half_fwd,
                        (self._d(x), self._d(y), w_dw.data_ptr(), pw.w.data_ptr(), _ptr(pw.bias), k, flags), tag,
-                       dict(kernel="sepconv_half", **meta))
+                       dict(kernel="sepconv_half", **meta), reads=(x, y) if flags & ACCUMULATE else (x,), writes=(y,))
 
     def bilinear(self, x: View, y: View, flags: int = 0, tag: str = "bilinear") -> None:
         meta = dict(kernel="bilinear", flops=8 * y.n * y.h * y.w * y.c,
                     bytes=(x.n * x.h * x.w * x.buf.element_size() + y.n * y.h * y.w * y.buf.element_size()) * x.c)
-        self._emit(lib.add_bilinear_fwd, (self._d(x), self._d(y), flags), tag, meta)
+        self._emit(lib.add_bilinear_fwd, (self._d(x), self._d(y), flags), tag, meta, reads=(x,), writes=(y,))
 
     def resized(self, x: View, h: int, w: int, tag: str = "bilinear") -> View:
         """Bilinear resize of a write-once tensor, computed once per (source, size) and shared by every later
@@ -307,26 +348,30 @@ class Builder:
         per = src[0].numel() * src.element_size()
         self.keep.extend((src, dst, idx))
         self._emit(lib.add_gather_images, (src.data_ptr(), dst.data_ptr(), idx.data_ptr(), dst.shape[0], per), tag,
-                   dict(kernel="gather_images", flops=0, bytes=2 * per * dst.shape[0]))
+                   dict(kernel="gather_images", flops=0, bytes=2 * per * dst.shape[0]), reads=(src, idx), writes=(dst,))
 
     def gap(self, x: View, out: torch.Tensor, flags: int = 0, tag: str = "gap") -> None:
         nbytes = lib.add_global_avgpool_workspace_bytes(x.n, x.h, x.w, x.c)
         ws = self.raw((max(int(nbytes), 16),), torch.uint8)
         self._emit(lib.add_global_avgpool_fwd, (self._d(x), out.data_ptr(), flags, ws.data_ptr(), nbytes), tag,
-                   dict(kernel="global_avgpool", flops=x.n * x.h * x.w * x.c, bytes=x.n * x.h * x.w * x.c * x.buf.element_size()))
+                   dict(kernel="global_avgpool", flops=x.n * x.h * x.w * x.c, bytes=x.n * x.h * x.w * x.c * x.buf.element_size()),
+                   reads=(x,), writes=(out, ws))
 
     def nchw_to_nhwc(self, src: torch.Tensor, c_src: int, y: View, tag: str = "nchw2nhwc") -> None:
         self.keep.append(src)
         self._emit(lib.add_nchw_to_nhwc, (src.data_ptr(), c_src, self._d(y)), tag,
-                   dict(kernel="nchw_to_nhwc", flops=0, bytes=src.numel() * 4 + y.n * y.h * y.w * y.c * y.buf.element_size()))
+                   dict(kernel="nchw_to_nhwc", flops=0, bytes=src.numel() * 4 + y.n * y.h * y.w * y.c * y.buf.element_size()),
+                   reads=(src,), writes=(y,))
 
     def nhwc_to_nchw(self, x: View, dst: torch.Tensor, tag: str = "nhwc2nchw") -> None:
         self._emit(lib.add_nhwc_to_nchw, (self._d(x), dst.data_ptr()), tag,
-                   dict(kernel="nhwc_to_nchw", flops=0, bytes=dst.numel() * 4 + x.n * x.h * x.w * x.c * x.buf.element_size()))
+                   dict(kernel="nhwc_to_nchw", flops=0, bytes=dst.numel() * 4 + x.n * x.h * x.w * x.c * x.buf.element_size()),
+                   reads=(x,), writes=(dst,))
 
     def upsample_logits(self, x: View, dst: torch.Tensor, H: int, W: int, tag: str = "upsample_logits") -> None:
         self._emit(lib.add_upsample_logits_nchw, (self._d(x), dst.data_ptr(), H, W), tag,
-                   dict(kernel="upsample_logits_nchw", flops=8 * dst.numel(), bytes=4 * (x.n * x.h * x.w * x.c + dst.numel())))
+                   dict(kernel="upsample_logits_nchw", flops=8 * dst.numel(), bytes=4 * (x.n * x.h * x.w * x.c + dst.numel())),
+                   reads=(x,), writes=(dst,))
 
     def upsample_argmax(self, x: View, H: int, W: int, gt: Optional[torch.Tensor], pred: Optional[torch.Tensor],
                         cm: Optional[torch.Tensor], ent: Optional[torch.Tensor], tag: str = "upsample_argmax") -> None:
@@ -335,12 +380,14 @@ class Builder:
         self._emit(lib.add_upsample_argmax_fwd,
                    (self._d(x), H, W, _ptr(gt), _ptr(pred), _ptr(cm), _ptr(ent), ws.data_ptr(), nbytes), tag,
                    dict(kernel="upsample_argmax", flops=8 * x.n * H * W * x.c,
-                        bytes=4 * x.n * x.h * x.w * x.c + x.n * H * W * (8 * (gt is not None) + 8 * (pred is not None))))
+                        bytes=4 * x.n * x.h * x.w * x.c + x.n * H * W * (8 * (gt is not None) + 8 * (pred is not None))),
+                   reads=(x, gt), writes=(pred, cm, ent, ws))
 
     def edm_mlp(self, pooled: torch.Tensor, n: int, ws: Sequence[torch.Tensor], out: torch.Tensor,
                 tag: str = "edm_mlp") -> None:
         self.keep.extend(ws)
-        self._emit(lib.add_edm_mlp_fwd, (pooled.data_ptr(), n, *[t.data_ptr() for t in ws], out.data_ptr()), tag)
+        self._emit(lib.add_edm_mlp_fwd, (pooled.data_ptr(), n, *[t.data_ptr() for t in ws], out.data_ptr()), tag,
+                   reads=(pooled,), writes=(out,))
 
 
 class Plan:
@@ -378,14 +425,101 @@ class Plan:
             if rc != 0:
                 check(rc, tag)
         stream.synchronize()
-        return [dict(tag=tag, ms=e0.elapsed_time(e1), **meta) for (_, _, tag, meta), (e0, e1) in zip(self.launches, evs)]
+        return [dict(tag=tag, ms=e0.elapsed_time(e1), **{k: v for k, v in meta.items() if k not in ("reads", "writes")})
+                for (_, _, tag, meta), (e0, e1) in zip(self.launches, evs)]
 
-    def capture(self) -> None:
+    # ---- launch DAG -------------------------------------------------------------------------
+    def dependencies(self) -> List[List[int]]:
+        """deps[i] = indices of the earlier launches launch i must wait for (RAW, WAW and WAR on channel ranges)."""
+        deps: List[List[int]] = []
+        hist: List[Tuple[tuple, int, bool]] = []            # (resource, launch index, is_write), newest last
+        barrier = -1
+        for i, (_, _, _, meta) in enumerate(self.launches):
+            reads, writes = meta.get("reads", []), meta.get("writes", [])
+            if not reads and not writes:                     # unknown footprint: full barrier
+                deps.append(list(range(i)))
+                barrier = i
+                continue
+            d = set() if barrier < 0 else {barrier}
+            for r in reads:
+                for res, j, is_w in hist:
+                    if is_w and _overlap(r, res):
+                        d.add(j)
+            for w in writes:
+                for res, j, _ in hist:
+                    if _overlap(w, res):
+                        d.add(j)
+            deps.append(sorted(d))
+            hist += [(r, i, False) for r in reads] + [(w, i, True) for w in writes]
+        return deps
+
+    def schedule(self, n_streams: int = 4) -> List[Tuple[int, List[int]]]:
+        """Greedy list scheduling of the launch DAG onto `n_streams` streams, in program order.
+        Returns [(stream index, [dependencies that live on OTHER streams])] per launch.  A launch continues the
+        stream of its newest dependency when that dependency is still the tail of its stream (chains stay put);
+        otherwise it goes to the stream whose tail is oldest (round-robin over idle lanes)."""
+        deps = self.dependencies()
+        stream_of: List[int] = []
+        tail = [-1] * n_streams                               # last launch index per stream
+        out = []
+        for i, d in enumerate(deps):
+            st = None
+            if not self.launches[i][3].get("reads") and not self.launches[i][3].get("writes"):
+                st = 0
+            for j in sorted(d, reverse=True):
+                if st is None and tail[stream_of[j]] == j:
+                    st = stream_of[j]
+                    break
+            if st is None:
+                st = min(range(n_streams), key=lambda k: tail[k])
+            # a dependency on the same stream is implied by stream order; so is one covered transitively by a
+            # later launch of that other stream that we already wait for — keep only the newest per other stream
+            newest = {}
+            for j in d:
+                sj = stream_of[j]
+                if sj != st:
+                    newest[sj] = max(newest.get(sj, -1), j)
+            out.append((st, sorted(newest.values())))
+            stream_of.append(st)
+            tail[st] = i
+        return out
+
+    def _run_streams(self, n_streams: int) -> None:
+        """Issue the launches on several streams with event edges (inside a CUDA-graph capture: the graph gets
+        the launch DAG's parallel branches instead of one serial chain)."""
+        dev = self.builder.device
+        main = torch.cuda.current_stream(dev)
+        streams = [main] + [torch.cuda.Stream(dev) for _ in range(n_streams - 1)]
+        for st in streams[1:]:
+            st.wait_stream(main)
+        sched = self.schedule(n_streams)
+        needed = set(j for _, cross in sched for j in cross)
+        events = {}
+        for i, ((fn, args, tag, _), (si, cross)) in enumerate(zip(self.launches, sched)):
+            st = streams[si]
+            for j in cross:
+                st.wait_event(events[j])
+            rc = fn(*args, ctypes.c_void_p(st.cuda_stream))
+            if rc != 0:
+                check(rc, tag)
+            if i in needed:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                events[i] = ev
+        for st in streams[1:]:
+            main.wait_stream(st)
+        self._streams = streams                                # keep alive with the graph
+
+    def capture(self, n_streams: Optional[int] = None) -> None:
         self.run_eager()  # warm-up: cudaFuncSetAttribute calls must not happen inside capture
         torch.cuda.current_stream(self.builder.device).synchronize()
+        n_streams = graph_streams() if n_streams is None else n_streams
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.run_eager()
+            if n_streams > 1 and len(self.launches) > 1:
+                self._run_streams(n_streams)
+            else:
+                self.run_eager()
         self.graph = g
 
     def run(self) -> None:

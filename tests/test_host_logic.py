@@ -68,3 +68,42 @@ def test_training_mode_is_refused():
     m.train()
     with pytest.raises(NotImplementedError):
         m(x)
+
+
+def _fake_plan(specs):
+    """specs: [(reads, writes)] with resources (buffer id, channel lo, channel hi)."""
+    class _B:
+        record = True
+        device = None
+    b = _B()
+    b.launches = [(None, (), f"op{i}", dict(kernel="k", flops=0, bytes=0, reads=list(r), writes=list(w)))
+                  for i, (r, w) in enumerate(specs)]
+    return rt.Plan(b)
+
+
+def test_launch_dag_tracks_channel_slices_and_accumulate():
+    A, B, CAT, MID = 1, 2, 3, 4
+    specs = [
+        ([(A, 0, 40)], [(CAT, 0, 40)]),                  # 0: op(s0) -> cat[0:40]
+        ([(B, 0, 40)], [(MID, 0, 40)]),                  # 1: sep half1(s1) -> mid
+        ([(MID, 0, 40), (CAT, 0, 40)], [(CAT, 0, 40)]),  # 2: sep half2(mid) += cat[0:40]   (RAW on 1, RAW/WAW on 0)
+        ([(A, 0, 40)], [(CAT, 40, 80)]),                 # 3: op(s0) -> cat[40:80]          (independent slice)
+        ([(CAT, 0, 80)], [(A, 0, 40)]),                  # 4: reads both slices, overwrites s0 (WAR on 0 and 3)
+    ]
+    plan = _fake_plan(specs)
+    assert plan.dependencies() == [[], [], [0, 1], [], [0, 2, 3]]
+    sched = plan.schedule(3)
+    streams = [s for s, _ in sched]
+    assert len({streams[0], streams[1], streams[3]}) == 3          # the three independent chains run side by side
+    # every dependency is honoured: same stream (earlier launch) or an explicit cross-stream wait that covers it
+    deps = plan.dependencies()
+    for i, (si, cross) in enumerate(sched):
+        for j in deps[i]:
+            sj = streams[j]
+            assert sj == si or any(streams[c] == sj and c >= j for c in cross), (i, j)
+
+
+def test_unknown_footprint_is_a_barrier():
+    plan = _fake_plan([([(1, 0, 8)], [(2, 0, 8)]), ([], []), ([(3, 0, 8)], [(4, 0, 8)])])
+    deps = plan.dependencies()
+    assert deps[1] == [0] and 1 in deps[2]
