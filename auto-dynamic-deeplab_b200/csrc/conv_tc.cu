@@ -134,6 +134,153 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   }
 }
 
+// ---- persistent, warp-specialised version of the kernel above ---------------------------------------
+// One tile per CTA pays the CTA's whole latency chain (TMEM alloc, barrier init, bias staging, tile-index math
+// by every thread, TMA round trip, epilogue drain) for 128 pixels; for the network's many small convs that
+// chain — not HBM or the tensor pipe — was the cost (ncu r01g: 4.2 k warp instructions per 128-pixel 1x1 tile,
+// ~0.8 k of them essential).  Here a CTA loops over tiles: the {A,B} ring keeps streaming across tile
+// boundaries, the accumulator is double-buffered in TMEM so tile i's epilogue overlaps tile i+1's MMAs, and
+// for small K the weights are loaded ONCE and stay resident.
+//   warp 0 TMA producer | warp 1 MMA issuer (+TMEM alloc) | warps 2..5 ReLU sweep | warps 6..9 epilogue
+constexpr int TCP_THREADS = 320;
+constexpr int TCP_MAX_STAGES = 8;
+
+__global__ void __launch_bounds__(TCP_THREADS)
+conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * TCP_MAX_STAGES + 5];   // full[s], empty[s], relu[s], tfull[2], tempty[2], bres
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
+  stage_bias(bias_s, p, threadIdx.x, TCP_THREADS);
+
+  const int iters = p.taps * p.kchunks;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bres_base = smem_base;                                                  // resident weights (if any)
+  const uint32_t ring_base = smem_base + (p.b_resident ? (uint32_t)iters * p.b_bytes : 0u);
+  const uint32_t stage_bytes = TC_A_BYTES + (p.b_resident ? 0u : p.b_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool relu_in = (p.flags & ADD_RELU_IN) != 0;
+  const uint32_t tmem_cols = (uint32_t)p.tmem_cols;
+
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[TCP_MAX_STAGES]);
+  const uint32_t bar_relu = smem_u32(&bars[2 * TCP_MAX_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[3 * TCP_MAX_STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[3 * TCP_MAX_STAGES + 2]);
+  const uint32_t bar_bres = smem_u32(&bars[3 * TCP_MAX_STAGES + 4]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_relu + 8 * s, 128);
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+    mbar_init(bar_bres, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_smem)), "r"(2u * tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+  const int BW = 1 << p.bw_log2, BH = TC_BM >> p.bw_log2;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      if (p.b_resident) {
+        mbar_expect_tx(bar_bres, (uint32_t)iters * p.b_bytes);
+        for (int it = 0; it < iters; ++it) tma_load_3d(bres_base + it * p.b_bytes, &map_w, bar_bres, 0, 0, it);
+      }
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int xin = tx * BW * p.stride - p.pad, yin = ty * BH * p.stride - p.pad;
+        int ky = 0, kx = 0, kc = 0;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t a_dst = ring_base + s * stage_bytes;
+          mbar_expect_tx(bar_full + 8 * s, stage_bytes);
+          tma_load_4d(a_dst, &map_x, bar_full + 8 * s, kc * TC_BK, xin + kx * p.dil, yin + ky * p.dil, n);
+          if (!p.b_resident) tma_load_3d(a_dst + TC_A_BYTES, &map_w, bar_full + 8 * s, 0, 0, it);
+          if (++kc == p.kchunks) { kc = 0; if (++kx == p.taps_w) { kx = 0; ++ky; } }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      if (p.b_resident) mbar_wait(bar_bres, 0);
+      int s = 0; uint32_t ph = 0; int ti = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+        const int ab = ti & 1; const uint32_t tph = (uint32_t)(ti >> 1) & 1u;
+        mbar_wait(bar_tempty + 8 * ab, tph ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        int kc = 0;
+        for (int it = 0; it < iters; ++it) {
+          const int krem = p.Cin - kc * TC_BK;
+          const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
+          mbar_wait((relu_in ? bar_relu : bar_full) + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_src = ring_base + s * stage_bytes;
+          const uint32_t b_src = p.b_resident ? bres_base + it * p.b_bytes : a_src + TC_A_BYTES;
+          const uint64_t adesc = make_kmajor_sw128_desc(a_src), bdesc = make_kmajor_sw128_desc(b_src);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base + ab * tmem_cols, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);
+          if (++kc == p.kchunks) kc = 0;
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * ab);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== ReLU-on-load sweep: warps 2..5 =====
+    if (relu_in) {
+      const int et = threadIdx.x - 64;
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(bar_full + 8 * s, ph);
+          relu_sweep(ring_base + s * stage_bytes, TC_A_BYTES, et);
+          mbar_arrive(bar_relu + 8 * s);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 6..9 (TMEM lane quadrants 2,3,0,1) =====
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      const int ab = ti & 1; const uint32_t tph = (uint32_t)(ti >> 1) & 1u;
+      const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      mbar_wait_relaxed(bar_tfull + 8 * ab, tph);
+      epilogue_store(p, tmem_base + ab * tmem_cols, bias_s, warp, lane, n, ty * BH, tx * BW);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * tmem_cols) : "memory");
+  }
+}
+
 // ---- halo-resident kernel (stride 1, BW = 128, BH = 1) ---------------------------------------------
 // The per-tap kernel above re-fetches the 128 x 64 A tile from L2 once per tap (9x / 25x).  Here the
 // kh halo rows of the current 64-channel chunk are brought into shared memory ONCE (one TMA box per
@@ -282,6 +429,7 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 }
 
 // ---- host side -----------------------------------------------------------------------------------
+int g_persistent = 1;  // 1 = persistent warp-specialised kernel for the non-halo path (default), 0 = one tile per CTA
 int g_halo_mode = 1;   // 0 = per-tap A tiles only, 1 = halo-resident A (measured on B200: base_offset must stay 0 — the
                        // swizzle is applied on absolute shared-memory address bits; mode 2 (base_offset = phase) is WRONG
                        // and kept only as the recorded experiment)
@@ -400,6 +548,33 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
   });
   const long long grid = (long long)p.tiles_x * p.tiles_y * y->n;
   ADD_CHECK_SUP(grid < (1ll << 31));
+  if (!halo && g_persistent) {
+    const int iters = p.taps * p.kchunks;
+    p.n_tiles = (int)grid;
+    p.b_resident = ((size_t)iters * p.b_bytes <= 72u * 1024u) ? 1 : 0;
+    const size_t fixed = 1024 + (p.b_resident ? (size_t)iters * p.b_bytes : 0);
+    const size_t sbytes = TC_A_BYTES + (p.b_resident ? 0 : p.b_bytes);
+    // two CTAs per SM when a 4-deep ring fits in half the shared memory and TMEM (4 accumulators) allows it
+    const bool two = fixed + 4 * sbytes <= 100u * 1024u && 4 * p.tmem_cols <= 512;
+    const size_t budget = two ? 100u * 1024u : 200u * 1024u;
+    int st = (int)((budget - fixed) / sbytes);
+    if (st > TCP_MAX_STAGES) st = TCP_MAX_STAGES;
+    if (st >= 2) {
+      p.stages = st;
+      const size_t psmem = fixed + (size_t)st * sbytes;
+      static std::once_flag ponce;
+      std::call_once(ponce, [] {
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      });
+      int sms = 148;
+      { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      long long g = (long long)sms * (two ? 2 : 1);
+      if (g > grid) g = grid;
+      conv2d_tc_persistent_kernel<<<(unsigned)g, TCP_THREADS, psmem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, p);
+      ADD_RETURN_LAUNCH();
+    }
+  }
   if (halo)
     conv2d_tc_halo_kernel<<<(unsigned)grid, TCH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, p);
   else
@@ -409,6 +584,8 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
 
 /* Tuning / experiment switch for the halo-resident A path (see conv2d_tc_halo_kernel). */
 extern "C" int add_conv2d_tc_set_halo_mode(int mode) {
+  if (mode >= 16) { g_persistent = (mode & 16) ? 0 : 1; mode &= 15; }     // bit 4 set = one tile per CTA (A/B runs)
+  else g_persistent = 1;
   if (mode < 0 || mode > 2) return ADD_ERR_BAD_ARG;
   g_halo_mode = mode;
   return ADD_OK;

@@ -31,6 +31,9 @@ struct TcParams {
   int halo_pitch;                          // pixels per halo row in smem (multiple of 8)
   int halo_bufs;                           // 1 or 2 halo buffers
   int base_off_mode;                       // descriptor base_offset: 0 = always 0, 1 = (addr >> 7) & 7
+  // persistent kernel
+  int n_tiles;                             // tiles_x * tiles_y * N
+  int b_resident;                          // 1: all weight chunks stay in shared memory for the whole kernel
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -97,7 +100,24 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
 // ---- shared pieces of the two kernels -----------------------------------------------------------
 // In-place ReLU over `bytes` of bf16 in shared memory by the 128 ReLU/epilogue threads (et = 0..127).
 __device__ __forceinline__ void relu_sweep(uint32_t base, uint32_t bytes, int et) {
-  for (uint32_t off = et * 16; off < bytes; off += 128 * 16) {
+  // batches of 4 x 16 B per thread: all loads of a batch are issued before the first max/store, so one batch costs
+  // one shared-memory round trip instead of four back-to-back ones (the sweep sits on the MMA's critical path)
+  constexpr uint32_t STEP = 128 * 16;
+  uint32_t off = et * 16;
+  for (; off + 3 * STEP < bytes; off += 4 * STEP) {
+    uint32_t v[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i][0]), "=r"(v[i][1]), "=r"(v[i][2]), "=r"(v[i][3])
+                   : "r"(base + off + i * STEP));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) asm("max.bf16x2 %0, %0, %1;" : "+r"(v[i][j]) : "r"(0u));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + off + i * STEP), "r"(v[i][0]), "r"(v[i][1]), "r"(v[i][2]), "r"(v[i][3]) : "memory");
+    }
+  }
+  for (; off < bytes; off += STEP) {
     const uint32_t addr = base + off;
     uint32_t v0, v1, v2, v3;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));

@@ -62,13 +62,21 @@ CASES = [
     (200, 48, 3, 1, 1, 1, 4, 65, 0),
     (64, 64, 3, 1, 1, 1, 3, 1024, RELU_OUT),
     (40, 40, 5, 1, 2, 1, 11, 256, RELU_IN),
+    # more tiles than resident CTAs (persistent kernel: ring continues across tiles, TMEM double buffer, resident B)
+    (40, 40, 1, 1, 0, 1, 160, 250, RELU_IN | ACCUMULATE),
+    (200, 40, 1, 1, 0, 1, 150, 253, RELU_IN),
+    (400, 80, 1, 1, 0, 1, 127, 200, RELU_IN | RELU_OUT),
+    (64, 64, 3, 1, 1, 1, 130, 200, RELU_OUT),
+    (64, 128, 3, 2, 1, 1, 257, 300, RELU_IN),
 ]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[f"c{c[0]}-{c[1]}_k{c[2]}s{c[3]}p{c[4]}d{c[5]}_{c[6]}x{c[7]}_f{c[8]}" for c in CASES])
+@pytest.mark.parametrize("persistent", [True, False], ids=["persistent", "tile_per_cta"])
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
-def test_tc_matches_ffma(case, out_dtype):
+def test_tc_matches_ffma(case, out_dtype, persistent):
     cin, cout, k, stride, pad, dil, H, W, flags = case
+    rt.set_tc_halo_mode(1 if persistent else 17)        # bit 4: one tile per CTA instead of the persistent kernel
     g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
     n = 2
     # input is a channel slice of a wider buffer (concat-slice reads)
@@ -85,7 +93,10 @@ def test_tc_matches_ffma(case, out_dtype):
     y_ctot, y_off = (cout + step - 1) // step * step + 2 * step, step
     y_init = torch.randn(n, ho, wo, y_ctot, generator=g).to(out_dtype).to(DEV)
     ref = _run(x_buf, c_off, cin, w, bias, stride, pad, dil, flags, (ho, wo), out_dtype, y_ctot, y_off, False, y_init)
-    got = _run(x_buf, c_off, cin, w, bias, stride, pad, dil, flags, (ho, wo), out_dtype, y_ctot, y_off, True, y_init)
+    try:
+        got = _run(x_buf, c_off, cin, w, bias, stride, pad, dil, flags, (ho, wo), out_dtype, y_ctot, y_off, True, y_init)
+    finally:
+        rt.set_tc_halo_mode(1)
     # untouched channels stay untouched
     assert torch.equal(got[..., :y_off], y_init[..., :y_off])
     assert torch.equal(got[..., y_off + cout:], y_init[..., y_off + cout:])
