@@ -100,43 +100,57 @@ nhwc_to_nchw_kernel(const TI* __restrict__ src, float* __restrict__ dst, int C, 
 }
 
 // ---- global average pool: two deterministic stages ------------------------------------------------
-// stage 1: grid (splits, n); each block sums a contiguous pixel range for ALL channels with 4-channel
-// vector loads (thread = channel vector x pixel lane), block-reduces over pixel lanes in smem and
-// writes partial[n][split][C].  stage 2: one block per image sums the splits in fixed order.
+// stage 1: grid (splits, n); each block sums a contiguous pixel range for ALL channels (thread = channel vector x
+// pixel lane, 4 independent loads in flight per thread), block-reduces over pixel lanes in smem and writes
+// partial[n][split][C].  stage 2: one block per image sums the splits in fixed order.
+// V = channels per thread: 8 for 16-byte-aligned bf16 views (16 B loads), else 4.
 constexpr int GAP_THREADS = 256;
-__host__ __device__ inline int gap_splits(int HW) {
-  int s = (HW + 1023) / 1024;
-  return s < 1 ? 1 : (s > 148 * 2 ? 148 * 2 : s);
+__host__ __device__ inline int gap_splits(int HW, int n) {
+  int s = (HW + 255) / 256;
+  int cap = (148 * 8 + n - 1) / n;
+  return s < 1 ? 1 : (s > cap ? cap : s);
 }
 
-template <typename TI>
+template <typename TI, int V>
 __global__ void __launch_bounds__(GAP_THREADS)
 gap_partial_kernel(const TI* __restrict__ x, float* __restrict__ part, int HW, int C, int xs, uint32_t flags) {
-  extern __shared__ float4 gap_red[];                // [lanes][cv]
-  const int cv = C >> 2;
+  extern __shared__ float gap_red[];                 // [lanes][C]
+  const int cv = C / V;
   const int lanes = GAP_THREADS / cv;                // pixel lanes (>= 1: host checks cv <= 256)
   const int n = blockIdx.y, S = gridDim.x;
   const int per = (HW + S - 1) / S;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
   const int v = threadIdx.x % cv, l = threadIdx.x / cv;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool relu = flags & ADD_RELU_IN;
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
   if (l < lanes) {
-    const TI* xn = x + (size_t)n * HW * xs + v * 4;
-    for (int p = p0 + l; p < p1; p += lanes) {
-      float4 t = ld4(xn + (size_t)p * xs);
-      if (flags & ADD_RELU_IN) t = relu4(t);
-      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    const TI* xn = x + (size_t)n * HW * xs + v * V;
+    int p = p0 + l;
+    for (; p + 3 * lanes < p1; p += 4 * lanes) {
+      float t[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) VecIO<V>::load(xn + (size_t)(p + u * lanes) * xs, t[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += relu ? fmaxf(t[u][i], 0.f) : t[u][i];
     }
-    gap_red[l * cv + v] = acc;
+    for (; p < p1; p += lanes) {
+      float t[V];
+      VecIO<V>::load(xn + (size_t)p * xs, t);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += relu ? fmaxf(t[i], 0.f) : t[i];
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) gap_red[l * C + v * V + i] = acc[i];
   }
   __syncthreads();
-  if (threadIdx.x < cv) {
-    float4 tot = gap_red[threadIdx.x];
-    for (int r = 1; r < lanes; ++r) {
-      float4 t = gap_red[r * cv + threadIdx.x];
-      tot.x += t.x; tot.y += t.y; tot.z += t.z; tot.w += t.w;
-    }
-    *reinterpret_cast<float4*>(part + ((size_t)n * S + blockIdx.x) * C + threadIdx.x * 4) = tot;
+  for (int c = threadIdx.x; c < C; c += GAP_THREADS) {
+    float tot = gap_red[c];
+    for (int r = 1; r < lanes; ++r) tot += gap_red[r * C + c];
+    part[((size_t)n * S + blockIdx.x) * C + c] = tot;
   }
 }
 
@@ -234,7 +248,7 @@ extern "C" int add_nhwc_to_nchw(const add_tensor_t* x, float* dst, void* stream)
 
 extern "C" int64_t add_global_avgpool_workspace_bytes(int n, int h, int w, int c) {
   if (n <= 0 || h <= 0 || w <= 0 || c <= 0) return ADD_ERR_BAD_ARG;
-  return (int64_t)n * gap_splits(h * w) * c * sizeof(float);
+  return (int64_t)n * gap_splits(h * w, n) * c * sizeof(float);
 }
 
 extern "C" int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_t flags, void* workspace,
@@ -242,14 +256,18 @@ extern "C" int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_
   ADD_CHECK_ARG(tensor_ok(x) && out && workspace);
   ADD_CHECK_SUP(tensor_vec4_ok(x) && x->c / 4 <= GAP_THREADS);
   if (workspace_bytes < add_global_avgpool_workspace_bytes(x->n, x->h, x->w, x->c)) return ADD_ERR_WORKSPACE;
-  const int HW = x->h * x->w, S = gap_splits(HW), cv = x->c / 4;
+  const int HW = x->h * x->w, S = gap_splits(HW, x->n);
+  const bool v8 = x->dtype == ADD_BF16 && x->c % 8 == 0 && x->pix_stride % 8 == 0 && ((uintptr_t)x->ptr % 16) == 0;
+  const int cv = x->c / (v8 ? 8 : 4);
   dim3 grid(S, x->n);
-  size_t smem = (size_t)(GAP_THREADS / cv) * cv * sizeof(float4);
+  size_t smem = (size_t)(GAP_THREADS / cv) * x->c * sizeof(float);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (x->dtype == ADD_F32)
-    gap_partial_kernel<float><<<grid, GAP_THREADS, smem, s>>>((const float*)x->ptr, (float*)workspace, HW, x->c, x->pix_stride, flags);
+  if (v8)
+    gap_partial_kernel<bf16, 8><<<grid, GAP_THREADS, smem, s>>>((const bf16*)x->ptr, (float*)workspace, HW, x->c, x->pix_stride, flags);
+  else if (x->dtype == ADD_F32)
+    gap_partial_kernel<float, 4><<<grid, GAP_THREADS, smem, s>>>((const float*)x->ptr, (float*)workspace, HW, x->c, x->pix_stride, flags);
   else
-    gap_partial_kernel<bf16><<<grid, GAP_THREADS, smem, s>>>((const bf16*)x->ptr, (float*)workspace, HW, x->c, x->pix_stride, flags);
+    gap_partial_kernel<bf16, 4><<<grid, GAP_THREADS, smem, s>>>((const bf16*)x->ptr, (float*)workspace, HW, x->c, x->pix_stride, flags);
   gap_finalize_kernel<<<x->n, GAP_THREADS, 0, s>>>((const float*)workspace, out, S, x->c, 1.f / (float)HW);
   ADD_RETURN_LAUNCH();
 }
