@@ -22,7 +22,7 @@ from .aspp_train import ASPP_train
 from .decoder import Decoder, ASPP_C, LOW_LEVEL_C
 from .operations import (AddModule, OPS, ReLUConvBN, FactorizedReduce, DoubleFactorizedReduce,
                          SynchronizedBatchNorm2d, _conv_holder, normalized_shannon_entropy, confidence_max)
-from .runtime import Builder, ConvWeights, Plan, View, RELU_IN, RELU_OUT, ACCUMULATE
+from .runtime import Builder, ConvWeights, Plan, View, RELU_IN, RELU_OUT, ACCUMULATE, IN_RELUD
 from ._lib import lib, check
 
 
@@ -103,7 +103,9 @@ class Cell(AddModule):
         else:
             h, w = s1_in.h, s1_in.w
         s1 = b.scratch(n, h, w, C)
-        self.preprocess.emit(b, s1_in, s1, 0)
+        # s0 / s1 are read only by the cell's ops, which all start with ReLU (operations.py:33,47): store relu(s)
+        # once (RELU_OUT) and let the five ops that read them skip their ReLU-on-load pass
+        self.preprocess.emit(b, s1_in, s1, RELU_OUT)
         s0 = b.scratch(n, h, w, C)
         temps += [s0, s1]
         if not self.dense_in:  # ADD.py:83-86
@@ -113,7 +115,7 @@ class Cell(AddModule):
                 b.bilinear(src, r, 0, "Cell.resize_pp")
                 temps.append(r)
                 src = r
-            self.pre_preprocess.emit(b, src, s0, 0)
+            self.pre_preprocess.emit(b, src, s0, RELU_OUT)
         else:  # ADD.py:87-93
             k = len(prev_prev)
             cat = b.scratch(n, h, w, k * C)
@@ -124,7 +126,7 @@ class Cell(AddModule):
                     self.pre_preprocess[i].emit(b, r, cat.slice(i * C, C), 0)
                 else:
                     self.pre_preprocess[i].emit(b, src, cat.slice(i * C, C), 0)
-            self.pre_preprocess_1x1.emit(b, cat, s0, 0)
+            self.pre_preprocess_1x1.emit(b, cat, s0, RELU_OUT)
         concat = b.alloc(n, h, w, self.B * C)
         states = [s0, s1] + [concat.slice(i * C, C) for i in range(self.B)]
         for i, edges in enumerate(self._steps):  # ADD.py:97-110
@@ -132,7 +134,7 @@ class Cell(AddModule):
             if not edges:
                 raise NotImplementedError("cell step without inputs (sum of empty list) is not supported")
             for e, (j, k) in enumerate(edges):
-                self._ops[k].emit(b, states[j], dst, ACCUMULATE if e > 0 else 0)
+                self._ops[k].emit(b, states[j], dst, (ACCUMULATE if e > 0 else 0) | (IN_RELUD if j < 2 else 0))
         dense = None
         if self.dense_out:
             dense = b.alloc(n, h, w, C)

@@ -26,3 +26,8 @@ extern "C" int add_device_sm_count(void) {
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return ADD_ERR_CUDA;
   return sms;
 }
+
+int g_add_pdl = 1;
+/* 1 (default) = tcgen05 kernels are launched with programmatic stream serialization (their prologue overlaps the
+ * previous kernel's tail; they wait for it with griddepcontrol.wait before touching activations); 0 = plain launches. */
+extern "C" int add_set_pdl(int on) { g_add_pdl = on ? 1 : 0; return ADD_OK; }

@@ -69,6 +69,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();
+  pdl_wait();                     // the previous kernel's activations are complete and visible from here on
 
   const int iters = p.taps * p.kchunks;
 
@@ -190,6 +192,8 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();
+  pdl_wait();                     // the previous kernel's activations are complete and visible from here on
   const int BW = 1 << p.bw_log2, BH = TC_BM >> p.bw_log2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
@@ -350,6 +354,8 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();
+  pdl_wait();                     // the previous kernel's activations are complete and visible from here on
 
   if (warp == 0) {
     // ===== halo producer: kh row boxes per 64-channel chunk =====
@@ -571,14 +577,14 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
       { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
       long long g = (long long)sms * (two ? 2 : 1);
       if (g > grid) g = grid;
-      conv2d_tc_persistent_kernel<<<(unsigned)g, TCP_THREADS, psmem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, p);
+      launch_kernel(conv2d_tc_persistent_kernel, dim3((unsigned)g), dim3(TCP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
       ADD_RETURN_LAUNCH();
     }
   }
   if (halo)
-    conv2d_tc_halo_kernel<<<(unsigned)grid, TCH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, p);
+    launch_kernel(conv2d_tc_halo_kernel, dim3((unsigned)grid), dim3(TCH_THREADS), smem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
   else
-    conv2d_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, p);
+    launch_kernel(conv2d_tc_kernel, dim3((unsigned)grid), dim3(TC_THREADS), smem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
   ADD_RETURN_LAUNCH();
 }
 

@@ -91,6 +91,8 @@ sepconv_half_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();
+  pdl_wait();                     // the previous kernel's activations are complete and visible from here on
 
   if (is_ctrl) {
     if (lane == 0) {
@@ -266,6 +268,8 @@ sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();
+  pdl_wait();                     // the previous kernel's activations are complete and visible from here on
   const int tiles_per_img = p.e.tiles_x * p.e.tiles_y;
 
   if (warp == 4) {
@@ -402,7 +406,7 @@ int launch_sepconv_tc_persistent(const CUtensorMap& map_x, const CUtensorMap& ma
     cudaFuncSetAttribute(sepconv_half_tc_persistent_kernel<K, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(sepconv_half_tc_persistent_kernel<K, MAXT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   });
-  sepconv_half_tc_persistent_kernel<K, MAXT, MINB><<<grid, threads, smem, s>>>(map_x, map_w, p);
+  launch_kernel(sepconv_half_tc_persistent_kernel<K, MAXT, MINB>, dim3(grid), dim3(threads), smem, s, map_x, map_w, p);
   ADD_RETURN_LAUNCH();
 }
 
@@ -417,7 +421,7 @@ int launch_sepconv_tc(const CUtensorMap& map_x, const CUtensorMap& map_w, const 
     cudaFuncSetAttribute(sepconv_half_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(sepconv_half_tc_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   });
-  sepconv_half_tc_kernel<K><<<(unsigned)grid, p.n_cthreads + 32, smem, s>>>(map_x, map_w, p);
+  launch_kernel(sepconv_half_tc_kernel<K>, dim3((unsigned)grid), dim3(p.n_cthreads + 32), smem, s, map_x, map_w, p);
   ADD_RETURN_LAUNCH();
 }
 

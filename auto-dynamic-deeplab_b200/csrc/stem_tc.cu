@@ -65,6 +65,8 @@ stem_conv3x3s2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();
+  pdl_wait();
   const int tiles_per_img = p.tiles_x * p.Ho;
 
   if (is_ctrl) {
@@ -256,6 +258,6 @@ extern "C" int add_stem_conv3x3s2_nchw_fwd(const float* x_nchw, int n, int h, in
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   long long grid = (long long)sms * 4;                 // 4 resident CTAs per SM (registers: 160 threads x ~100)
   if (grid > n_tiles) grid = n_tiles;
-  stem_conv3x3s2_kernel<<<(unsigned)grid, ST_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map_w, map_y, p);
+  launch_kernel(stem_conv3x3s2_kernel, dim3((unsigned)grid), dim3(ST_THREADS), smem, static_cast<cudaStream_t>(stream), map_w, map_y, p);
   ADD_RETURN_LAUNCH();
 }

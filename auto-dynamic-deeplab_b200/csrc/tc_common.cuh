@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cstring>
 #include <mutex>
+#include <utility>
 
 namespace {
 
@@ -35,6 +36,26 @@ struct TcParams {
   int n_tiles;                             // tiles_x * tiles_y * N
   int b_resident;                          // 1: all weight chunks stay in shared memory for the whole kernel
 };
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Kernels launched through launch_kernel() with PDL on may START before the previous kernel of their stream has
+// finished: everything up to pdl_wait() (barrier init, TMEM alloc, bias staging, tensor-map prefetch — nothing
+// that reads activations) overlaps the predecessor's tail; pdl_wait() returns once the predecessor grid has
+// completed and its writes are visible.  pdl_launch_dependents() lets OUR successor start its own prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_add_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

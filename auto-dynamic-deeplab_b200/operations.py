@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import runtime as rt
-from .runtime import Builder, ConvWeights, View, RELU_IN, RELU_OUT, ACCUMULATE
+from .runtime import Builder, ConvWeights, View, RELU_IN, RELU_OUT, ACCUMULATE, IN_RELUD
 from ._lib import lib, check
 
 
@@ -79,6 +79,11 @@ class AddModule(nn.Module):
         raise NotImplementedError
 
 
+def _relu_in(flags: int) -> int:
+    """ReLU-on-load unless the producer already stored relu(x) (IN_RELUD); strips the host-only bit."""
+    return (0 if flags & IN_RELUD else RELU_IN) | (flags & ~IN_RELUD)
+
+
 def _conv_holder(cin, cout, k, stride=1, padding=0, dilation=1, groups=1, bias=False) -> nn.Conv2d:
     return nn.Conv2d(cin, cout, k, stride=stride, padding=padding, dilation=dilation, groups=groups, bias=bias)
 
@@ -103,7 +108,7 @@ class ReLUConvBN(AddModule):
 
     def emit(self, b, x, y, flags=0):
         self._ensure_prepared()
-        b.conv(x, y, self.cw, self.stride, self.padding, 1, RELU_IN | flags, "ReLUConvBN")
+        b.conv(x, y, self.cw, self.stride, self.padding, 1, _relu_in(flags), "ReLUConvBN")
 
 
 class DilConv(AddModule):
@@ -126,7 +131,7 @@ class DilConv(AddModule):
 
     def emit(self, b, x, y, flags=0):
         self._ensure_prepared()
-        b.conv(x, y, self.cw, self.stride, self.padding, self.dilation, RELU_IN | flags, "DilConv")
+        b.conv(x, y, self.cw, self.stride, self.padding, self.dilation, _relu_in(flags), "DilConv")
 
 
 class SepConv(AddModule):
@@ -158,8 +163,8 @@ class SepConv(AddModule):
     def emit(self, b, x, y, flags=0):
         self._ensure_prepared()
         mid = b.scratch(x.n, x.h, x.w, self.C)
-        b.sepconv_half(x, mid, self.dw1, self.pw1, self.k, RELU_IN | RELU_OUT, "SepConv.half1")
-        b.sepconv_half(mid, y, self.dw2, self.pw2, self.k, flags, "SepConv.half2")
+        b.sepconv_half(x, mid, self.dw1, self.pw1, self.k, _relu_in(flags & IN_RELUD) | RELU_OUT, "SepConv.half1")
+        b.sepconv_half(mid, y, self.dw2, self.pw2, self.k, flags & ~IN_RELUD, "SepConv.half2")
         b.release(mid)
 
 
@@ -242,8 +247,8 @@ class _FactorizedReduceBase(AddModule):
     def emit(self, b, x, y, flags=0):
         self._ensure_prepared()
         half = self.C_out // 2
-        b.conv(x, y.slice(0, half), self.cw1, self.STEP, 0, 1, RELU_IN | flags, type(self).__name__ + ".even")
-        b.conv(x, y.slice(half, half), self.cw2, self.STEP, -(self.STEP // 2), 1, RELU_IN | flags,
+        b.conv(x, y.slice(0, half), self.cw1, self.STEP, 0, 1, _relu_in(flags), type(self).__name__ + ".even")
+        b.conv(x, y.slice(half, half), self.cw2, self.STEP, -(self.STEP // 2), 1, _relu_in(flags),
                type(self).__name__ + ".odd")
 
 

@@ -15,6 +15,9 @@ import torch
 from . import _lib
 from ._lib import AddTensor, lib, check, ADD_F32, ADD_BF16, RELU_IN, RELU_OUT, ACCUMULATE
 
+IN_RELUD = 8   # host-only emit flag: the input view already holds relu(x) (its producer stored it with RELU_OUT), so
+               # the op skips its ReLU-on-load.  Exact: relu(round(x)) == round(relu(x)).  Never passed to the C ABI.
+
 _GENERATION = 0  # bumped whenever any add_b200 module's parameters may have changed
 
 
@@ -158,6 +161,8 @@ def set_tc_halo_mode(mode: int) -> None:
 
 
 import os as _os
+if _os.environ.get("ADD_PDL"):
+    check(lib.add_set_pdl(int(_os.environ["ADD_PDL"])), "set_pdl")
 if _os.environ.get("ADD_TC_HALO_MODE"):
     set_tc_halo_mode(int(_os.environ["ADD_TC_HALO_MODE"]))
 

@@ -54,6 +54,9 @@ const char* add_status_string(int status);
 const char* add_last_cuda_error(void); /* text of the last CUDA error behind an ADD_ERR_CUDA on this thread */
 int  add_version(void);               /* 10000*major + 100*minor + patch                       */
 int  add_device_sm_count(void);       /* SMs of the current device, <0 on error                */
+/* 1 (default): the tcgen05 kernels are launched with programmatic dependent launch — their prologue overlaps the
+ * previous kernel's tail and they wait for it (griddepcontrol.wait) before touching activations; 0: plain launches. */
+int  add_set_pdl(int on);
 
 /* ---- layout / dtype edges --------------------------------------------------------------- */
 
