@@ -42,10 +42,11 @@ _SIGS = {
     "add_set_pdl": (c_int, [c_int]),
     "add_nchw_to_nhwc": (c_int, [c_void_p, c_int, TP, c_void_p]),
     "add_nhwc_to_nchw": (c_int, [TP, c_void_p, c_void_p]),
-    "add_conv2d_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
+    "add_conv2d_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
     "add_conv2d_tc_packed_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "add_conv2d_tc_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "add_conv2d_tc_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
+    "add_conv2d_tc_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
+    "add_aspp_pool_bias_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "add_stem_tc_packed_bytes": (c_int64, []),
     "add_stem_tc_pack": (c_int, [c_void_p, c_void_p]),
     "add_stem_conv3x3s2_nchw_fwd": (c_int, [c_void_p, c_int, c_int, c_int, TP, c_void_p, c_void_p, c_uint32, c_void_p]),

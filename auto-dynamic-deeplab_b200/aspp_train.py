@@ -35,6 +35,10 @@ class ASPP_train(AddModule):
     def _prepare(self):
         self.cw = [ConvWeights(getattr(self, f"aspp{k}").weight, getattr(self, f"aspp{k}_bn")) for k in range(1, 6)]
         self.cw_out = ConvWeights(self.conv1.weight, self.bn1)
+        d = self._depth
+        # the 1x1 over the concatenation, split: rows of the four spatial branches / rows of the image-pool branch
+        self.cw_out_main = ConvWeights.from_folded(self.cw_out.w[:, :, :4 * d, :].contiguous(), self.cw_out.bias)
+        self.w_out_pool = self.cw_out.w[0, 0, 4 * d:, :].contiguous()            # [depth][out] fp32
 
     def out_shape(self, n, c, h, w):
         return n, self._out, h, w
@@ -43,14 +47,15 @@ class ASPP_train(AddModule):
         """aspp_train.py:34-61."""
         self._ensure_prepared()
         d = self._depth
-        cat = b.scratch(x.n, x.h, x.w, 5 * d)
+        cat = b.scratch(x.n, x.h, x.w, 4 * d)
         b.conv(x, cat.slice(0, d), self.cw[0], 1, 0, 1, RELU_IN | RELU_OUT, "ASPP.aspp1")
         for i, dil in enumerate(self.dils):
             b.conv(x, cat.slice(d * (i + 1), d), self.cw[i + 1], 1, dil, dil, RELU_IN | RELU_OUT, f"ASPP.aspp{i + 2}")
-        pooled = View(b.raw((x.n, 1, 1, self._C), torch.float32))
-        b.gap(x, pooled.buf, RELU_IN, "ASPP.gap")
-        p5 = View(b.raw((x.n, 1, 1, d), torch.float32))
-        b.conv(pooled, p5, self.cw[4], 1, 0, 1, RELU_OUT, "ASPP.aspp5")
-        b.bilinear(p5, cat.slice(4 * d, d), 0, "ASPP.broadcast")
-        b.conv(cat, y, self.cw_out, 1, 0, 1, flags, "ASPP.conv1")
+        # image-pool branch (aspp_train.py:49-57): GAP -> 1x1+BN+ReLU -> broadcast is constant over the image, so it
+        # enters the final 1x1 as a per-image bias instead of 256 broadcast channels of the concatenation
+        pooled = b.raw((x.n, self._C), torch.float32)
+        b.gap(x, pooled, RELU_IN, "ASPP.gap")
+        bias_n = b.raw((x.n, self._out), torch.float32)
+        b.aspp_pool_bias(pooled, self.cw[4], self.w_out_pool, self.cw_out.bias, bias_n, "ASPP.pool_bias")
+        b.conv(cat, y, self.cw_out_main, 1, 0, 1, flags, "ASPP.conv1", image_bias=bias_n)
         b.release(cat)

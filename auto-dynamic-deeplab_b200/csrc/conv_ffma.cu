@@ -7,6 +7,7 @@ namespace {
 
 struct ConvParams {
   const void* x; void* y; const float* w; const float* bias;
+  long long bias_img_stride;   // floats between images' bias vectors (0 = shared)
   int N, H, W, Cin, xs;        // input view
   int Ho, Wo, Cout, ys;        // output view
   int kh, kw, stride, pad, dil;
@@ -108,12 +109,13 @@ conv2d_ffma_kernel(const ConvParams p) {
   for (int j = 0; j < TN; ++j) {
     int co = n0 + j * 8 + tx;
     if (co >= p.Cout) continue;
-    float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+    const float bv0 = (p.bias && p.bias_img_stride == 0) ? __ldg(p.bias + co) : 0.f;
 #pragma unroll
     for (int i = 0; i < CV_TM; ++i) {
       int m = m0 + ty * CV_TM + i;
       if (m >= p.M) continue;
       TO* dst = y + (size_t)m * p.ys + co;
+      const float bv = (p.bias && p.bias_img_stride != 0) ? __ldg(p.bias + (long long)(m / (p.Ho * p.Wo)) * p.bias_img_stride + co) : bv0;
       float v = acc[i][j] + bv;
       if (accum) v += ld1(const_cast<const TO*>(dst));
       if (relu_out) v = fmaxf(v, 0.f);
@@ -271,7 +273,7 @@ int launch_sep(const SepParams& p, cudaStream_t s) {
 }  // namespace
 
 extern "C" int add_conv2d_fwd(const add_tensor_t* x, const add_tensor_t* y, const float* w,
-                              const float* bias, int kh, int kw, int stride, int pad, int dil,
+                              const float* bias, int64_t bias_image_stride, int kh, int kw, int stride, int pad, int dil,
                               uint32_t flags, void* stream) {
   ADD_CHECK_ARG(tensor_ok(x) && tensor_ok(y) && w);
   ADD_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && dil > 0);
@@ -284,7 +286,7 @@ extern "C" int add_conv2d_fwd(const add_tensor_t* x, const add_tensor_t* y, cons
   ADD_CHECK_SUP(tensor_vec4_ok(x));
   ADD_CHECK_SUP((long long)y->n * y->h * y->w < (1ll << 31));
   ConvParams p;
-  p.x = x->ptr; p.y = y->ptr; p.w = w; p.bias = bias;
+  p.x = x->ptr; p.y = y->ptr; p.w = w; p.bias = bias; p.bias_img_stride = bias ? bias_image_stride : 0;
   p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c; p.xs = x->pix_stride;
   p.Ho = y->h; p.Wo = y->w; p.Cout = y->c; p.ys = y->pix_stride;
   p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.dil = dil; p.flags = flags;

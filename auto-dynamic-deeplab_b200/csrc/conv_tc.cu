@@ -30,7 +30,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 1];   // full[s], empty[s], relu[s], accum
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
-  stage_bias(bias_s, p, threadIdx.x, TC_THREADS);
+  stage_bias(bias_s, p, threadIdx.x, TC_THREADS, (int)(blockIdx.x / (unsigned)(p.tiles_x * p.tiles_y)));
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles: 1024-B aligned
   const uint32_t stage_bytes = TC_A_BYTES + p.b_bytes;
@@ -152,8 +152,7 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[3 * TCP_MAX_STAGES + 5];   // full[s], empty[s], relu[s], tfull[2], tempty[2], bres
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
-  stage_bias(bias_s, p, threadIdx.x, TCP_THREADS);
+  __shared__ __align__(16) float bias_s[TC_MAX_NPAD];    // staged by the epilogue warps themselves (off the prologue's critical path)
 
   const int iters = p.taps * p.kchunks;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -265,11 +264,20 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     }
   } else {
     // ===== epilogue: warps 6..9 (TMEM lane quadrants 2,3,0,1) =====
+    int cur_n = (int)blockIdx.x / tiles_per_img;
+    stage_bias(bias_s, p, threadIdx.x - 192, 128, cur_n);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     int ti = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
       const int ab = ti & 1; const uint32_t tph = (uint32_t)(ti >> 1) & 1u;
       const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      if (p.bias_img_stride != 0 && n != cur_n) {              // per-image bias: restage when the image changes
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        stage_bias(bias_s, p, threadIdx.x - 192, 128, n);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_n = n;
+      }
       mbar_wait_relaxed(bar_tfull + 8 * ab, tph);
       epilogue_store(p, tmem_base + ab * tmem_cols, bias_s, warp, lane, n, ty * BH, tx * BW);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -309,7 +317,7 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   __shared__ __align__(8) uint64_t bars[6 + 2 * TC_MAX_STAGES + 1];   // halo full/empty/relu [2], b_full[s], b_empty[s], accum
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
-  stage_bias(bias_s, p, threadIdx.x, TCH_THREADS);
+  stage_bias(bias_s, p, threadIdx.x, TCH_THREADS, (int)(blockIdx.x / (unsigned)(p.tiles_x * p.tiles_y)));
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t halo_bytes = (uint32_t)(p.taps / p.taps_w) * p.halo_pitch * 128u;    // kh rows
@@ -471,7 +479,7 @@ extern "C" int add_conv2d_tc_pack(const float* w_hwio, int cin, int cout, int kh
 }
 
 extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, const void* w_packed,
-                                 const float* bias, int kh, int kw, int stride, int pad, int dil,
+                                 const float* bias, int64_t bias_image_stride, int kh, int kw, int stride, int pad, int dil,
                                  uint32_t flags, void* stream) {
   ADD_CHECK_ARG(tensor_ok(x) && tensor_ok(y) && w_packed);
   ADD_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && dil > 0 && x->n == y->n);
@@ -485,6 +493,7 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
   if (!encode) { g_add_last_cuda_error = (int)cudaErrorSymbolNotFound; return ADD_ERR_CUDA; }
 
   TcParams p;
+  p.bias_img_stride = bias ? bias_image_stride : 0;
   p.y = y->ptr; p.bias = bias; p.Ho = y->h; p.Wo = y->w; p.Cout = y->c; p.ys = y->pix_stride;
   p.y_is_f32 = (y->dtype == ADD_F32);
   int bw_log2 = 3;                                   // BW = smallest power of two >= Wo, clamped to [8, 128]

@@ -279,6 +279,44 @@ extern "C" int add_edm_mlp_fwd(const float* pooled, int n, const float* w0, cons
   ADD_RETURN_LAUNCH();
 }
 
+// ---- ASPP image-pool branch folded into a per-image bias (aspp_train.py:49-57) -------------------------------
+// The pooled branch is constant over the image, so after the 1x1 over the concatenation it is just a per-image
+// vector: bias_n[co] = b_out[co] + sum_d Wout_pool[d][co] * relu(b5[d] + sum_ci W5[ci][d] * pooled[n][ci]).
+// One block per image, fp32 throughout; replaces the GAP->1x1->broadcast->concat-slice round trip (268 MB written
+// and re-read per 4 images at 256x512).
+namespace {
+__global__ void __launch_bounds__(256)
+aspp_pool_bias_kernel(const float* __restrict__ pooled, int cin, const float* __restrict__ w5, const float* __restrict__ b5,
+                      int depth, const float* __restrict__ w_out_pool, const float* __restrict__ b_out, int cout,
+                      float* __restrict__ bias_out) {
+  extern __shared__ float sm[];                 // [cin] pooled, [depth] p5
+  float* pin = sm; float* p5 = sm + cin;
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < cin; i += 256) pin[i] = pooled[(size_t)n * cin + i];
+  __syncthreads();
+  for (int d = threadIdx.x; d < depth; d += 256) {
+    float s = b5 ? b5[d] : 0.f;
+    for (int ci = 0; ci < cin; ++ci) s = fmaf(__ldg(w5 + (size_t)ci * depth + d), pin[ci], s);
+    p5[d] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int co = threadIdx.x; co < cout; co += 256) {
+    float s = b_out ? b_out[co] : 0.f;
+    for (int d = 0; d < depth; ++d) s = fmaf(__ldg(w_out_pool + (size_t)d * cout + co), p5[d], s);
+    bias_out[(size_t)n * cout + co] = s;
+  }
+}
+}  // namespace
+
+extern "C" int add_aspp_pool_bias_fwd(const float* pooled, int n, int cin, const float* w5, const float* b5, int depth,
+                                      const float* w_out_pool, const float* b_out, int cout, float* bias_out, void* stream) {
+  ADD_CHECK_ARG(pooled && w5 && w_out_pool && bias_out && n > 0 && cin > 0 && depth > 0 && cout > 0);
+  ADD_CHECK_SUP((size_t)(cin + depth) * sizeof(float) <= 48 * 1024);
+  aspp_pool_bias_kernel<<<n, 256, (size_t)(cin + depth) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      pooled, cin, w5, b5, depth, w_out_pool, b_out, cout, bias_out);
+  ADD_RETURN_LAUNCH();
+}
+
 // ---- image gather: dst[j] = src[idx[j]] for whole per-image slabs (early-exit batch compaction) ----
 namespace {
 template <typename V>

@@ -229,8 +229,7 @@ sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, con
   constexpr int HR = SC_TH + K - 1, HC = SC_TW + K - 1;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * SP_MAX_S + 8 + 1];
-  __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
-  stage_bias(bias_s, p.e, threadIdx.x, blockDim.x);
+  __shared__ __align__(16) float bias_s[TC_MAX_NPAD];    // staged by the epilogue warps (warps 0..3)
   const int SP_S = p.stages;
   __shared__ uint32_t tmem_base_smem;
 
@@ -313,6 +312,8 @@ sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, con
     }
   } else if (warp < 4) {
     // ===== epilogue =====
+    stage_bias(bias_s, p.e, threadIdx.x, 128);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1; const uint32_t ph = (uint32_t)(it >> 1) & 1u;

@@ -33,6 +33,7 @@ struct TcParams {
   int halo_bufs;                           // 1 or 2 halo buffers
   int base_off_mode;                       // descriptor base_offset: 0 = always 0, 1 = (addr >> 7) & 7
   // persistent kernel
+  long long bias_img_stride;               // floats between consecutive images' bias vectors (0 = one shared vector)
   int n_tiles;                             // tiles_x * tiles_y * N
   int b_resident;                          // 1: all weight chunks stay in shared memory for the whole kernel
 };
@@ -155,8 +156,9 @@ __device__ __forceinline__ void relu_sweep(uint32_t base, uint32_t bytes, int et
 // broadcast 16-byte loads instead of one predicated global load per output element (ncu r01g: that single line
 // was 16 % of all warp instructions of the SepConv kernel — more than its FFMA2s).
 constexpr int TC_MAX_NPAD = 256;
-__device__ __forceinline__ void stage_bias(float* bias_s, const TcParams& p, int tid, int nthreads) {
-  for (int i = tid; i < p.n_pad; i += nthreads) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+__device__ __forceinline__ void stage_bias(float* bias_s, const TcParams& p, int tid, int nthreads, int n = 0) {
+  const float* b = p.bias ? p.bias + (long long)n * p.bias_img_stride : nullptr;      // per-image bias (ASPP pool branch)
+  for (int i = tid; i < p.n_pad; i += nthreads) bias_s[i] = (b && i < p.Cout) ? __ldg(b + i) : 0.f;
 }
 
 // spin on an mbarrier with a short sleep between polls: for waiters with slack (producers, epilogue warps), so

@@ -113,6 +113,16 @@ class ConvWeights:
         self.cin, self.cout, self.kh, self.kw = ci, co, kh, kw
         self._packed: Optional[torch.Tensor] = None
 
+    @classmethod
+    def from_folded(cls, w_hwio: torch.Tensor, bias: Optional[torch.Tensor]) -> "ConvWeights":
+        """From already folded fp32 [kh][kw][Cin][Cout] weights (e.g. an input-channel slice of another conv)."""
+        self = cls.__new__(cls)
+        self.w = w_hwio.contiguous()
+        self.bias = bias
+        self.kh, self.kw, self.cin, self.cout = self.w.shape
+        self._packed = None
+        return self
+
     def packed_tc(self) -> torch.Tensor:
         if self._packed is None:
             nbytes = lib.add_conv2d_tc_packed_bytes(self.cin, self.cout, self.kh, self.kw)
@@ -270,9 +280,15 @@ class Builder:
 
     # ---- ops --------------------------------------------------------------------------------
     def conv(self, x: View, y: View, cw: ConvWeights, stride: int = 1, pad: int = 0, dil: int = 1,
-             flags: int = 0, tag: str = "conv") -> None:
+             flags: int = 0, tag: str = "conv", image_bias: Optional[torch.Tensor] = None) -> None:
+        """image_bias: fp32 [N, Cout] per-image bias replacing cw.bias (ASPP pool branch, see aspp_pool_bias)."""
         assert x.c == cw.cin and y.c == cw.cout, (x.c, cw.cin, y.c, cw.cout, tag)
         self.keep.append(cw)
+        bias_ptr, bias_stride = _ptr(cw.bias), 0
+        extra_reads = ()
+        if image_bias is not None:
+            assert image_bias.dtype == torch.float32 and tuple(image_bias.shape) == (x.n, cw.cout) and image_bias.is_contiguous()
+            bias_ptr, bias_stride, extra_reads = image_bias.data_ptr(), cw.cout, (image_bias,)
         # tcgen05 path: bf16 NHWC input whose base/stride are 16-byte multiples (TMA), Cout <= 256
         use_tc = (x.dtype == torch.bfloat16 and tc_available() and cw.cout <= 256 and stride <= 2
                   and x.buf.shape[3] % 8 == 0 and x.c_off % 8 == 0
@@ -287,14 +303,14 @@ class Builder:
                     + cw.cin * cw.cout * cw.kh * cw.kw * (2 if use_tc else 4))
         if use_tc:
             self._emit(lib.add_conv2d_tc_fwd,
-                       (self._d(x), self._d(y), cw.packed_tc().data_ptr(), _ptr(cw.bias), cw.kh, cw.kw,
+                       (self._d(x), self._d(y), cw.packed_tc().data_ptr(), bias_ptr, bias_stride, cw.kh, cw.kw,
                         stride, pad, dil, flags), tag + ":tc", dict(kernel="conv2d_tc", **meta),
-                       reads=(x, y) if flags & ACCUMULATE else (x,), writes=(y,))
+                       reads=((x, y) if flags & ACCUMULATE else (x,)) + extra_reads, writes=(y,))
         else:
             self._emit(lib.add_conv2d_fwd,
-                       (self._d(x), self._d(y), cw.w.data_ptr(), _ptr(cw.bias), cw.kh, cw.kw,
+                       (self._d(x), self._d(y), cw.w.data_ptr(), bias_ptr, bias_stride, cw.kh, cw.kw,
                         stride, pad, dil, flags), tag, dict(kernel="conv2d_ffma", **meta),
-                       reads=(x, y) if flags & ACCUMULATE else (x,), writes=(y,))
+                       reads=((x, y) if flags & ACCUMULATE else (x,)) + extra_reads, writes=(y,))
 
     def stem_nchw(self, src: torch.Tensor, y: View, w_packed: torch.Tensor, bias: torch.Tensor, flags: int,
                   tag: str = "stem0") -> None:
@@ -361,6 +377,19 @@ class Builder:
         self._emit(lib.add_global_avgpool_fwd, (self._d(x), out.data_ptr(), flags, ws.data_ptr(), nbytes), tag,
                    dict(kernel="global_avgpool", flops=x.n * x.h * x.w * x.c, bytes=x.n * x.h * x.w * x.c * x.buf.element_size()),
                    reads=(x,), writes=(out, ws))
+
+    def aspp_pool_bias(self, pooled: torch.Tensor, cw5: ConvWeights, w_out_pool: torch.Tensor,
+                       b_out: Optional[torch.Tensor], out: torch.Tensor, tag: str = "aspp_pool_bias") -> None:
+        """out[n][co] = b_out[co] + sum_d w_out_pool[d][co] * relu(b5[d] + sum_ci w5[ci][d] * pooled[n][ci])."""
+        n, cin = pooled.shape[0], cw5.cin
+        depth, cout = cw5.cout, out.shape[1]
+        assert cw5.kh == 1 and tuple(w_out_pool.shape) == (depth, cout) and tuple(out.shape) == (n, cout)
+        self.keep.extend((cw5, w_out_pool, b_out))
+        self._emit(lib.add_aspp_pool_bias_fwd,
+                   (pooled.data_ptr(), n, cin, cw5.w.data_ptr(), _ptr(cw5.bias), depth, w_out_pool.data_ptr(), _ptr(b_out),
+                    cout, out.data_ptr()), tag,
+                   dict(kernel="aspp_pool_bias", flops=2 * n * (cin * depth + depth * cout), bytes=4 * (cin * depth + depth * cout)),
+                   reads=(pooled,), writes=(out,))
 
     def nchw_to_nhwc(self, src: torch.Tensor, c_src: int, y: View, tag: str = "nchw2nhwc") -> None:
         self.keep.append(src)

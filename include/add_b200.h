@@ -77,7 +77,10 @@ int add_nhwc_to_nchw(const add_tensor_t* x, float* dst, void* stream);
  * w: fp32, layout [kh][kw][Cin][Cout] with the BN scale already folded in; bias: fp32[Cout] or NULL.
  * `pad` may be negative (FactorizedReduce's odd lattice).  Out-of-range taps read zero. */
 int add_conv2d_fwd(const add_tensor_t* x, const add_tensor_t* y, const float* w, const float* bias,
-                   int kh, int kw, int stride, int pad, int dil, uint32_t flags, void* stream);
+                   int64_t bias_image_stride, int kh, int kw, int stride, int pad, int dil, uint32_t flags,
+                   void* stream);
+/* bias_image_stride: 0 = one bias vector; else image n uses bias + n*bias_image_stride (floats) — how the ASPP
+ * image-pool branch (constant over an image) enters the 1x1 over the concatenation (aspp_train.py:49-59). */
 
 /* ---- dense convolution on tcgen05 tensor cores (bf16 in, fp32 TMEM accumulate) ----------- */
 /* Same contract as add_conv2d_fwd for bf16 activations; weights are pre-packed by
@@ -85,7 +88,7 @@ int add_conv2d_fwd(const add_tensor_t* x, const add_tensor_t* y, const float* w,
 int64_t add_conv2d_tc_packed_bytes(int cin, int cout, int kh, int kw);
 int add_conv2d_tc_pack(const float* w_hwio, int cin, int cout, int kh, int kw, void* packed_host);
 int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, const void* w_packed,
-                      const float* bias, int kh, int kw, int stride, int pad, int dil,
+                      const float* bias, int64_t bias_image_stride, int kh, int kw, int stride, int pad, int dil,
                       uint32_t flags, void* stream);
 
 /* ---- first layer on the bf16 path: NCHW fp32 image -> 3x3 stride-2 conv 3->64 + folded BN (+ReLU) -> NHWC
@@ -131,6 +134,14 @@ int add_gather_images(const void* src, void* dst, const int32_t* idx_dev, int co
 int64_t add_global_avgpool_workspace_bytes(int n, int h, int w, int c);
 int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_t flags, void* workspace,
                            int64_t workspace_bytes, void* stream);
+
+/* ---- ASPP image-pool branch as a per-image bias (aspp_train.py:49-59): GAP -> 1x1 (+BN, ReLU) -> align_corners
+ * upsample from 1x1 (a broadcast) -> its 256 channels of the 1280->256 1x1.  Constant over the image, so
+ *   bias_out[n][co] = b_out[co] + sum_d w_out_pool[d][co] * relu(b5[d] + sum_ci w5[ci][d] * pooled[n][ci])
+ * (fp32; w5 [cin][depth], w_out_pool [depth][cout] = the pool-branch rows of the folded 1x1) feeds
+ * add_conv2d*_fwd(bias_image_stride = cout) over the other four branches. */
+int add_aspp_pool_bias_fwd(const float* pooled, int n, int cin, const float* w5, const float* b5, int depth,
+                           const float* w_out_pool, const float* b_out, int cout, float* bias_out, void* stream);
 
 /* ---- EDM tail (ADD.py:509-513,523-525): pooled[n][128] → Linear/ReLU ×2 → Linear → out[n] */
 int add_edm_mlp_fwd(const float* pooled, int n, const float* w0, const float* b0, const float* w1,

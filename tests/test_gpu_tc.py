@@ -237,3 +237,27 @@ def test_stem_tc_matches_torch(hw):
     torch.cuda.synchronize()
     ref = F.relu(F.conv2d(_bf16_exact(x), w, bias, stride=2, padding=1)).permute(0, 2, 3, 1)
     assert util.rel_err(y.buf.float(), ref) < 2 ** -7
+
+
+@pytest.mark.parametrize("tc", [True, False], ids=["tcgen05", "ffma"])
+@pytest.mark.parametrize("hw", [(9, 40), (40, 300)])
+def test_per_image_bias_matches_torch(tc, hw):
+    """bias_image_stride (ASPP pool branch folded into the 1x1): image n gets its own bias vector.  vs plain PyTorch
+    fp32 on bf16-representable operands; fp32 output, tolerance 2e-5 max-norm relative."""
+    import torch.nn.functional as F
+    H, W = hw
+    g = torch.Generator().manual_seed(H * 31 + W)
+    n, cin, cout = 3, 128, 64
+    x = torch.randn(n, H, W, cin, generator=g).to(torch.bfloat16).to(DEV)
+    w = _bf16_exact(torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5).to(DEV)
+    bias_n = torch.randn(n, cout, generator=g).to(DEV)
+    rt.set_tc_enabled(tc)
+    try:
+        b = Builder(DEV, torch.bfloat16)
+        y = b.alloc(n, H, W, cout, torch.float32)
+        b.conv(View(x), y, ConvWeights(w), 1, 0, 1, RELU_IN, image_bias=bias_n)
+        torch.cuda.synchronize()
+    finally:
+        rt.set_tc_enabled(True)
+    ref = F.conv2d(F.relu(x.float().permute(0, 3, 1, 2)), w) + bias_n.view(n, cout, 1, 1)
+    assert util.rel_err(y.buf, ref.permute(0, 2, 3, 1)) < 2e-5
