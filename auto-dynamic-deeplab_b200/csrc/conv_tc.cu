@@ -402,17 +402,22 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         mbar_wait((relu_in ? bar_hrelu : bar_hfull) + 8 * hb, hph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t halo = smem_base + hb * halo_bytes;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int ky = tap / p.taps_w, kx = tap - ky * p.taps_w;
-          mbar_wait(bar_bfull + 8 * s2, bph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_src = halo + (uint32_t)(ky * p.halo_pitch + kx * p.dil) * 128u;
-          const uint64_t adesc = make_kmajor_sw128_desc_shifted(a_src, p.base_off_mode);
-          const uint64_t bdesc = make_kmajor_sw128_desc(b_base + s2 * p.b_bytes);
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-          umma_commit(bar_bempty + 8 * s2);
-          if (++s2 == p.stages) { s2 = 0; bph ^= 1; }
+        const uint64_t adesc0 = make_kmajor_sw128_desc_shifted(halo, p.base_off_mode);
+        const uint64_t bdesc0 = make_kmajor_sw128_desc(b_base);
+        const uint32_t row_step = (uint32_t)p.halo_pitch * 8u, tap_step = (uint32_t)p.dil * 8u, bstep = p.b_bytes >> 4;
+        uint32_t acc = kc > 0 ? 1u : 0u;
+        uint32_t a_row = 0;
+        for (int ky = 0; ky < kh; ++ky, a_row += row_step) {
+          uint32_t a_off = a_row;
+          for (int kx = 0; kx < p.taps_w; ++kx, a_off += tap_step) {
+            mbar_wait(bar_bfull + 8 * s2, bph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t adesc = adesc0 + a_off, bdesc = bdesc0 + (uint32_t)s2 * bstep;
+#pragma unroll 4
+            for (int k = 0; k < ksteps; ++k) { umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc); acc = 1u; }
+            umma_commit(bar_bempty + 8 * s2);
+            if (++s2 == p.stages) { s2 = 0; bph ^= 1; }
+          }
         }
         umma_commit(bar_hempty + 8 * hb);     // halo buffer free once this chunk's MMAs have read it
         if (++hb == p.halo_bufs) { hb = 0; hph ^= 1; }
@@ -439,6 +444,206 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---- persistent halo-resident kernel -----------------------------------------------------------------
+// Same A-operand scheme as conv2d_tc_halo_kernel (halo rows resident, taps through shifted descriptors), but a
+// CTA loops over tiles: two halo buffers form a ring over (tile, channel chunk) so the next tile's halo streams in
+// while the current one is multiplied, the accumulator is double-buffered in TMEM (epilogue of tile i overlaps the
+// MMAs of tile i+1), and when all taps' weights fit they are loaded ONCE and stay resident — the one-tile-per-CTA
+// kernel re-streamed every weight tile from L2 for each 128-pixel row (25 x 6 KB for a 5x5 at C=40).
+//   warp 0 halo producer | warp 1 MMA issuer (+TMEM alloc) | warp 2 weight producer | warps 3..6 ReLU sweep |
+//   warps 7..10 epilogue (TMEM lane quadrants 3,0,1,2)
+constexpr int TCHP_THREADS = 352;
+constexpr int TCHP_MAX_STAGES = 16;          // weight ring depth when the taps do not fit resident
+
+__global__ void __launch_bounds__(TCHP_THREADS, 1)
+conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // halo full/empty/relu [2], b_full[s], b_empty[s], tfull[2], tempty[2], bres
+  __shared__ __align__(8) uint64_t bars[6 + 2 * TCHP_MAX_STAGES + 5];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
+
+  const int kh = p.taps / p.taps_w;
+  const int iters = p.taps * p.kchunks;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t halo_bytes = (uint32_t)kh * p.halo_pitch * 128u;
+  const uint32_t b_base = smem_base + (uint32_t)p.halo_bufs * halo_bytes;  // ring slots, or the resident image
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool relu_in = (p.flags & ADD_RELU_IN) != 0;
+  const uint32_t tmem_cols = (uint32_t)p.tmem_cols;
+
+  const uint32_t bar_hfull = smem_u32(&bars[0]);
+  const uint32_t bar_hempty = smem_u32(&bars[2]);
+  const uint32_t bar_hrelu = smem_u32(&bars[4]);
+  const uint32_t bar_bfull = smem_u32(&bars[6]);
+  const uint32_t bar_bempty = smem_u32(&bars[6 + TCHP_MAX_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[6 + 2 * TCHP_MAX_STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[6 + 2 * TCHP_MAX_STAGES + 2]);
+  const uint32_t bar_bres = smem_u32(&bars[6 + 2 * TCHP_MAX_STAGES + 4]);
+
+  if (threadIdx.x == 0) {
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar_hfull + 8 * h, 1);
+      mbar_init(bar_hempty + 8 * h, 1);
+      mbar_init(bar_hrelu + 8 * h, 128);
+      mbar_init(bar_tfull + 8 * h, 1);
+      mbar_init(bar_tempty + 8 * h, 4);
+    }
+    for (int s2 = 0; s2 < p.stages; ++s2) {
+      mbar_init(bar_bfull + 8 * s2, 1);
+      mbar_init(bar_bempty + 8 * s2, 1);
+    }
+    mbar_init(bar_bres, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_smem)), "r"(2u * tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ===== halo producer: kh row boxes per (tile, 64-channel chunk) =====
+    if (lane == 0) {
+      pdl_wait();
+      int hb = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(bar_hempty + 8 * hb, ph ^ 1);
+          mbar_expect_tx(bar_hfull + 8 * hb, halo_bytes);
+          const uint32_t dst = smem_base + hb * halo_bytes;
+          for (int ky = 0; ky < kh; ++ky)
+            tma_load_4d(dst + ky * p.halo_pitch * 128, &map_x, bar_hfull + 8 * hb, kc * TC_BK, tx * TC_BM - p.pad,
+                        ty - p.pad + ky * p.dil, n);
+          if (++hb == p.halo_bufs) { hb = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== weight producer: resident image once, or one [n_pad x 64] tile per (tile, chunk, tap) through the ring =====
+    if (lane == 0) {
+      if (p.b_resident) {
+        mbar_expect_tx(bar_bres, (uint32_t)iters * p.b_bytes);
+        for (int it = 0; it < iters; ++it) tma_load_3d(b_base + it * p.b_bytes, &map_w, bar_bres, 0, 0, it);
+      } else {
+        int s2 = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            for (int tap = 0; tap < p.taps; ++tap) {
+              mbar_wait(bar_bempty + 8 * s2, ph ^ 1);
+              mbar_expect_tx(bar_bfull + 8 * s2, p.b_bytes);
+              tma_load_3d(b_base + s2 * p.b_bytes, &map_w, bar_bfull + 8 * s2, 0, 0, tap * p.kchunks + kc);
+              if (++s2 == p.stages) { s2 = 0; ph ^= 1; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      if (p.b_resident) mbar_wait(bar_bres, 0);
+      int hb = 0; uint32_t hph = 0; int s2 = 0; uint32_t bph = 0; int ti = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+        const int ab = ti & 1; const uint32_t tph = (uint32_t)(ti >> 1) & 1u;
+        mbar_wait(bar_tempty + 8 * ab, tph ^ 1u);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          const int krem = p.Cin - kc * TC_BK;
+          const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
+          mbar_wait((relu_in ? bar_hrelu : bar_hfull) + 8 * hb, hph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          // The single issuing thread is the pipeline's metronome: keep its per-MMA instruction count minimal
+          // (ncu r01l: a division per tap and 64-bit descriptor rebuilds made it ~700 instructions per tile and
+          // the tensor pipe idle 84 % of the time).  Descriptors differ only in their 14-bit address field.
+          const uint32_t halo = smem_base + hb * halo_bytes;
+          const uint64_t adesc0 = make_kmajor_sw128_desc_shifted(halo, p.base_off_mode);
+          const uint64_t bdesc0 = make_kmajor_sw128_desc(b_base);
+          const uint32_t row_step = (uint32_t)p.halo_pitch * 8u, tap_step = (uint32_t)p.dil * 8u;   // in 16-byte units
+          const uint32_t bstep = p.b_bytes >> 4;
+          uint32_t bidx = p.b_resident ? (uint32_t)kc * bstep : 0u;              // resident: tile (tap*kchunks+kc)
+          const uint32_t bidx_step = (uint32_t)p.kchunks * bstep;
+          uint32_t acc = kc > 0 ? 1u : 0u;
+          uint32_t a_row = 0;
+          for (int ky = 0; ky < kh; ++ky, a_row += row_step) {
+            uint32_t a_off = a_row;
+            for (int kx = 0; kx < p.taps_w; ++kx, a_off += tap_step) {
+              uint64_t bdesc;
+              if (p.b_resident) {
+                bdesc = bdesc0 + bidx; bidx += bidx_step;
+              } else {
+                mbar_wait(bar_bfull + 8 * s2, bph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                bdesc = bdesc0 + (uint32_t)s2 * bstep;
+              }
+              const uint64_t adesc = adesc0 + a_off;
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k) { umma_bf16(tmem_base + ab * tmem_cols, adesc + 2 * k, bdesc + 2 * k, idesc, acc); acc = 1u; }
+              if (!p.b_resident) {
+                umma_commit(bar_bempty + 8 * s2);
+                if (++s2 == p.stages) { s2 = 0; bph ^= 1; }
+              }
+            }
+          }
+          umma_commit(bar_hempty + 8 * hb);     // halo buffer free once this chunk's MMAs have read it
+          if (++hb == p.halo_bufs) { hb = 0; hph ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * ab);
+      }
+    }
+  } else if (warp < 7) {
+    // ===== ReLU sweep (one per halo chunk): warps 3..6 =====
+    if (relu_in) {
+      const int et = threadIdx.x - 96;        // 0..127
+      int hb = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(bar_hfull + 8 * hb, ph);
+          relu_sweep(smem_base + hb * halo_bytes, halo_bytes, et);
+          mbar_arrive(bar_hrelu + 8 * hb);
+          if (++hb == p.halo_bufs) { hb = 0; ph ^= 1; }
+        }
+    }
+  } else {
+    // ===== epilogue: warps 7..10 =====
+    pdl_wait();                               // += y reads and y writes must follow the previous kernel
+    int cur_n = (int)blockIdx.x / tiles_per_img;
+    stage_bias(bias_s, p, threadIdx.x - 224, 128, cur_n);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      const int ab = ti & 1; const uint32_t tph = (uint32_t)(ti >> 1) & 1u;
+      const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      if (p.bias_img_stride != 0 && n != cur_n) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        stage_bias(bias_s, p, threadIdx.x - 224, 128, n);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_n = n;
+      }
+      mbar_wait_relaxed(bar_tfull + 8 * ab, tph);
+      epilogue_store(p, tmem_base + ab * tmem_cols, bias_s, warp, lane, n, ty, tx * TC_BM);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * tmem_cols) : "memory");
   }
 }
 
@@ -587,6 +792,44 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
       long long g = (long long)sms * (two ? 2 : 1);
       if (g > grid) g = grid;
       launch_kernel(conv2d_tc_persistent_kernel, dim3((unsigned)g), dim3(TCP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
+      ADD_RETURN_LAUNCH();
+    }
+  }
+  if (halo && g_persistent) {
+    const int iters = p.taps * p.kchunks;
+    const size_t hbytes = (size_t)kh * p.halo_pitch * 128u;
+    const size_t budget = 222u * 1024u;
+    TcParams q = p;
+    q.n_tiles = (int)grid;
+    size_t psmem = 0;
+    bool ok = true;
+    if (2 * hbytes + (size_t)iters * p.b_bytes + 1024 <= budget) {
+      // every tap's weights resident + two halo buffers (next tile's halo streams in under this tile's MMAs)
+      q.b_resident = 1; q.halo_bufs = 2;
+      psmem = 2 * hbytes + (size_t)iters * p.b_bytes + 1024;
+    } else {
+      // weights stream through a ring: a deep ring matters more than a second halo buffer (each weight tile is a
+      // full TMA round trip; with 3 slots the 25 taps of a 5x5 were latency-bound)
+      q.b_resident = 0;
+      q.halo_bufs = (2 * hbytes + 8 * (size_t)p.b_bytes + 1024 <= budget) ? 2 : 1;
+      long long sb = ((long long)budget - 1024 - (long long)q.halo_bufs * (long long)hbytes) / (long long)p.b_bytes;
+      if (sb > TCHP_MAX_STAGES) sb = TCHP_MAX_STAGES;
+      if (sb < 2) ok = false;
+      q.stages = (int)sb;
+      psmem = (size_t)q.halo_bufs * hbytes + (size_t)(sb > 0 ? sb : 0) * p.b_bytes + 1024;
+    }
+    // measured (r01l microbench): the streaming-weights variant loses to two co-resident one-tile CTAs for the 5x5s;
+    // the persistent kernel is used where the weights are resident (3x3 at C <= 64 per chunk: stem1, dil_conv_3x3)
+    if (ok && q.b_resident && 2 * q.tmem_cols <= 512) {
+      static std::once_flag hponce;
+      std::call_once(hponce, [] {
+        cudaFuncSetAttribute(conv2d_tc_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+        cudaFuncSetAttribute(conv2d_tc_halo_persistent_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      });
+      int sms = 148;
+      { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      long long g = sms < grid ? sms : grid;
+      launch_kernel(conv2d_tc_halo_persistent_kernel, dim3((unsigned)g), dim3(TCHP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, q);
       ADD_RETURN_LAUNCH();
     }
   }

@@ -68,6 +68,12 @@ CASES = [
     (400, 80, 1, 1, 0, 1, 127, 200, RELU_IN | RELU_OUT),
     (64, 64, 3, 1, 1, 1, 130, 200, RELU_OUT),
     (64, 128, 3, 2, 1, 1, 257, 300, RELU_IN),
+    # persistent halo kernel: more row tiles than SMs; resident weights (3x3 C<=64, 5x5 ring), two channel chunks
+    (40, 40, 5, 1, 4, 2, 100, 253, RELU_IN | ACCUMULATE),
+    (40, 40, 3, 1, 2, 2, 110, 250, 0),
+    (64, 64, 3, 1, 1, 1, 90, 300, RELU_OUT),
+    (80, 80, 3, 1, 2, 2, 120, 127, RELU_IN),
+    (80, 80, 5, 1, 4, 2, 100, 128, RELU_IN | ACCUMULATE),
 ]
 
 
