@@ -40,6 +40,7 @@ _SIGS = {
     "add_version": (c_int, []),
     "add_device_sm_count": (c_int, []),
     "add_set_pdl": (c_int, [c_int]),
+    "add_set_persistent_grid_pct": (c_int, [c_int]),
     "add_nchw_to_nhwc": (c_int, [c_void_p, c_int, TP, c_void_p]),
     "add_nhwc_to_nchw": (c_int, [TP, c_void_p, c_void_p]),
     "add_conv2d_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),

@@ -31,3 +31,8 @@ int g_add_pdl = 1;
 /* 1 (default) = tcgen05 kernels are launched with programmatic stream serialization (their prologue overlaps the
  * previous kernel's tail; they wait for it with griddepcontrol.wait before touching activations); 0 = plain launches. */
 extern "C" int add_set_pdl(int on) { g_add_pdl = on ? 1 : 0; return ADD_OK; }
+
+int g_add_grid_pct = 100;
+/* Tuning: persistent kernels launch (pct/100) x their default CTA count (default 100), leaving room for kernels of
+ * other streams of the captured graph to co-reside. */
+extern "C" int add_set_persistent_grid_pct(int pct) { if (pct < 10 || pct > 100) return ADD_ERR_BAD_ARG; g_add_grid_pct = pct; return ADD_OK; }

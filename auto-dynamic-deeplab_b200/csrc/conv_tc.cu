@@ -789,8 +789,9 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
       });
       int sms = 148;
       { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-      long long g = (long long)sms * (two ? 2 : 1);
+      long long g = (long long)sms * (two ? 2 : 1) * g_add_grid_pct / 100;
       if (g > grid) g = grid;
+      if (g < 1) g = 1;
       launch_kernel(conv2d_tc_persistent_kernel, dim3((unsigned)g), dim3(TCP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
       ADD_RETURN_LAUNCH();
     }

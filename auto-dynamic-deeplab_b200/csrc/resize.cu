@@ -285,34 +285,49 @@ extern "C" int add_edm_mlp_fwd(const float* pooled, int n, const float* w0, cons
 // One block per image, fp32 throughout; replaces the GAP->1x1->broadcast->concat-slice round trip (268 MB written
 // and re-read per 4 images at 256x512).
 namespace {
-__global__ void __launch_bounds__(256)
+constexpr int PB_THREADS = 1024, PB_KSPLIT = 4;
+// thread (o, q): output o (< 256), reduction slice q (k = q, q+4, ...); partial sums meet in shared memory in
+// fixed order (deterministic)
+__device__ __forceinline__ void pb_gemv(const float* __restrict__ w, const float* __restrict__ bias, const float* vin, int kdim,
+                                        int odim, float* part, float* vout, bool relu) {
+  for (int o0 = 0; o0 < odim; o0 += PB_THREADS / PB_KSPLIT) {
+    const int o = o0 + (threadIdx.x % (PB_THREADS / PB_KSPLIT)), q = threadIdx.x / (PB_THREADS / PB_KSPLIT);
+    float s = 0.f;
+    if (o < odim) {
+#pragma unroll 8
+      for (int k = q; k < kdim; k += PB_KSPLIT) s = fmaf(__ldg(w + (size_t)k * odim + o), vin[k], s);
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (q == 0 && o < odim) {
+      float t = bias ? bias[o] : 0.f;
+#pragma unroll
+      for (int j = 0; j < PB_KSPLIT; ++j) t += part[j * (PB_THREADS / PB_KSPLIT) + (threadIdx.x % (PB_THREADS / PB_KSPLIT))];
+      vout[o] = relu ? fmaxf(t, 0.f) : t;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(PB_THREADS)
 aspp_pool_bias_kernel(const float* __restrict__ pooled, int cin, const float* __restrict__ w5, const float* __restrict__ b5,
                       int depth, const float* __restrict__ w_out_pool, const float* __restrict__ b_out, int cout,
                       float* __restrict__ bias_out) {
-  extern __shared__ float sm[];                 // [cin] pooled, [depth] p5
-  float* pin = sm; float* p5 = sm + cin;
+  extern __shared__ float sm[];                 // [cin] pooled, [depth] p5, [PB_THREADS] partials
+  float* pin = sm; float* p5 = sm + cin; float* part = p5 + depth;
   const int n = blockIdx.x;
-  for (int i = threadIdx.x; i < cin; i += 256) pin[i] = pooled[(size_t)n * cin + i];
+  for (int i = threadIdx.x; i < cin; i += PB_THREADS) pin[i] = pooled[(size_t)n * cin + i];
   __syncthreads();
-  for (int d = threadIdx.x; d < depth; d += 256) {
-    float s = b5 ? b5[d] : 0.f;
-    for (int ci = 0; ci < cin; ++ci) s = fmaf(__ldg(w5 + (size_t)ci * depth + d), pin[ci], s);
-    p5[d] = fmaxf(s, 0.f);
-  }
-  __syncthreads();
-  for (int co = threadIdx.x; co < cout; co += 256) {
-    float s = b_out ? b_out[co] : 0.f;
-    for (int d = 0; d < depth; ++d) s = fmaf(__ldg(w_out_pool + (size_t)d * cout + co), p5[d], s);
-    bias_out[(size_t)n * cout + co] = s;
-  }
+  pb_gemv(w5, b5, pin, cin, depth, part, p5, true);
+  pb_gemv(w_out_pool, b_out, p5, depth, cout, part, bias_out + (size_t)n * cout, false);
 }
 }  // namespace
 
 extern "C" int add_aspp_pool_bias_fwd(const float* pooled, int n, int cin, const float* w5, const float* b5, int depth,
                                       const float* w_out_pool, const float* b_out, int cout, float* bias_out, void* stream) {
   ADD_CHECK_ARG(pooled && w5 && w_out_pool && bias_out && n > 0 && cin > 0 && depth > 0 && cout > 0);
-  ADD_CHECK_SUP((size_t)(cin + depth) * sizeof(float) <= 48 * 1024);
-  aspp_pool_bias_kernel<<<n, 256, (size_t)(cin + depth) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  ADD_CHECK_SUP((size_t)(cin + depth + PB_THREADS) * sizeof(float) <= 48 * 1024);
+  aspp_pool_bias_kernel<<<n, PB_THREADS, (size_t)(cin + depth + PB_THREADS) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       pooled, cin, w5, b5, depth, w_out_pool, b_out, cout, bias_out);
   ADD_RETURN_LAUNCH();
 }

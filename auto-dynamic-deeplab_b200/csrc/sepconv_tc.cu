@@ -522,8 +522,9 @@ extern "C" int add_sepconv_half_tc_fwd(const add_tensor_t* x, const add_tensor_t
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     if (psmem <= 200u * 1024u && 2 * q.e.tmem_cols <= 512) {
       const bool two = threads <= 352 && psmem <= 110u * 1024u && 4 * q.e.tmem_cols <= 512;
-      long long g = (long long)sms * (two ? 2 : 1);
+      long long g = (long long)sms * (two ? 2 : 1) * g_add_grid_pct / 100;
       if (g > grid) g = grid;
+      if (g < 1) g = 1;
       if (two) return k == 3 ? launch_sepconv_tc_persistent<3, 352, 2>(map_x, map_w, q, (int)g, threads, psmem, s)
                              : launch_sepconv_tc_persistent<5, 352, 2>(map_x, map_w, q, (int)g, threads, psmem, s);
       return k == 3 ? launch_sepconv_tc_persistent<3, 512, 1>(map_x, map_w, q, (int)g, threads, psmem, s)

@@ -239,6 +239,17 @@ class _FactorizedReduceBase(AddModule):
                 s.eps = bn.eps
         self.cw1 = ConvWeights(self.conv_1.weight, _Half(0, half, self.bn))
         self.cw2 = ConvWeights(self.conv_2.weight, _Half(half, self.C_out, self.bn))
+        # FactorizedReduce (stride 2) as ONE 2x2 stride-2 conv: tap (0,0) carries conv_1 into the first half of the
+        # output channels, tap (1,1) carries conv_2 (the odd lattice x[2i+1, 2j+1], zero outside the image like the
+        # reference's pad + slice) into the second half; taps (0,1),(1,0) are zero.  One launch, aligned channel
+        # range (the halves alone start at C_out/2, which is not 16-byte aligned for C_out = 40).
+        self.cw_merged = None
+        if self.STEP == 2:
+            cin = self.cw1.cin
+            w = torch.zeros(2, 2, cin, self.C_out, device=self.cw1.w.device, dtype=torch.float32)
+            w[0, 0, :, :half] = self.cw1.w[0, 0]
+            w[1, 1, :, half:] = self.cw2.w[0, 0]
+            self.cw_merged = ConvWeights.from_folded(w, torch.cat([self.cw1.bias, self.cw2.bias]).contiguous())
 
     def out_shape(self, n, c, h, w):
         s = self.STEP
@@ -247,6 +258,9 @@ class _FactorizedReduceBase(AddModule):
     def emit(self, b, x, y, flags=0):
         self._ensure_prepared()
         half = self.C_out // 2
+        if self.cw_merged is not None and x.dtype == torch.bfloat16 and rt.tc_available():
+            b.conv(x, y, self.cw_merged, 2, 0, 1, _relu_in(flags), type(self).__name__ + ".merged")
+            return
         b.conv(x, y.slice(0, half), self.cw1, self.STEP, 0, 1, _relu_in(flags), type(self).__name__ + ".even")
         b.conv(x, y.slice(half, half), self.cw2, self.STEP, -(self.STEP // 2), 1, _relu_in(flags),
                type(self).__name__ + ".odd")

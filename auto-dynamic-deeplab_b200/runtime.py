@@ -173,6 +173,8 @@ def set_tc_halo_mode(mode: int) -> None:
 import os as _os
 if _os.environ.get("ADD_PDL"):
     check(lib.add_set_pdl(int(_os.environ["ADD_PDL"])), "set_pdl")
+if _os.environ.get("ADD_GRID_PCT"):
+    check(lib.add_set_persistent_grid_pct(int(_os.environ["ADD_GRID_PCT"])), "set_persistent_grid_pct")
 if _os.environ.get("ADD_TC_HALO_MODE"):
     set_tc_halo_mode(int(_os.environ["ADD_TC_HALO_MODE"]))
 

@@ -80,8 +80,11 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "10", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 3.0:     # nvidia-smi needs a few hundred ms to start
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
