@@ -412,6 +412,7 @@ int launch_sepconv_tc_persistent(const CUtensorMap& map_x, const CUtensorMap& ma
 }
 
 int g_sepconv_merged = 1;  // merged {W*C} halo tensor map for contiguous inputs (A/B switch: mode bit 1)
+int g_sepconv_three = 0;   // 1 = try three CTAs per SM for the 3x3 (tuning; mode bit 2)
 int g_sepconv_stages = 0;  // 0 = auto
 int g_sepconv_mode = 1;    // 1 = persistent pipeline where it fits (default), 0 = one tile per CTA
 
@@ -525,6 +526,16 @@ extern "C" int add_sepconv_half_tc_fwd(const add_tensor_t* x, const add_tensor_t
       long long g = (long long)sms * (two ? 2 : 1) * g_add_grid_pct / 100;
       if (g > grid) g = grid;
       if (g < 1) g = 1;
+      if (two && k == 3 && g_sepconv_three) {
+        // 3x3 at C <= 40: three CTAs per SM (15 depthwise warps) when a 2-deep halo ring fits a third of the SM
+        const size_t psmem3 = fixed + 2 * hstride;
+        if (psmem3 <= 74u * 1024u && 6 * q.e.tmem_cols <= 512) {
+          q.stages = 2;
+          long long g3 = (long long)sms * 3 * g_add_grid_pct / 100;
+          if (g3 > grid) g3 = grid;
+          return launch_sepconv_tc_persistent<3, 352, 3>(map_x, map_w, q, (int)g3, threads, psmem3, s);
+        }
+      }
       if (two) return k == 3 ? launch_sepconv_tc_persistent<3, 352, 2>(map_x, map_w, q, (int)g, threads, psmem, s)
                              : launch_sepconv_tc_persistent<5, 352, 2>(map_x, map_w, q, (int)g, threads, psmem, s);
       return k == 3 ? launch_sepconv_tc_persistent<3, 512, 1>(map_x, map_w, q, (int)g, threads, psmem, s)
@@ -537,7 +548,8 @@ extern "C" int add_sepconv_half_tc_fwd(const add_tensor_t* x, const add_tensor_t
 /* 1 = persistent warp-specialised pipeline where it fits (default); 0 = one tile per CTA (kept for A/B runs). */
 extern "C" int add_sepconv_tc_set_mode(int mode) {
   if (mode >= 16) { g_sepconv_stages = (mode >> 4) & 15; mode &= 15; }      // bits 4..7: forced halo ring depth (tuning)
-  if (mode < 0 || mode > 3) return ADD_ERR_BAD_ARG;
+  if (mode < 0 || mode > 7) return ADD_ERR_BAD_ARG;
+  g_sepconv_three = (mode & 4) ? 1 : 0;
   g_sepconv_mode = mode & 1;
   g_sepconv_merged = (mode & 2) ? 0 : 1;      // bit 1 set = per-pixel halo rows even for contiguous inputs
   return ADD_OK;
