@@ -76,7 +76,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0; uint32_t ph = 0;
       for (int it = 0; it < iters; ++it) {
         const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
@@ -92,7 +92,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int s = 0; uint32_t ph = 0;
       for (int it = 0; it < iters; ++it) {
@@ -198,7 +198,7 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       if (p.b_resident) {
         mbar_expect_tx(bar_bres, (uint32_t)iters * p.b_bytes);
         for (int it = 0; it < iters; ++it) tma_load_3d(bres_base + it * p.b_bytes, &map_w, bar_bres, 0, 0, it);
@@ -222,7 +222,7 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       if (p.b_resident) mbar_wait(bar_bres, 0);
       int s = 0; uint32_t ph = 0; int ti = 0;
@@ -290,6 +290,53 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * tmem_cols) : "memory");
+  }
+}
+
+// ---- MMA issue for one 64-channel chunk of a halo tile ---------------------------------------------
+// The issuing thread is the pipeline's metronome.  With run-time tap / k-step loops it spent ~16 instructions
+// (~160 cycles) per tcgen05.mma while a 128xNx16 MMA with N <= 96 occupies the tensor pipe for only 24-48 cycles
+// (ncu r01p: tensor pipe 19 % busy on stem1, all samples of the issuing warp inside the loop, none in waits).
+// Fully unrolled per (KH, KW, KSTEPS) the descriptor arithmetic is a handful of independent uniform adds.
+template <int KH, int KW, int KS>
+__device__ __forceinline__ void issue_chunk_resident(uint32_t tmem_d, uint64_t adesc0, uint64_t bdesc0, uint32_t row_step,
+                                                     uint32_t tap_step, uint32_t bidx_step, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int ky = 0; ky < KH; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < KW; ++kx) {
+      const uint64_t a = adesc0 + (uint32_t)(ky * row_step + kx * tap_step);
+      const uint64_t b = bdesc0 + (uint32_t)((ky * KW + kx) * bidx_step);
+#pragma unroll
+      for (int k = 0; k < KS; ++k)
+        umma_bf16(tmem_d, a + 2 * k, b + 2 * k, idesc, (ky == 0 && kx == 0 && k == 0) ? acc_first : 1u);
+    }
+  }
+}
+
+// returns false when (kh, kw, ksteps) has no unrolled instance (caller falls back to the generic loop)
+__device__ __forceinline__ bool issue_chunk_resident_dispatch(int kh, int kw, int ks, uint32_t tmem_d, uint64_t adesc0,
+                                                              uint64_t bdesc0, uint32_t row_step, uint32_t tap_step,
+                                                              uint32_t bidx_step, uint32_t idesc, uint32_t acc_first) {
+#define ICR(KH_, KW_, KS_) if (kh == KH_ && kw == KW_ && ks == KS_) { \
+    issue_chunk_resident<KH_, KW_, KS_>(tmem_d, adesc0, bdesc0, row_step, tap_step, bidx_step, idesc, acc_first); return true; }
+  ICR(3, 3, 4) ICR(3, 3, 3) ICR(3, 3, 2) ICR(3, 3, 1)
+#undef ICR
+  return false;
+}
+
+// streamed weights: one ring slot per tap; k-steps unrolled
+template <int KS>
+__device__ __forceinline__ void issue_tap_ring(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) umma_bf16(tmem_d, a + 2 * k, b + 2 * k, idesc, k == 0 ? acc_first : 1u);
+}
+__device__ __forceinline__ void issue_tap_ring_dispatch(int ks, uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc_first) {
+  switch (ks) {
+    case 4: issue_tap_ring<4>(tmem_d, a, b, idesc, acc_first); break;
+    case 3: issue_tap_ring<3>(tmem_d, a, b, idesc, acc_first); break;
+    case 2: issue_tap_ring<2>(tmem_d, a, b, idesc, acc_first); break;
+    default: issue_tap_ring<1>(tmem_d, a, b, idesc, acc_first); break;
   }
 }
 
@@ -367,7 +414,7 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 
   if (warp == 0) {
     // ===== halo producer: kh row boxes per 64-channel chunk =====
-    if (lane == 0) {
+    if (elect_one()) {
       int hb = 0; uint32_t ph = 0;
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(bar_hempty + 8 * hb, ph ^ 1);
@@ -381,7 +428,7 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     }
   } else if (warp == 2) {
     // ===== weight producer: one [n_pad x 64] K-major tile per (chunk, tap) =====
-    if (lane == 0) {
+    if (elect_one()) {
       int s2 = 0; uint32_t ph = 0;
       for (int kc = 0; kc < p.kchunks; ++kc)
         for (int tap = 0; tap < p.taps; ++tap) {
@@ -393,7 +440,7 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int hb = 0; uint32_t hph = 0; int s2 = 0; uint32_t bph = 0;
       for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -412,9 +459,8 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           for (int kx = 0; kx < p.taps_w; ++kx, a_off += tap_step) {
             mbar_wait(bar_bfull + 8 * s2, bph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t adesc = adesc0 + a_off, bdesc = bdesc0 + (uint32_t)s2 * bstep;
-#pragma unroll 4
-            for (int k = 0; k < ksteps; ++k) { umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc); acc = 1u; }
+            issue_tap_ring_dispatch(ksteps, tmem_base, adesc0 + a_off, bdesc0 + (uint32_t)s2 * bstep, idesc, acc);
+            acc = 1u;
             umma_commit(bar_bempty + 8 * s2);
             if (++s2 == p.stages) { s2 = 0; bph ^= 1; }
           }
@@ -515,7 +561,7 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
 
   if (warp == 0) {
     // ===== halo producer: kh row boxes per (tile, 64-channel chunk) =====
-    if (lane == 0) {
+    if (elect_one()) {
       pdl_wait();
       int hb = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -534,7 +580,7 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
     }
   } else if (warp == 2) {
     // ===== weight producer: resident image once, or one [n_pad x 64] tile per (tile, chunk, tap) through the ring =====
-    if (lane == 0) {
+    if (elect_one()) {
       if (p.b_resident) {
         mbar_expect_tx(bar_bres, (uint32_t)iters * p.b_bytes);
         for (int it = 0; it < iters; ++it) tma_load_3d(b_base + it * p.b_bytes, &map_w, bar_bres, 0, 0, it);
@@ -552,7 +598,7 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       if (p.b_resident) mbar_wait(bar_bres, 0);
       int hb = 0; uint32_t hph = 0; int s2 = 0; uint32_t bph = 0; int ti = 0;
@@ -575,24 +621,29 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
           uint32_t bidx = p.b_resident ? (uint32_t)kc * bstep : 0u;              // resident: tile (tap*kchunks+kc)
           const uint32_t bidx_step = (uint32_t)p.kchunks * bstep;
           uint32_t acc = kc > 0 ? 1u : 0u;
-          uint32_t a_row = 0;
-          for (int ky = 0; ky < kh; ++ky, a_row += row_step) {
-            uint32_t a_off = a_row;
-            for (int kx = 0; kx < p.taps_w; ++kx, a_off += tap_step) {
-              uint64_t bdesc;
-              if (p.b_resident) {
-                bdesc = bdesc0 + bidx; bidx += bidx_step;
-              } else {
-                mbar_wait(bar_bfull + 8 * s2, bph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                bdesc = bdesc0 + (uint32_t)s2 * bstep;
-              }
-              const uint64_t adesc = adesc0 + a_off;
-#pragma unroll 4
-              for (int k = 0; k < ksteps; ++k) { umma_bf16(tmem_base + ab * tmem_cols, adesc + 2 * k, bdesc + 2 * k, idesc, acc); acc = 1u; }
-              if (!p.b_resident) {
-                umma_commit(bar_bempty + 8 * s2);
-                if (++s2 == p.stages) { s2 = 0; bph ^= 1; }
+          const uint32_t tmem_d = tmem_base + ab * tmem_cols;
+          if (p.b_resident && issue_chunk_resident_dispatch(kh, p.taps_w, ksteps, tmem_d, adesc0, bdesc0 + bidx, row_step, tap_step,
+                                                            bidx_step, idesc, acc)) {
+            // fully unrolled instance issued
+          } else {
+            uint32_t a_row = 0;
+            for (int ky = 0; ky < kh; ++ky, a_row += row_step) {
+              uint32_t a_off = a_row;
+              for (int kx = 0; kx < p.taps_w; ++kx, a_off += tap_step) {
+                uint64_t bdesc;
+                if (p.b_resident) {
+                  bdesc = bdesc0 + bidx; bidx += bidx_step;
+                } else {
+                  mbar_wait(bar_bfull + 8 * s2, bph);
+                  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                  bdesc = bdesc0 + (uint32_t)s2 * bstep;
+                }
+                issue_tap_ring_dispatch(ksteps, tmem_d, adesc0 + a_off, bdesc, idesc, acc);
+                acc = 1u;
+                if (!p.b_resident) {
+                  umma_commit(bar_bempty + 8 * s2);
+                  if (++s2 == p.stages) { s2 = 0; bph ^= 1; }
+                }
               }
             }
           }

@@ -95,7 +95,7 @@ sepconv_half_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   pdl_wait();                     // the previous kernel's activations are complete and visible from here on
 
   if (is_ctrl) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(bar_in, p.halo_bytes + (uint32_t)p.kchunks * p.e.b_bytes);
       if (p.merged) tma_load_3d(halo, &map_x, bar_in, (x0 - K / 2) * (C >> 2), y0 - K / 2, n);
       else tma_load_4d(halo, &map_x, bar_in, 0, x0 - K / 2, y0 - K / 2, n);
@@ -178,7 +178,7 @@ sepconv_half_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   if (is_ctrl) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_wait(bar_in, 0);                                         // pointwise weights landed
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.e.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -273,7 +273,7 @@ sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, con
 
   if (warp == 4) {
     // ===== producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(bar_b, (uint32_t)p.kchunks * p.e.b_bytes);
       for (int kc = 0; kc < p.kchunks; ++kc) tma_load_3d(b_base + kc * p.e.b_bytes, &map_w, bar_b, 0, 0, kc);
       int it = 0;
@@ -289,7 +289,7 @@ sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, con
     }
   } else if (warp == 5) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.e.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       mbar_wait(bar_b, 0);
       int it = 0;

@@ -70,7 +70,7 @@ stem_conv3x3s2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   const int tiles_per_img = p.tiles_x * p.Ho;
 
   if (is_ctrl) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(bar_w, ST_COUT * 128u);
       tma_load_3d(b_base, &map_w, bar_w, 0, 0, 0);
       mbar_wait(bar_w, 0);

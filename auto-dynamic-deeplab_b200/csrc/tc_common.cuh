@@ -58,6 +58,15 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// One thread of a converged warp, chosen with elect.sync: unlike `lane == 0` the compiler then KNOWS the region is
+// single-threaded and emits each tcgen05.mma / TMA once instead of wrapping it in an elect-and-loop-over-active-
+// threads sequence (4 extra instructions and a branch per MMA in the issuing thread's critical loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -189,7 +198,7 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_
     uint32_t v[16];
     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (!valid) continue;
+    if (!valid || (p.flags & 0x100u)) continue;      // 0x100: experiment — skip the epilogue math and stores
     float f[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -32,8 +32,10 @@ def cases():
     return out
 
 
+import os
+
+
 def main():
-    import os
     if os.environ.get("ADD_SEPCONV_MODE"):
         from add_b200._lib import lib
         assert lib.add_sepconv_tc_set_mode(int(os.environ["ADD_SEPCONV_MODE"])) == 0
@@ -63,6 +65,7 @@ def main():
                 m.emit(b, x, y, 0)
         else:
             cin, cout, k, stride, pad, dil, n, h, w, flags = a
+            flags |= int(os.environ.get("ADD_MB_FLAGS", "0"), 0)
             cw = ConvWeights(torch.randn(cout, cin, k, k, device=DEV) / (cin * k * k) ** 0.5)
             cw.bias = torch.zeros(cout, device=DEV)
             ho, wo = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
