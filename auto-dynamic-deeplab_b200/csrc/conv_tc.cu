@@ -699,6 +699,7 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
 }
 
 // ---- host side -----------------------------------------------------------------------------------
+int g_halo_stream_persistent = 0;   // 1 = use the persistent halo kernel also when the weights stream through a ring (tuning)
 int g_persistent = 1;  // 1 = persistent warp-specialised kernel for the non-halo path (default), 0 = one tile per CTA
 int g_halo_mode = 1;   // 0 = per-tap A tiles only, 1 = halo-resident A (measured on B200: base_offset must stay 0 — the
                        // swizzle is applied on absolute shared-memory address bits; mode 2 (base_offset = phase) is WRONG
@@ -863,7 +864,7 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
       // weights stream through a ring: a deep ring matters more than a second halo buffer (each weight tile is a
       // full TMA round trip; with 3 slots the 25 taps of a 5x5 were latency-bound)
       q.b_resident = 0;
-      q.halo_bufs = (2 * hbytes + 8 * (size_t)p.b_bytes + 1024 <= budget) ? 2 : 1;
+      q.halo_bufs = (2 * hbytes + 5 * (size_t)p.b_bytes + 1024 <= budget) ? 2 : 1;
       long long sb = ((long long)budget - 1024 - (long long)q.halo_bufs * (long long)hbytes) / (long long)p.b_bytes;
       if (sb > TCHP_MAX_STAGES) sb = TCHP_MAX_STAGES;
       if (sb < 2) ok = false;
@@ -872,7 +873,7 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
     }
     // measured (r01l microbench): the streaming-weights variant loses to two co-resident one-tile CTAs for the 5x5s;
     // the persistent kernel is used where the weights are resident (3x3 at C <= 64 per chunk: stem1, dil_conv_3x3)
-    if (ok && q.b_resident && 2 * q.tmem_cols <= 512) {
+    if (ok && (q.b_resident || g_halo_stream_persistent) && 2 * q.tmem_cols <= 512) {
       static std::once_flag hponce;
       std::call_once(hponce, [] {
         cudaFuncSetAttribute(conv2d_tc_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
@@ -894,8 +895,9 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
 
 /* Tuning / experiment switch for the halo-resident A path (see conv2d_tc_halo_kernel). */
 extern "C" int add_conv2d_tc_set_halo_mode(int mode) {
-  if (mode >= 16) { g_persistent = (mode & 16) ? 0 : 1; mode &= 15; }     // bit 4 set = one tile per CTA (A/B runs)
-  else g_persistent = 1;
+  g_persistent = (mode & 16) ? 0 : 1;                 // bit 4 set = one tile per CTA (A/B runs)
+  g_halo_stream_persistent = (mode & 32) ? 1 : 0;     // bit 5 set = persistent halo kernel with streamed weights
+  mode &= 15;
   if (mode < 0 || mode > 2) return ADD_ERR_BAD_ARG;
   g_halo_mode = mode;
   return ADD_OK;
