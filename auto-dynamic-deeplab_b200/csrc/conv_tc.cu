@@ -147,6 +147,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 constexpr int TCP_THREADS = 320;
 constexpr int TCP_MAX_STAGES = 8;
 
+__device__ __forceinline__ void issue_tap_ring_dispatch(int ks, uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc_first);
+
+// MT = M-tiles (128 pixels each) that share every weight tile: with N_pad = 256 the weight tile (32 KB) is 2/3 of a
+// stage's L2->smem traffic and the ASPP / decoder 3x3s ran AT the L2 bandwidth ceiling (1085 TF/s x 48 KB per
+// 128x256x64 MACs = 12.4 TB/s); MT = 2 computes two adjacent pixel tiles per weight tile (1.5x less traffic).
+template <int MT>
 __global__ void __launch_bounds__(TCP_THREADS)
 conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -158,10 +164,11 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bres_base = smem_base;                                                  // resident weights (if any)
   const uint32_t ring_base = smem_base + (p.b_resident ? (uint32_t)iters * p.b_bytes : 0u);
-  const uint32_t stage_bytes = TC_A_BYTES + (p.b_resident ? 0u : p.b_bytes);
+  const uint32_t stage_bytes = MT * TC_A_BYTES + (p.b_resident ? 0u : p.b_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool relu_in = (p.flags & ADD_RELU_IN) != 0;
   const uint32_t tmem_cols = (uint32_t)p.tmem_cols;
+  const int nbuf = (2u * MT * tmem_cols <= 512u) ? 2 : 1;          // accumulator sets: double-buffered when TMEM allows
 
   const uint32_t bar_full = smem_u32(&bars[0]);
   const uint32_t bar_empty = smem_u32(&bars[TCP_MAX_STAGES]);
@@ -184,7 +191,7 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(&tmem_base_smem)), "r"(2u * tmem_cols) : "memory");
+                 ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)nbuf * MT * tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -195,6 +202,8 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   pdl_wait();                     // the previous kernel's activations are complete and visible from here on
   const int BW = 1 << p.bw_log2, BH = TC_BM >> p.bw_log2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int n_units = (p.n_tiles + MT - 1) / MT;                   // a unit = MT consecutive tiles
+  const int n_img = p.n_tiles / tiles_per_img;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -204,17 +213,25 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         for (int it = 0; it < iters; ++it) tma_load_3d(bres_base + it * p.b_bytes, &map_w, bar_bres, 0, 0, it);
       }
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
-        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        const int xin = tx * BW * p.stride - p.pad, yin = ty * BH * p.stride - p.pad;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        int tn[MT], xin[MT], yin[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const int tile = u * MT + m;
+          const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+          const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+          tn[m] = tile < p.n_tiles ? n : n_img;                   // past the end: an image index out of bounds -> zero fill
+          xin[m] = tx * BW * p.stride - p.pad; yin[m] = ty * BH * p.stride - p.pad;
+        }
         int ky = 0, kx = 0, kc = 0;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t a_dst = ring_base + s * stage_bytes;
           mbar_expect_tx(bar_full + 8 * s, stage_bytes);
-          tma_load_4d(a_dst, &map_x, bar_full + 8 * s, kc * TC_BK, xin + kx * p.dil, yin + ky * p.dil, n);
-          if (!p.b_resident) tma_load_3d(a_dst + TC_A_BYTES, &map_w, bar_full + 8 * s, 0, 0, it);
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            tma_load_4d(a_dst + m * TC_A_BYTES, &map_x, bar_full + 8 * s, kc * TC_BK, xin[m] + kx * p.dil, yin[m] + ky * p.dil, tn[m]);
+          if (!p.b_resident) tma_load_3d(a_dst + MT * TC_A_BYTES, &map_w, bar_full + 8 * s, 0, 0, it);
           if (++kc == p.kchunks) { kc = 0; if (++kx == p.taps_w) { kx = 0; ++ky; } }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -226,8 +243,9 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       if (p.b_resident) mbar_wait(bar_bres, 0);
       int s = 0; uint32_t ph = 0; int ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
-        const int ab = ti & 1; const uint32_t tph = (uint32_t)(ti >> 1) & 1u;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
+        const int ab = nbuf == 2 ? (ti & 1) : 0;
+        const uint32_t tph = nbuf == 2 ? ((uint32_t)(ti >> 1) & 1u) : ((uint32_t)ti & 1u);
         mbar_wait(bar_tempty + 8 * ab, tph ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         int kc = 0;
@@ -237,10 +255,13 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
           mbar_wait((relu_in ? bar_relu : bar_full) + 8 * s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_src = ring_base + s * stage_bytes;
-          const uint32_t b_src = p.b_resident ? bres_base + it * p.b_bytes : a_src + TC_A_BYTES;
-          const uint64_t adesc = make_kmajor_sw128_desc(a_src), bdesc = make_kmajor_sw128_desc(b_src);
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16(tmem_base + ab * tmem_cols, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          const uint32_t b_src = p.b_resident ? bres_base + it * p.b_bytes : a_src + MT * TC_A_BYTES;
+          const uint64_t bdesc = make_kmajor_sw128_desc(b_src);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const uint64_t adesc = make_kmajor_sw128_desc(a_src + m * TC_A_BYTES);
+            issue_tap_ring_dispatch(ksteps, tmem_base + (uint32_t)(ab * MT + m) * tmem_cols, adesc, bdesc, idesc, it > 0 ? 1u : 0u);
+          }
           umma_commit(bar_empty + 8 * s);
           if (++kc == p.kchunks) kc = 0;
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -253,10 +274,10 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     if (relu_in) {
       const int et = threadIdx.x - 64;
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         for (int it = 0; it < iters; ++it) {
           mbar_wait(bar_full + 8 * s, ph);
-          relu_sweep(ring_base + s * stage_bytes, TC_A_BYTES, et);
+          relu_sweep(ring_base + s * stage_bytes, MT * TC_A_BYTES, et);
           mbar_arrive(bar_relu + 8 * s);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -264,22 +285,28 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     }
   } else {
     // ===== epilogue: warps 6..9 (TMEM lane quadrants 2,3,0,1) =====
-    int cur_n = (int)blockIdx.x / tiles_per_img;
+    int cur_n = ((int)blockIdx.x * MT) / tiles_per_img;
     stage_bias(bias_s, p, threadIdx.x - 192, 128, cur_n);
     asm volatile("bar.sync 1, 128;" ::: "memory");
     int ti = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
-      const int ab = ti & 1; const uint32_t tph = (uint32_t)(ti >> 1) & 1u;
-      const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
-      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      if (p.bias_img_stride != 0 && n != cur_n) {              // per-image bias: restage when the image changes
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        stage_bias(bias_s, p, threadIdx.x - 192, 128, n);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        cur_n = n;
-      }
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
+      const int ab = nbuf == 2 ? (ti & 1) : 0;
+      const uint32_t tph = nbuf == 2 ? ((uint32_t)(ti >> 1) & 1u) : ((uint32_t)ti & 1u);
       mbar_wait_relaxed(bar_tfull + 8 * ab, tph);
-      epilogue_store(p, tmem_base + ab * tmem_cols, bias_s, warp, lane, n, ty * BH, tx * BW);
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int tile = u * MT + m;
+        if (tile >= p.n_tiles) break;
+        const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        if (p.bias_img_stride != 0 && n != cur_n) {              // per-image bias: restage when the image changes
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          stage_bias(bias_s, p, threadIdx.x - 192, 128, n);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          cur_n = n;
+        }
+        epilogue_store(p, tmem_base + (uint32_t)(ab * MT + m) * tmem_cols, bias_s, warp, lane, n, ty * BH, tx * BW);
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
@@ -289,7 +316,7 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)nbuf * MT * tmem_cols) : "memory");
   }
 }
 
@@ -699,6 +726,7 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
 }
 
 // ---- host side -----------------------------------------------------------------------------------
+int g_conv_mt2 = 1;                 // 1 = two pixel tiles per weight tile for the weight-heavy convs (mode bit 6 clears)
 int g_halo_stream_persistent = 0;   // 1 = use the persistent halo kernel also when the weights stream through a ring (tuning)
 int g_persistent = 1;  // 1 = persistent warp-specialised kernel for the non-halo path (default), 0 = one tile per CTA
 int g_halo_mode = 1;   // 0 = per-tap A tiles only, 1 = halo-resident A (measured on B200: base_offset must stay 0 — the
@@ -825,9 +853,13 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
     p.n_tiles = (int)grid;
     p.b_resident = ((size_t)iters * p.b_bytes <= 72u * 1024u) ? 1 : 0;
     const size_t fixed = 1024 + (p.b_resident ? (size_t)iters * p.b_bytes : 0);
-    const size_t sbytes = TC_A_BYTES + (p.b_resident ? 0 : p.b_bytes);
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    // MT = 2 (two pixel tiles per weight tile) for the weight-heavy big convs: streamed weights, N_pad >= 128, many tiles
+    const int mt = (g_conv_mt2 && !p.b_resident && p.n_pad >= 128 && grid >= 4ll * sms) ? 2 : 1;
+    const size_t sbytes = (size_t)mt * TC_A_BYTES + (p.b_resident ? 0 : p.b_bytes);
     // two CTAs per SM when a 4-deep ring fits in half the shared memory and TMEM (4 accumulators) allows it
-    const bool two = fixed + 4 * sbytes <= 100u * 1024u && 4 * p.tmem_cols <= 512;
+    const bool two = mt == 1 && fixed + 4 * sbytes <= 100u * 1024u && 4 * p.tmem_cols <= 512;
     const size_t budget = two ? 100u * 1024u : 200u * 1024u;
     int st = (int)((budget - fixed) / sbytes);
     if (st > TCP_MAX_STAGES) st = TCP_MAX_STAGES;
@@ -836,15 +868,19 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
       const size_t psmem = fixed + (size_t)st * sbytes;
       static std::once_flag ponce;
       std::call_once(ponce, [] {
-        cudaFuncSetAttribute(conv2d_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv2d_tc_persistent_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       });
-      int sms = 148;
-      { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      const long long units = (grid + mt - 1) / mt;
       long long g = (long long)sms * (two ? 2 : 1) * g_add_grid_pct / 100;
-      if (g > grid) g = grid;
+      if (g > units) g = units;
       if (g < 1) g = 1;
-      launch_kernel(conv2d_tc_persistent_kernel, dim3((unsigned)g), dim3(TCP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
+      if (mt == 2)
+        launch_kernel(conv2d_tc_persistent_kernel<2>, dim3((unsigned)g), dim3(TCP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
+      else
+        launch_kernel(conv2d_tc_persistent_kernel<1>, dim3((unsigned)g), dim3(TCP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
       ADD_RETURN_LAUNCH();
     }
   }
@@ -896,6 +932,7 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
 /* Tuning / experiment switch for the halo-resident A path (see conv2d_tc_halo_kernel). */
 extern "C" int add_conv2d_tc_set_halo_mode(int mode) {
   g_persistent = (mode & 16) ? 0 : 1;                 // bit 4 set = one tile per CTA (A/B runs)
+  g_conv_mt2 = (mode & 64) ? 0 : 1;                   // bit 6 set = one pixel tile per weight tile everywhere
   g_halo_stream_persistent = (mode & 32) ? 1 : 0;     // bit 5 set = persistent halo kernel with streamed weights
   mode &= 15;
   if (mode < 0 || mode > 2) return ADD_ERR_BAD_ARG;
