@@ -198,8 +198,8 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
-  pdl_launch_dependents();
-  pdl_wait();                     // the previous kernel's activations are complete and visible from here on
+  pdl_launch_dependents();        // (waits for the previous kernel: producer before its first activation load,
+                                  //  epilogue warps before their first y access — see pdl_wait() below)
   const int BW = 1 << p.bw_log2, BH = TC_BM >> p.bw_log2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int n_units = (p.n_tiles + MT - 1) / MT;                   // a unit = MT consecutive tiles
@@ -212,6 +212,7 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         mbar_expect_tx(bar_bres, (uint32_t)iters * p.b_bytes);
         for (int it = 0; it < iters; ++it) tma_load_3d(bres_base + it * p.b_bytes, &map_w, bar_bres, 0, 0, it);
       }
+      pdl_wait();
       int s = 0; uint32_t ph = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         int tn[MT], xin[MT], yin[MT];
@@ -288,6 +289,7 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     int cur_n = ((int)blockIdx.x * MT) / tiles_per_img;
     stage_bias(bias_s, p, threadIdx.x - 192, 128, cur_n);
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    pdl_wait();
     int ti = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
       const int ab = nbuf == 2 ? (ti & 1) : 0;

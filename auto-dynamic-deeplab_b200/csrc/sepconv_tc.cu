@@ -268,7 +268,9 @@ sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
   pdl_launch_dependents();
-  pdl_wait();                     // the previous kernel's activations are complete and visible from here on
+  // programmatic dependent launch: only the threads that touch activations wait for the previous kernel (the halo
+  // producer before its first load, the epilogue warps before their first y access); weight loads, the depthwise
+  // warps' register weights and the bias staging overlap the predecessor's tail
   const int tiles_per_img = p.e.tiles_x * p.e.tiles_y;
 
   if (warp == 4) {
@@ -276,6 +278,7 @@ sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, con
     if (elect_one()) {
       mbar_expect_tx(bar_b, (uint32_t)p.kchunks * p.e.b_bytes);
       for (int kc = 0; kc < p.kchunks; ++kc) tma_load_3d(b_base + kc * p.e.b_bytes, &map_w, bar_b, 0, 0, kc);
+      pdl_wait();
       int it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const int s = it % SP_S; const uint32_t ph = (uint32_t)(it / SP_S) & 1u;
@@ -314,6 +317,7 @@ sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, con
     // ===== epilogue =====
     stage_bias(bias_s, p.e, threadIdx.x, 128);
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    pdl_wait();
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1; const uint32_t ph = (uint32_t)(it >> 1) & 1u;

@@ -116,7 +116,10 @@ class _Segment:
         if k > 0:
             self.gather = Plan(b, *self.gather_range)
         if net.use_cuda_graph:
-            self.main.capture()
+            if k > 0 and not is_last or (k > 0 and _TRUNK_PCT != 100):
+                _capture_with_pct(self.main, _TRUNK_PCT)
+            else:
+                self.main.capture()
             if self.gather is not None:
                 self.gather.capture()
 
@@ -145,11 +148,27 @@ class _Head:
         self.out = runner.emit_head_output(b, logits, m, self)
         self.main = Plan(b)
         if net.use_cuda_graph:
-            self.main.capture()
+            _capture_with_pct(self.main, _HEAD_PCT)
 
     @property
     def n_launches(self) -> int:
         return self.main.n_launches
+
+
+import os as _os
+_OVERLAP_HEADS = _os.environ.get("ADD_OVERLAP_HEADS", "1") != "0"
+# share of the persistent kernels' CTAs given to the early-exit head plan / to the trunk plan that runs beside it
+_HEAD_PCT = int(_os.environ.get("ADD_HEAD_PCT", "100"))
+_TRUNK_PCT = int(_os.environ.get("ADD_TRUNK_PCT", "100"))
+
+
+def _capture_with_pct(plan, pct: int) -> None:
+    from ._lib import lib, check
+    check(lib.add_set_persistent_grid_pct(pct), "set_persistent_grid_pct")
+    try:
+        plan.capture()
+    finally:
+        check(lib.add_set_persistent_grid_pct(100), "set_persistent_grid_pct")
 
 
 class _EdmRunner:
@@ -175,6 +194,7 @@ class _EdmRunner:
         if mode == "evaluate":
             self.gt_full = torch.empty((self.n, self.H, self.W), dtype=torch.int64, device=device)
         self.last_launches = 0
+        self._side: Optional[torch.cuda.Stream] = None
 
     # ---- per-plan output tail -------------------------------------------------------------------
     def emit_head_output(self, b: Builder, logits: View, m: int, owner) -> torch.Tensor:
@@ -211,6 +231,7 @@ class _EdmRunner:
         flags = [0] * n
         confs: List[Optional[torch.Tensor]] = [None] * n
         launches = 0
+        pending_side = False
         self.last_plans: List[Plan] = []
         if self.mode == "evaluate":
             self.gt_full.copy_(target, non_blocking=True)
@@ -240,7 +261,18 @@ class _EdmRunner:
                 head.idx.copy_(torch.tensor(ex, dtype=torch.int32), non_blocking=True)
                 if self.mode == "evaluate":
                     head.idx_gt.copy_(torch.tensor([active[j] for j in ex], dtype=torch.int32), non_blocking=True)
-                head.main.run()
+                if co and _OVERLAP_HEADS:
+                    # the early-exit head (throughput-bound: ASPP on the up-sampled map) and the remaining trunk
+                    # (latency-bound small kernels) only READ this segment's state: replay them side by side
+                    main = torch.cuda.current_stream(self.device)
+                    if self._side is None:
+                        self._side = torch.cuda.Stream(self.device)
+                    self._side.wait_stream(main)
+                    with torch.cuda.stream(self._side):
+                        head.main.run()
+                    pending_side = True
+                else:
+                    head.main.run()
                 self.last_plans.append(head.main)
                 launches += head.n_launches
                 for jj, j in enumerate(ex):
@@ -252,6 +284,8 @@ class _EdmRunner:
             nxt.idx.copy_(torch.tensor(co, dtype=torch.int32), non_blocking=True)
             active = [active[j] for j in co]
             seg = nxt
+        if pending_side:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
         self.last_launches = launches
         return outs, flags, confs
 
