@@ -69,3 +69,27 @@ def test_fullsize_early_exit_is_batch_composition_invariant(bench_net):
         assert flags_1[0] == flags_b[i]
         assert float(confs_1[0]) == float(confs_b[i])
         assert torch.equal(cm_1[0], cm_b[i])
+
+
+def test_config1_512x1024_fp32_parity_vs_oracle():
+    """BASELINE.json configs[0]: searched-dense, one 3x512x1024 image, fp32, all exits + confusion matrix — the
+    CUDA fp32 path against the CPU oracle on the same seeded input and weights.  Gates (north_star): logits within
+    1e-3 max-norm relative, argmax agreement >= 99.9 %, confusion matrix bit-exact given identical predictions."""
+    from oracle import add_oracle as orc
+    net = add_b200.build_add("searched-dense", 2, 20, seed=1)
+    sd = orc.randomize_bn_({k: v.clone() for k, v in net.state_dict().items()}, 21)
+    net.load_state_dict(sd)
+    x, gt = orc.synthetic_batch(1, 512, 1024)
+    na, ci, low = add_b200.NETWORKS["searched-dense"][2]
+    with torch.no_grad():
+        ref = orc.add_forward(sd, orc.Arch(na, ci, low_level_layer=low), x)
+    net = net.to(DEV).eval()
+    outs = net(x.to(DEV))
+    cm = net.evaluate(x.to(DEV), gt.to(DEV)).cpu().numpy()
+    for e, (o, r) in enumerate(zip(outs, ref)):
+        oc = o.cpu()
+        err = float((oc.double() - r.double()).abs().max() / r.double().abs().max())
+        agree = float((oc.argmax(1) == r.argmax(1)).float().mean())
+        assert err < 1e-3 and agree >= 0.999, (e, err, agree)
+        want = orc.generate_matrix(gt.numpy(), oc.argmax(1).numpy())
+        assert np.array_equal(cm[e].sum(0), want)
