@@ -385,14 +385,14 @@ class ADD(AddModule):
         return run_dynamic(self, x, threshold, confidence, edm, exit_mode)
 
     def dynamic_evaluate(self, x: torch.Tensor, target: torch.Tensor, threshold=1.0, edm=False,
-                         exit_mode: str = "reference"):
+                         exit_mode: str = "reference", bind_inputs: bool = False):
         """eval.py:195-221 fused for a batch: EDM-gated early exit → argmax → per-image int64
         confusion matrix [N,nc,nc] (no full-resolution logits are materialised).
         Returns (cm, exit flags, confidence values)."""
         from .dynamic import run_dynamic_evaluate
         self._check_eval()
         rt.require_cuda(x)
-        return run_dynamic_evaluate(self, x, target, threshold, edm, exit_mode)
+        return run_dynamic_evaluate(self, x, target, threshold, edm, exit_mode, bind_inputs)
 
 
 class _NetPlan:

@@ -81,7 +81,11 @@ class _Segment:
         self.idx = b.raw((m,), torch.int32, zero=True)   # valid ids even before the host fills them
         self.gather: Optional[Plan] = None
         if k == 0:
-            self.x_static = b.raw((m, 3, H, W), torch.float32)
+            if runner.bound is not None:
+                self.x_static = runner.bound[0]
+                b.keep.append(self.x_static)
+            else:
+                self.x_static = b.raw((m, 3, H, W), torch.float32)
             st: dict = {}
         else:
             st = _alloc_state_like(b, prev.state, m, need_two=first <= 2)
@@ -174,8 +178,12 @@ def _capture_with_pct(plan, pct: int) -> None:
 class _EdmRunner:
     """Batched, per-image EDM-gated inference for one (input shape, precision, output mode)."""
 
-    def __init__(self, net, shape, device, precision: str, edm, mode: str, exit_mode: str):
+    def __init__(self, net, shape, device, precision: str, edm, mode: str, exit_mode: str,
+                 bound: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None):
+        """bound = (x, target): record the plans directly on THESE device tensors (the caller promises to refill the
+        same buffers for every call, as HostPipeline's slots do) — no copy into private static inputs."""
         self.generation = rt.generation()
+        self.bound = bound
         self.net, self.edm, self.mode = net, edm, mode
         self.device, self.dtype = device, rt.act_dtype(precision)
         self.n, _, self.H, self.W = shape
@@ -192,7 +200,8 @@ class _EdmRunner:
         self.heads: Dict[Tuple[int, int], _Head] = {}
         self.gt_full: Optional[torch.Tensor] = None
         if mode == "evaluate":
-            self.gt_full = torch.empty((self.n, self.H, self.W), dtype=torch.int64, device=device)
+            self.gt_full = (bound[1] if bound is not None else
+                            torch.empty((self.n, self.H, self.W), dtype=torch.int64, device=device))
         self.last_launches = 0
         self._side: Optional[torch.cuda.Stream] = None
 
@@ -233,11 +242,12 @@ class _EdmRunner:
         launches = 0
         pending_side = False
         self.last_plans: List[Plan] = []
-        if self.mode == "evaluate":
+        if self.mode == "evaluate" and self.bound is None:
             self.gt_full.copy_(target, non_blocking=True)
         active = list(range(n))
         seg = self.segment(0, n, None)
-        seg.x_static.copy_(x, non_blocking=True)
+        if self.bound is None:
+            seg.x_static.copy_(x, non_blocking=True)
         for k in range(len(self.exits) + 1):
             if k > 0:
                 seg.gather.run()
@@ -290,12 +300,19 @@ class _EdmRunner:
         return outs, flags, confs
 
 
-def _get_runner(net, x: torch.Tensor, edm, mode: str, exit_mode: str) -> _EdmRunner:
+def _get_runner(net, x: torch.Tensor, edm, mode: str, exit_mode: str, target: Optional[torch.Tensor] = None,
+                bind_inputs: bool = False) -> _EdmRunner:
     prec = net.precision or rt.default_precision()
     key = ("edm", tuple(x.shape), str(x.device), prec, id(edm), mode, exit_mode, bool(net.use_cuda_graph))
+    bound = None
+    if bind_inputs:
+        if not (x.dtype == torch.float32 and x.is_contiguous() and (target is None or (target.dtype == torch.int64 and target.is_contiguous()))):
+            raise ValueError("bind_inputs needs contiguous fp32 NCHW images and int64 labels")
+        key = key + (x.data_ptr(), 0 if target is None else target.data_ptr())
+        bound = (x, target)
     r = net._plans.get(key)
     if r is None or r.generation != rt.generation():
-        r = _EdmRunner(net, tuple(x.shape), x.device, prec, edm, mode, exit_mode)
+        r = _EdmRunner(net, tuple(x.shape), x.device, prec, edm, mode, exit_mode, bound)
         net._plans[key] = r
     return r
 
@@ -389,10 +406,13 @@ def run_dynamic(net, x: torch.Tensor, threshold, confidence, edm, exit_mode: str
     return outs, flags, confs
 
 
-def run_dynamic_evaluate(net, x: torch.Tensor, target: torch.Tensor, threshold, edm, exit_mode: str = "reference"):
+def run_dynamic_evaluate(net, x: torch.Tensor, target: torch.Tensor, threshold, edm, exit_mode: str = "reference",
+                         bind_inputs: bool = False):
     """eval.py:195-221 for a batch, fused: per-image EDM gate → exit head → argmax → int64 confusion
-    matrix, without materialising full-resolution logits.  Returns (cm int64 [N,nc,nc], flags, confs)."""
-    r = _get_runner(net, x, edm, "evaluate", exit_mode)
+    matrix, without materialising full-resolution logits.  Returns (cm int64 [N,nc,nc], flags, confs).
+    bind_inputs: record the plans on x / target themselves (stable buffers refilled by the caller, e.g. the slots
+    of HostPipeline) instead of copying into private static inputs."""
+    r = _get_runner(net, x, edm, "evaluate", exit_mode, target, bind_inputs)
     outs, flags, confs = r.run(x, float(threshold), target)
     net.last_dynamic_launches = r.last_launches
     return torch.stack(outs), flags, confs

@@ -68,7 +68,9 @@ class HostPipeline:
             if self.edm is None:
                 cm, flags = self.net.evaluate(slot["x"], slot["gt"]), None
             else:
-                cm, flags, _ = self.net.dynamic_evaluate(slot["x"], slot["gt"], self.threshold, self.edm, self.exit_mode)
+                # the slot buffers are stable: the plans are recorded directly on them (no device-to-device input copy)
+                cm, flags, _ = self.net.dynamic_evaluate(slot["x"], slot["gt"], self.threshold, self.edm, self.exit_mode,
+                                                         bind_inputs=True)
                 cm = cm.unsqueeze(0)
             slot["free"].record(main)
             if slot["out"] is None or slot["out"].shape != cm.shape:

@@ -130,3 +130,29 @@ def test_batched_edm_gating_matches_per_image():
     _, f_all, _ = net.dynamic_inference_batch(xd, 1e30, 'edm', edm)
     _, f_none, _ = net.dynamic_inference_batch(xd, -1e30, 'edm', edm)
     assert f_all == [1] * 5 and f_none == [0] * 5
+
+
+def test_host_pipeline_matches_direct_calls():
+    """HostPipeline (pinned host batches, double-buffered H2D, plans bound to the slot buffers) returns exactly what
+    direct ADD.dynamic_evaluate / ADD.evaluate calls return, batch after batch (slots are reused across batches)."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec).to(DEV)
+    edm = util.make_edm().to(DEV)
+    batches = [util.make_input(3, 33, 65, seed=300 + i) for i in range(5)]
+    _, _, confs = net.dynamic_evaluate(batches[0][0].to(DEV), batches[0][1].to(DEV), -1e30, edm)
+    thr = sorted(float(c) for c in confs)[1]
+    want = []
+    for x, gt in batches:
+        cm, flags, _ = net.dynamic_evaluate(x.to(DEV), gt.to(DEV), thr, edm)
+        want.append((cm.cpu().clone(), list(flags)))
+    pipe = add_b200.HostPipeline(net, edm, thr)
+    got = [(cm.clone(), list(flags)) for cm, flags in pipe.evaluate((x.pin_memory(), gt.pin_memory()) for x, gt in batches)]
+    assert len(got) == len(want)
+    for (cm_g, fl_g), (cm_w, fl_w) in zip(got, want):
+        assert fl_g == fl_w
+        assert torch.equal(cm_g[0], cm_w)
+    # multi-exit mode (no EDM): per-exit confusion matrices
+    pipe2 = add_b200.HostPipeline(net)
+    for (cm_g, fl), (x, gt) in zip(pipe2.evaluate((x.pin_memory(), gt.pin_memory()) for x, gt in batches[:2]), batches[:2]):
+        assert fl is None
+        assert torch.equal(cm_g, net.evaluate(x.to(DEV), gt.to(DEV)).cpu())
