@@ -533,6 +533,20 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 constexpr int TCHP_THREADS = 352;
 constexpr int TCHP_MAX_STAGES = 16;          // weight ring depth when the taps do not fit resident
 
+// Row pairs (p.mt == 2): a unit is two output rows r and r + dil of one 128-pixel column strip.  They share kh-1 of
+// their kh halo rows (kh + 1 rows are loaded instead of 2 kh) and EVERY weight tile: for the 5x5s the weight stream
+// (25 x 6 KB per tile through a ring that smem limits to ~36 KB in flight = 37 GB/s per SM, ncu r01u) was the
+// bound, so two tiles per weight tile doubles the useful work per streamed byte.
+__device__ __forceinline__ void halo_unit_rows(int u, int units_per_col, int tiles_x, int dil, int mt, int& n, int& tx, int& r0) {
+  // u -> (image n, column strip tx, first output row r0); mt == 2: rows are paired (r0, r0 + dil), r0 = blk*2*dil + off
+  const int per_img = units_per_col * tiles_x;
+  n = u / per_img;
+  const int r = u - n * per_img;
+  const int j = r / tiles_x;
+  tx = r - j * tiles_x;
+  r0 = mt == 2 ? (j / dil) * 2 * dil + (j % dil) : j;
+}
+
 __global__ void __launch_bounds__(TCHP_THREADS, 1)
 conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -542,13 +556,16 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
   __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
 
   const int kh = p.taps / p.taps_w;
+  const int MT = p.mt;
+  const int hrows = kh + (MT - 1);                                         // halo rows per (unit, chunk)
   const int iters = p.taps * p.kchunks;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t halo_bytes = (uint32_t)kh * p.halo_pitch * 128u;
+  const uint32_t halo_bytes = (uint32_t)hrows * p.halo_pitch * 128u;
   const uint32_t b_base = smem_base + (uint32_t)p.halo_bufs * halo_bytes;  // ring slots, or the resident image
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool relu_in = (p.flags & ADD_RELU_IN) != 0;
   const uint32_t tmem_cols = (uint32_t)p.tmem_cols;
+  const int nbuf = (2u * MT * tmem_cols <= 512u) ? 2 : 1;                  // accumulator sets
 
   const uint32_t bar_hfull = smem_u32(&bars[0]);
   const uint32_t bar_hempty = smem_u32(&bars[2]);
@@ -578,7 +595,7 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(&tmem_base_smem)), "r"(2u * tmem_cols) : "memory");
+                 ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)nbuf * MT * tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -586,36 +603,37 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
   pdl_launch_dependents();
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  // units: (image, column strip, row or row pair); p.n_tiles holds the unit count, p.tiles_y the units per column
+  const int n_units = p.n_tiles, upc = p.tiles_y;
 
   if (warp == 0) {
-    // ===== halo producer: kh row boxes per (tile, 64-channel chunk) =====
+    // ===== halo producer: hrows row boxes per (unit, 64-channel chunk) =====
     if (elect_one()) {
       pdl_wait();
       int hb = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
-        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        int n, tx, r0;
+        halo_unit_rows(u, upc, p.tiles_x, p.dil, MT, n, tx, r0);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(bar_hempty + 8 * hb, ph ^ 1);
           mbar_expect_tx(bar_hfull + 8 * hb, halo_bytes);
           const uint32_t dst = smem_base + hb * halo_bytes;
-          for (int ky = 0; ky < kh; ++ky)
-            tma_load_4d(dst + ky * p.halo_pitch * 128, &map_x, bar_hfull + 8 * hb, kc * TC_BK, tx * TC_BM - p.pad,
-                        ty - p.pad + ky * p.dil, n);
+          for (int j = 0; j < hrows; ++j)
+            tma_load_4d(dst + j * p.halo_pitch * 128, &map_x, bar_hfull + 8 * hb, kc * TC_BK, tx * TC_BM - p.pad,
+                        r0 - p.pad + j * p.dil, n);
           if (++hb == p.halo_bufs) { hb = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 2) {
-    // ===== weight producer: resident image once, or one [n_pad x 64] tile per (tile, chunk, tap) through the ring =====
+    // ===== weight producer: resident image once, or one [n_pad x 64] tile per (unit, chunk, tap) through the ring =====
     if (elect_one()) {
       if (p.b_resident) {
         mbar_expect_tx(bar_bres, (uint32_t)iters * p.b_bytes);
         for (int it = 0; it < iters; ++it) tma_load_3d(b_base + it * p.b_bytes, &map_w, bar_bres, 0, 0, it);
       } else {
         int s2 = 0; uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x)
           for (int kc = 0; kc < p.kchunks; ++kc)
             for (int tap = 0; tap < p.taps; ++tap) {
               mbar_wait(bar_bempty + 8 * s2, ph ^ 1);
@@ -631,17 +649,17 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       if (p.b_resident) mbar_wait(bar_bres, 0);
       int hb = 0; uint32_t hph = 0; int s2 = 0; uint32_t bph = 0; int ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
-        const int ab = ti & 1; const uint32_t tph = (uint32_t)(ti >> 1) & 1u;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
+        const int ab = nbuf == 2 ? (ti & 1) : 0;
+        const uint32_t tph = nbuf == 2 ? ((uint32_t)(ti >> 1) & 1u) : ((uint32_t)ti & 1u);
         mbar_wait(bar_tempty + 8 * ab, tph ^ 1u);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           const int krem = p.Cin - kc * TC_BK;
           const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
           mbar_wait((relu_in ? bar_hrelu : bar_hfull) + 8 * hb, hph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          // The single issuing thread is the pipeline's metronome: keep its per-MMA instruction count minimal
-          // (ncu r01l: a division per tap and 64-bit descriptor rebuilds made it ~700 instructions per tile and
-          // the tensor pipe idle 84 % of the time).  Descriptors differ only in their 14-bit address field.
+          // The single issuing thread is the pipeline's metronome: keep its per-MMA instruction count minimal.
+          // Descriptors differ only in their 14-bit address field.
           const uint32_t halo = smem_base + hb * halo_bytes;
           const uint64_t adesc0 = make_kmajor_sw128_desc_shifted(halo, p.base_off_mode);
           const uint64_t bdesc0 = make_kmajor_sw128_desc(b_base);
@@ -650,9 +668,9 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
           uint32_t bidx = p.b_resident ? (uint32_t)kc * bstep : 0u;              // resident: tile (tap*kchunks+kc)
           const uint32_t bidx_step = (uint32_t)p.kchunks * bstep;
           uint32_t acc = kc > 0 ? 1u : 0u;
-          const uint32_t tmem_d = tmem_base + ab * tmem_cols;
-          if (p.b_resident && issue_chunk_resident_dispatch(kh, p.taps_w, ksteps, tmem_d, adesc0, bdesc0 + bidx, row_step, tap_step,
-                                                            bidx_step, idesc, acc)) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)(ab * MT) * tmem_cols;
+          if (MT == 1 && p.b_resident && issue_chunk_resident_dispatch(kh, p.taps_w, ksteps, tmem_d, adesc0, bdesc0 + bidx, row_step,
+                                                                       tap_step, bidx_step, idesc, acc)) {
             // fully unrolled instance issued
           } else {
             uint32_t a_row = 0;
@@ -668,6 +686,8 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
                   bdesc = bdesc0 + (uint32_t)s2 * bstep;
                 }
                 issue_tap_ring_dispatch(ksteps, tmem_d, adesc0 + a_off, bdesc, idesc, acc);
+                if (MT == 2)       // second output row: same weights, halo rows one further down
+                  issue_tap_ring_dispatch(ksteps, tmem_d + tmem_cols, adesc0 + a_off + row_step, bdesc, idesc, acc);
                 acc = 1u;
                 if (!p.b_resident) {
                   umma_commit(bar_bempty + 8 * s2);
@@ -687,7 +707,7 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
     if (relu_in) {
       const int et = threadIdx.x - 96;        // 0..127
       int hb = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x)
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(bar_hfull + 8 * hb, ph);
           relu_sweep(smem_base + hb * halo_bytes, halo_bytes, et);
@@ -697,15 +717,17 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
     }
   } else {
     // ===== epilogue: warps 7..10 =====
-    pdl_wait();                               // += y reads and y writes must follow the previous kernel
-    int cur_n = (int)blockIdx.x / tiles_per_img;
+    int cur_n = 0;
+    { int tx0, r00; halo_unit_rows((int)blockIdx.x < n_units ? (int)blockIdx.x : 0, upc, p.tiles_x, p.dil, MT, cur_n, tx0, r00); }
     stage_bias(bias_s, p, threadIdx.x - 224, 128, cur_n);
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    pdl_wait();                               // += y reads and y writes must follow the previous kernel
     int ti = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
-      const int ab = ti & 1; const uint32_t tph = (uint32_t)(ti >> 1) & 1u;
-      const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
-      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
+      const int ab = nbuf == 2 ? (ti & 1) : 0;
+      const uint32_t tph = nbuf == 2 ? ((uint32_t)(ti >> 1) & 1u) : ((uint32_t)ti & 1u);
+      int n, tx, r0;
+      halo_unit_rows(u, upc, p.tiles_x, p.dil, MT, n, tx, r0);
       if (p.bias_img_stride != 0 && n != cur_n) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         stage_bias(bias_s, p, threadIdx.x - 224, 128, n);
@@ -713,7 +735,11 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
         cur_n = n;
       }
       mbar_wait_relaxed(bar_tfull + 8 * ab, tph);
-      epilogue_store(p, tmem_base + ab * tmem_cols, bias_s, warp, lane, n, ty, tx * TC_BM);
+      for (int m = 0; m < MT; ++m) {
+        const int row = r0 + m * p.dil;
+        if (row < p.Ho)                        // rows past the image (odd remainder of the pairing) computed on zeros, not stored
+          epilogue_store(p, tmem_base + (uint32_t)(ab * MT + m) * tmem_cols, bias_s, warp, lane, n, row, tx * TC_BM);
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
@@ -723,11 +749,12 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)nbuf * MT * tmem_cols) : "memory");
   }
 }
 
 // ---- host side -----------------------------------------------------------------------------------
+int g_halo_pairs = 1;               // 1 = row pairs in the persistent halo kernel (mode bit 7 clears)
 int g_conv_mt2 = 1;                 // 1 = two pixel tiles per weight tile for the weight-heavy convs (mode bit 6 clears)
 int g_halo_stream_persistent = 0;   // 1 = use the persistent halo kernel also when the weights stream through a ring (tuning)
 int g_persistent = 1;  // 1 = persistent warp-specialised kernel for the non-halo path (default), 0 = one tile per CTA
@@ -888,38 +915,43 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
   }
   if (halo && g_persistent) {
     const int iters = p.taps * p.kchunks;
-    const size_t hbytes = (size_t)kh * p.halo_pitch * 128u;
     const size_t budget = 222u * 1024u;
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     TcParams q = p;
-    q.n_tiles = (int)grid;
+    // row pairs (r, r + dil) share halo rows and every weight tile: used when the weights have to stream (5x5s)
+    // or the map is tall enough that pairing leaves every SM busy
+    const bool resident1 = 2 * (size_t)kh * p.halo_pitch * 128u + (size_t)iters * p.b_bytes + 1024 <= budget;
+    q.mt = (g_halo_pairs && 2 * p.tmem_cols <= 512 && (!resident1 || grid >= 4ll * sms)) ? 2 : 1;
+    const size_t hbytes = (size_t)(kh + q.mt - 1) * p.halo_pitch * 128u;
+    const int upc = q.mt == 2 ? ceil_div(y->h, 2 * dil) * dil : y->h;             // units per column strip
+    q.tiles_y = upc;
+    const long long units = (long long)upc * p.tiles_x * y->n;
+    q.n_tiles = (int)units;
     size_t psmem = 0;
     bool ok = true;
     if (2 * hbytes + (size_t)iters * p.b_bytes + 1024 <= budget) {
-      // every tap's weights resident + two halo buffers (next tile's halo streams in under this tile's MMAs)
+      // every tap's weights resident + two halo buffers (next unit's halo streams in under this unit's MMAs)
       q.b_resident = 1; q.halo_bufs = 2;
       psmem = 2 * hbytes + (size_t)iters * p.b_bytes + 1024;
     } else {
-      // weights stream through a ring: a deep ring matters more than a second halo buffer (each weight tile is a
-      // full TMA round trip; with 3 slots the 25 taps of a 5x5 were latency-bound)
+      // weights stream through a ring: what limits it is bytes in flight (ring depth x tile size over the TMA round
+      // trip), so the ring gets everything a single halo buffer leaves
       q.b_resident = 0;
-      q.halo_bufs = (2 * hbytes + 5 * (size_t)p.b_bytes + 1024 <= budget) ? 2 : 1;
+      q.halo_bufs = (2 * hbytes + 12 * (size_t)p.b_bytes + 1024 <= budget) ? 2 : 1;
       long long sb = ((long long)budget - 1024 - (long long)q.halo_bufs * (long long)hbytes) / (long long)p.b_bytes;
       if (sb > TCHP_MAX_STAGES) sb = TCHP_MAX_STAGES;
       if (sb < 2) ok = false;
       q.stages = (int)sb;
       psmem = (size_t)q.halo_bufs * hbytes + (size_t)(sb > 0 ? sb : 0) * p.b_bytes + 1024;
     }
-    // measured (r01l microbench): the streaming-weights variant loses to two co-resident one-tile CTAs for the 5x5s;
-    // the persistent kernel is used where the weights are resident (3x3 at C <= 64 per chunk: stem1, dil_conv_3x3)
-    if (ok && (q.b_resident || g_halo_stream_persistent) && 2 * q.tmem_cols <= 512) {
+    if (ok && (q.b_resident || q.mt == 2 || g_halo_stream_persistent)) {
       static std::once_flag hponce;
       std::call_once(hponce, [] {
         cudaFuncSetAttribute(conv2d_tc_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
         cudaFuncSetAttribute(conv2d_tc_halo_persistent_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       });
-      int sms = 148;
-      { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-      long long g = sms < grid ? sms : grid;
+      long long g = sms < units ? sms : units;
       launch_kernel(conv2d_tc_halo_persistent_kernel, dim3((unsigned)g), dim3(TCHP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, q);
       ADD_RETURN_LAUNCH();
     }
@@ -934,6 +966,7 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
 /* Tuning / experiment switch for the halo-resident A path (see conv2d_tc_halo_kernel). */
 extern "C" int add_conv2d_tc_set_halo_mode(int mode) {
   g_persistent = (mode & 16) ? 0 : 1;                 // bit 4 set = one tile per CTA (A/B runs)
+  g_halo_pairs = (mode & 128) ? 0 : 1;                // bit 7 set = no row pairs in the persistent halo kernel
   g_conv_mt2 = (mode & 64) ? 0 : 1;                   // bit 6 set = one pixel tile per weight tile everywhere
   g_halo_stream_persistent = (mode & 32) ? 1 : 0;     // bit 5 set = persistent halo kernel with streamed weights
   mode &= 15;

@@ -36,6 +36,7 @@ struct TcParams {
   long long bias_img_stride;               // floats between consecutive images' bias vectors (0 = one shared vector)
   int n_tiles;                             // tiles_x * tiles_y * N
   int b_resident;                          // 1: all weight chunks stay in shared memory for the whole kernel
+  int mt;                                  // halo kernel: output rows per unit (1, or 2 = rows r and r+dil sharing halo rows and weights)
 };
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------

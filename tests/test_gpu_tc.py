@@ -74,6 +74,11 @@ CASES = [
     (64, 64, 3, 1, 1, 1, 90, 300, RELU_OUT),
     (80, 80, 3, 1, 2, 2, 120, 127, RELU_IN),
     (80, 80, 5, 1, 4, 2, 100, 128, RELU_IN | ACCUMULATE),
+    # row pairs (r, r + dil): odd heights leave unpaired / out-of-image rows
+    (40, 40, 5, 1, 4, 2, 125, 253, RELU_IN),
+    (40, 40, 3, 1, 2, 2, 63, 127, RELU_IN | ACCUMULATE),
+    (64, 64, 3, 1, 1, 1, 131, 200, RELU_OUT),
+    (80, 80, 5, 1, 4, 2, 63, 127, 0),
 ]
 
 

@@ -19,12 +19,16 @@ BN = torch.nn.BatchNorm2d
 
 def cases():
     out = []
-    for name, C, h, w in (("L1", 40, 128, 256), ("L2", 80, 64, 128), ("L3", 160, 32, 64)):
+    for name, C, h, w in (("L1", 40, 128, 256), ("L2", 80, 64, 128), ("L3", 160, 32, 64), ("tiny", 40, 8, 16)):
         for op in ("sep_conv_3x3", "sep_conv_5x5", "dil_conv_3x3", "dil_conv_5x5"):
             out.append((f"{op}_{name}", "op", (op, C, 8, h, w)))
     out += [("pw_200to40_L1", "pw", (200, 40, 8, 128, 256)), ("pw_40to40_L1", "pw", (40, 40, 8, 128, 256)),
             ("pw_400to80_L2", "pw", (400, 80, 8, 64, 128)), ("pw_80to80_L2", "pw", (80, 80, 8, 64, 128)),
             ("pw_800to80_L2", "pw", (800, 80, 8, 64, 128)),
+            ("dil5_L1_norelu", "conv", (40, 40, 5, 1, 4, 2, 8, 128, 256, 0)),
+            ("dil5_L1_relu", "conv", (40, 40, 5, 1, 4, 2, 8, 128, 256, RELU_IN)),
+            ("dil5_L1_half_rows", "conv", (40, 40, 5, 1, 4, 2, 8, 64, 256, RELU_IN)),
+            ("dil5_L1_quarter", "conv", (40, 40, 5, 1, 4, 2, 8, 32, 256, RELU_IN)),
             ("stem1_64to64_3x3", "conv", (64, 64, 3, 1, 1, 1, 8, 512, 1024, RELU_OUT)),
             ("stem2_64to128_s2", "conv", (64, 128, 3, 2, 1, 1, 8, 512, 1024, RELU_IN)),
             ("aspp_400to256_d12", "conv", (400, 256, 3, 1, 12, 12, 4, 256, 512, RELU_IN | RELU_OUT)),
