@@ -63,6 +63,7 @@ _SIGS = {
     "add_upsample_logits_nchw": (c_int, [TP, c_void_p, c_int, c_int, c_void_p]),
     "add_head_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "add_upsample_argmax_fwd": (c_int, [TP, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "add_widen_labels_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "add_confusion_workspace_bytes": (c_int64, [c_int64, c_int]),
     "add_confusion_matrix": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "add_confidence_workspace_bytes": (c_int64, [c_int, c_int, c_int]),

@@ -332,6 +332,40 @@ extern "C" int add_aspp_pool_bias_fwd(const float* pooled, int n, int cin, const
   ADD_RETURN_LAUNCH();
 }
 
+// ---- label widening: uint8 labels (Cityscapes PNG depth; 255 = ignore) -> the int64 the Evaluator path consumes ----
+// Lets the host ship 1 byte per pixel instead of 8 (utils/metrics.py:35 masks on 0 <= gt < num_class, so 255 stays ignored).
+namespace {
+__global__ void __launch_bounds__(256)
+widen_labels_kernel(const uint8_t* __restrict__ src, long long* __restrict__ dst, long long n) {
+  for (long long i = (blockIdx.x * 256ll + threadIdx.x) * 16; i < n; i += (long long)gridDim.x * 256 * 16) {
+    if (i + 16 <= n) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        longlong2 o;
+        o.x = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        o.y = (w[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xffu;
+        *reinterpret_cast<longlong2*>(dst + i + j) = o;
+      }
+    } else {
+      for (long long k = i; k < n; ++k) dst[k] = src[k];
+    }
+  }
+}
+}  // namespace
+
+extern "C" int add_widen_labels_u8(const uint8_t* src, int64_t* dst, int64_t n, void* stream) {
+  ADD_CHECK_ARG(src && dst && n >= 0);
+  ADD_CHECK_SUP(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0);
+  if (n == 0) return ADD_OK;
+  long long blocks = (n / 16 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  widen_labels_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, (long long*)dst, n);
+  ADD_RETURN_LAUNCH();
+}
+
 // ---- image gather: dst[j] = src[idx[j]] for whole per-image slabs (early-exit batch compaction) ----
 namespace {
 template <typename V>

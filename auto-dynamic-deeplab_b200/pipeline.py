@@ -10,11 +10,14 @@ from typing import Iterable, Iterator, List, Optional, Tuple
 
 import torch
 
+import ctypes
+
 from . import runtime as rt
+from ._lib import lib, check
 
 
 class HostPipeline:
-    """evaluate(batches) yields, per batch of HOST tensors (x fp32 [N,3,H,W], gt int64 [N,H,W], ideally
+    """evaluate(batches) yields, per batch of HOST tensors (x fp32 [N,3,H,W], gt int64 or uint8 [N,H,W], ideally
     pinned), `(cm int64 [n_exits or 1, N, nc, nc] pinned host tensor, exit flags or None)`.
 
     edm=None  → multi-exit `ADD.evaluate` (eval.py:165-193, every exit scored);
@@ -38,13 +41,23 @@ class HostPipeline:
         for _ in range(self.depth):
             self._slots.append(dict(x=torch.empty(x.shape, dtype=torch.float32, device=self.device),
                                     gt=torch.empty(gt.shape, dtype=torch.int64, device=self.device),
+                                    gt_u8=(torch.empty(gt.shape, dtype=torch.uint8, device=self.device)
+                                           if gt.dtype == torch.uint8 else None),
                                     ready=torch.cuda.Event(), free=torch.cuda.Event(), out=None))
 
     def _prefetch(self, slot: dict, x: torch.Tensor, gt: torch.Tensor) -> None:
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot["free"])        # the compute that last read this slot is done
             slot["x"].copy_(x, non_blocking=True)
-            slot["gt"].copy_(gt, non_blocking=True)
+            if gt.dtype == torch.uint8:
+                # labels travel at their native 1 byte per pixel and are widened on the device (add_widen_labels_u8)
+                if slot["gt_u8"] is None:
+                    slot["gt_u8"] = torch.empty(gt.shape, dtype=torch.uint8, device=self.device)
+                slot["gt_u8"].copy_(gt, non_blocking=True)
+                check(lib.add_widen_labels_u8(slot["gt_u8"].data_ptr(), slot["gt"].data_ptr(), gt.numel(),
+                                              ctypes.c_void_p(self.copy_stream.cuda_stream)), "widen_labels_u8")
+            else:
+                slot["gt"].copy_(gt, non_blocking=True)
             slot["ready"].record(self.copy_stream)
         self.h2d_bytes += x.numel() * x.element_size() + gt.numel() * gt.element_size()
 

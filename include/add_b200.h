@@ -163,6 +163,10 @@ int add_upsample_argmax_fwd(const add_tensor_t* x, int H, int W, const int64_t* 
                             int64_t* pred_out, int64_t* cm_out, float* entropy_out,
                             void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- label edge: uint8 labels (Cityscapes PNG depth, 255 = ignore) -> int64 [n] as the Evaluator path reads them.
+ * The loader-side H2D then moves 1 byte per pixel instead of 8 (cityscapes.py:85-91 encodes ids into 0..18 / 255). */
+int add_widen_labels_u8(const uint8_t* src, int64_t* dst, int64_t n, void* stream);
+
 /* ---- Evaluator (utils/metrics.py:34-39): int64 confusion matrix, atomics-free ------------ */
 int64_t add_confusion_workspace_bytes(int64_t n_pixels, int num_class);
 int add_confusion_matrix(const int64_t* gt, const int64_t* pred, int64_t n_pixels, int num_class,

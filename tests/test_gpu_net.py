@@ -151,6 +151,11 @@ def test_host_pipeline_matches_direct_calls():
     for (cm_g, fl_g), (cm_w, fl_w) in zip(got, want):
         assert fl_g == fl_w
         assert torch.equal(cm_g[0], cm_w)
+    # uint8 host labels (1 byte per pixel over PCIe, widened on the device): same matrices
+    got8 = [(cm.clone(), list(flags)) for cm, flags in
+            pipe.evaluate((x.pin_memory(), gt.to(torch.uint8).pin_memory()) for x, gt in batches)]
+    for (cm_g, fl_g), (cm_w, fl_w) in zip(got8, want):
+        assert fl_g == fl_w and torch.equal(cm_g[0], cm_w)
     # multi-exit mode (no EDM): per-exit confusion matrices
     pipe2 = add_b200.HostPipeline(net)
     for (cm_g, fl), (x, gt) in zip(pipe2.evaluate((x.pin_memory(), gt.pin_memory()) for x, gt in batches[:2]), batches[:2]):
