@@ -346,7 +346,15 @@ def main_b200(a):
         else:
             ach = t["bytes"] / (t["ms"] / 1e3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
-        roof.update({"kernel": top, "traffic": None, "peak_source": src, "launches": t["launches"],
+        traffic, traffic_src = None, None
+        tj = ROOT / "profiles" / "traffic.json"
+        if tj.exists():                       # measured DRAM bytes per launch of this kernel family (ncu, committed)
+            tk = json.loads(tj.read_text()).get("kernels", {}).get(top)
+            if tk:
+                traffic, traffic_src = tk["traffic_per_launch"], "profiles/traffic.json (ncu dram__bytes_read+write per launch)"
+        roof.update({"kernel": top, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_per_launch": (t["flops"] if roof["bound"] == "tensor" else t["bytes"]) / t["launches"],
+                     "peak_source": src, "launches": t["launches"],
                      "avg_launch_ms": t["ms"] / t["launches"], "share_of_step": t["ms"] / total_ms,
                      "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                                      "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
