@@ -80,6 +80,10 @@ class Cell(AddModule):
         for row in arch:
             self._ops.append(OPS[PRIMITIVES[int(row[1])]](C_out, 1, BatchNorm, eps=eps, momentum=momentum, affine=True))
         self._steps = executed_edges(arch, B)
+        # s0 / s1 may be stored post-ReLU only if every executed op starts with ReLU (sep/dil convs do, operations.py:33,47;
+        # pools, skip_connect and none take the raw signed input)
+        relu_first = {'sep_conv_3x3', 'sep_conv_5x5', 'dil_conv_3x3', 'dil_conv_5x5'}
+        self._all_relu_first = all(PRIMITIVES[int(row[1])] in relu_first for row in arch)
 
     def _prepare(self):
         pass
@@ -105,7 +109,8 @@ class Cell(AddModule):
         s1 = b.scratch(n, h, w, C)
         # s0 / s1 are read only by the cell's ops, which all start with ReLU (operations.py:33,47): store relu(s)
         # once (RELU_OUT) and let the five ops that read them skip their ReLU-on-load pass
-        self.preprocess.emit(b, s1_in, s1, RELU_OUT)
+        pre_flags = RELU_OUT if self._all_relu_first else 0
+        self.preprocess.emit(b, s1_in, s1, pre_flags)
         s0 = b.scratch(n, h, w, C)
         temps += [s0, s1]
         if not self.dense_in:  # ADD.py:83-86
@@ -115,7 +120,7 @@ class Cell(AddModule):
                 b.bilinear(src, r, 0, "Cell.resize_pp")
                 temps.append(r)
                 src = r
-            self.pre_preprocess.emit(b, src, s0, RELU_OUT)
+            self.pre_preprocess.emit(b, src, s0, pre_flags)
         else:  # ADD.py:87-93
             k = len(prev_prev)
             cat = b.scratch(n, h, w, k * C)
@@ -126,7 +131,7 @@ class Cell(AddModule):
                     self.pre_preprocess[i].emit(b, r, cat.slice(i * C, C), 0)
                 else:
                     self.pre_preprocess[i].emit(b, src, cat.slice(i * C, C), 0)
-            self.pre_preprocess_1x1.emit(b, cat, s0, RELU_OUT)
+            self.pre_preprocess_1x1.emit(b, cat, s0, pre_flags)
         concat = b.alloc(n, h, w, self.B * C)
         states = [s0, s1] + [concat.slice(i * C, C) for i in range(self.B)]
         for i, edges in enumerate(self._steps):  # ADD.py:97-110
@@ -134,7 +139,8 @@ class Cell(AddModule):
             if not edges:
                 raise NotImplementedError("cell step without inputs (sum of empty list) is not supported")
             for e, (j, k) in enumerate(edges):
-                self._ops[k].emit(b, states[j], dst, (ACCUMULATE if e > 0 else 0) | (IN_RELUD if j < 2 else 0))
+                self._ops[k].emit(b, states[j], dst, (ACCUMULATE if e > 0 else 0) |
+                                  (IN_RELUD if (j < 2 and self._all_relu_first) else 0))
         dense = None
         if self.dense_out:
             dense = b.alloc(n, h, w, C)

@@ -169,7 +169,8 @@ class SepConv(AddModule):
 
 
 class Identity(AddModule):
-    """operations.py:65-71."""
+    """operations.py:65-71 (skip_connect).  Stand-alone it returns its input (like the reference); as a cell edge it
+    is one copy / accumulate launch."""
 
     def _prepare(self):
         pass
@@ -178,31 +179,58 @@ class Identity(AddModule):
         return x
 
     def emit(self, b, x, y, flags=0):
-        raise NotImplementedError("skip_connect inside a fused cell is a supernet-only op (SURVEY §8f #2)")
+        b.scale(x, y, 1.0, 1, flags & ~IN_RELUD, "Identity")
 
 
 class Zero(AddModule):
-    """operations.py:74-83 (supernet-only; not on the ADD inference path)."""
+    """operations.py:74-83 ('none'): x[:, :, ::stride, ::stride].mul(0.) — IEEE x*0, so NaN/inf propagate as in torch."""
 
     def __init__(self, stride):
         super().__init__()
         self.stride = stride
 
-    def forward(self, x):
-        raise NotImplementedError("'none' is a supernet-only primitive (SURVEY §8f #2)")
+    def _prepare(self):
+        pass
+
+    def out_shape(self, n, c, h, w):
+        return n, c, (h - 1) // self.stride + 1, (w - 1) // self.stride + 1
+
+    def emit(self, b, x, y, flags=0):
+        b.scale(x, y, 0.0, self.stride, flags & ~IN_RELUD, "Zero")
 
 
-def _unsupported_pool(name):
-    def make(C, stride, BatchNorm, eps, momentum, affine):
-        raise NotImplementedError(f"{name} is a supernet-only primitive, not on the ADD path (SURVEY §8f #2)")
-    return make
+class _Pool3x3(AddModule):
+    """nn.AvgPool2d(3, stride, padding=1, count_include_pad=False) / nn.MaxPool2d(3, stride, padding=1)
+    (operations.py:9-10) — parameter-free, one launch."""
+    MODE = 0
+
+    def __init__(self, stride):
+        super().__init__()
+        self.stride = stride
+
+    def _prepare(self):
+        pass
+
+    def out_shape(self, n, c, h, w):
+        return n, c, (h - 1) // self.stride + 1, (w - 1) // self.stride + 1
+
+    def emit(self, b, x, y, flags=0):
+        b.pool3x3(x, y, self.MODE, self.stride, flags & ~IN_RELUD, type(self).__name__)
+
+
+class AvgPool3x3(_Pool3x3):
+    MODE = 0
+
+
+class MaxPool3x3(_Pool3x3):
+    MODE = 1
 
 
 # operations.py:7-16 — same keys, same lambda signature.
 OPS = {
     'none': lambda C, stride, BatchNorm, eps, momentum, affine: Zero(stride),
-    'avg_pool_3x3': _unsupported_pool('avg_pool_3x3'),
-    'max_pool_3x3': _unsupported_pool('max_pool_3x3'),
+    'avg_pool_3x3': lambda C, stride, BatchNorm, eps, momentum, affine: AvgPool3x3(stride),
+    'max_pool_3x3': lambda C, stride, BatchNorm, eps, momentum, affine: MaxPool3x3(stride),
     'skip_connect': lambda C, stride, BatchNorm, eps, momentum, affine: Identity(),
     'sep_conv_3x3': lambda C, stride, BatchNorm, eps, momentum, affine: SepConv(C, C, 3, stride, 1, BatchNorm, eps=eps, momentum=momentum, affine=affine),
     'sep_conv_5x5': lambda C, stride, BatchNorm, eps, momentum, affine: SepConv(C, C, 5, stride, 2, BatchNorm, eps=eps, momentum=momentum, affine=affine),

@@ -349,6 +349,22 @@ class Builder:
                        (self._d(x), self._d(y), w_dw.data_ptr(), pw.w.data_ptr(), _ptr(pw.bias), k, flags), tag,
                        dict(kernel="sepconv_half", **meta), reads=(x, y) if flags & ACCUMULATE else (x,), writes=(y,))
 
+    def pool3x3(self, x: View, y: View, mode: int, stride: int, flags: int = 0, tag: str = "pool3x3") -> None:
+        """mode 0 = avg_pool_3x3 (count_include_pad=False), 1 = max_pool_3x3 (operations.py:9-10)."""
+        e = x.buf.element_size()
+        meta = dict(kernel="pool3x3", flops=9 * y.n * y.h * y.w * y.c,
+                    bytes=(x.n * x.h * x.w + y.n * y.h * y.w * (2 if flags & ACCUMULATE else 1)) * x.c * e)
+        self._emit(lib.add_pool3x3_fwd, (self._d(x), self._d(y), mode, stride, flags), tag, meta,
+                   reads=(x, y) if flags & ACCUMULATE else (x,), writes=(y,))
+
+    def scale(self, x: View, y: View, scale: float, stride: int = 1, flags: int = 0, tag: str = "scale") -> None:
+        """y (+)= scale * x[::stride, ::stride]: skip_connect (1.0) / none (0.0) (operations.py:8,11)."""
+        e = x.buf.element_size()
+        meta = dict(kernel="scale", flops=y.n * y.h * y.w * y.c,
+                    bytes=y.n * y.h * y.w * y.c * e * (3 if flags & ACCUMULATE else 2))
+        self._emit(lib.add_scale_fwd, (self._d(x), self._d(y), float(scale), stride, flags), tag, meta,
+                   reads=(x, y) if flags & ACCUMULATE else (x,), writes=(y,))
+
     def bilinear(self, x: View, y: View, flags: int = 0, tag: str = "bilinear") -> None:
         meta = dict(kernel="bilinear", flops=8 * y.n * y.h * y.w * y.c,
                     bytes=(x.n * x.h * x.w * x.buf.element_size() + y.n * y.h * y.w * y.buf.element_size()) * x.c)

@@ -123,6 +123,14 @@ int add_sepconv_half_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, const 
 /* add_sepconv_half_tc_fwd scheduling: 1 = persistent warp-specialised pipeline (default), 0 = one tile per CTA. */
 int add_sepconv_tc_set_mode(int mode);
 
+/* ---- the non-convolutional OPS primitives (operations.py:7-11) ------------------------------------------ */
+/* avg_pool_3x3 = nn.AvgPool2d(3, stride, padding=1, count_include_pad=False) (mode 0: divisor = taps inside the image);
+ * max_pool_3x3 = nn.MaxPool2d(3, stride, padding=1) (mode 1).  y: [n, (h-1)/stride+1, (w-1)/stride+1, c]. */
+int add_pool3x3_fwd(const add_tensor_t* x, const add_tensor_t* y, int mode, int stride, uint32_t flags, void* stream);
+/* y (+)= scale * x[:, ::stride, ::stride, :] — skip_connect / Identity (scale 1, stride 1, operations.py:65-71) and
+ * none / Zero (scale 0: IEEE x*0 like the reference's x.mul(0.), operations.py:74-83). */
+int add_scale_fwd(const add_tensor_t* x, const add_tensor_t* y, float scale, int stride, uint32_t flags, void* stream);
+
 /* ---- bilinear resize, align_corners=False (F.interpolate: ADD.py:76,84,89,317; decoder.py:24) */
 int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, uint32_t flags, void* stream);
 

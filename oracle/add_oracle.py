@@ -116,8 +116,11 @@ def sep_conv(sd: SD, p: str, x: torch.Tensor, k: int) -> torch.Tensor:
     return _bn(sd, p + '.op.7', x)
 
 
-def apply_primitive(sd: SD, p: str, name: str, x: torch.Tensor) -> torch.Tensor:
-    """operations.py:7-16 — the OPS factory at stride 1."""
+def apply_primitive(sd: SD, p: str, name: str, x: torch.Tensor, stride: int = 1) -> torch.Tensor:
+    """operations.py:7-16 — the OPS factory (ADD only ever uses stride 1, ADD.py:61; the parameter-free primitives
+    also at stride 2 as the supernets build them, cell_level_search.py:19)."""
+    if stride != 1 and name not in ('none', 'avg_pool_3x3', 'max_pool_3x3'):
+        raise NotImplementedError("strided convolutional primitives are not on the ADD path")
     if name == 'sep_conv_3x3':
         return sep_conv(sd, p, x, 3)
     if name == 'sep_conv_5x5':
@@ -128,12 +131,12 @@ def apply_primitive(sd: SD, p: str, name: str, x: torch.Tensor) -> torch.Tensor:
         return dil_conv(sd, p, x, 5)
     if name == 'skip_connect':
         return x
-    if name == 'none':
-        return x.mul(0.)
-    if name == 'avg_pool_3x3':
-        return F.avg_pool2d(x, 3, 1, 1, count_include_pad=False)
-    if name == 'max_pool_3x3':
-        return F.max_pool2d(x, 3, 1, 1)
+    if name == 'none':                      # Zero, operations.py:74-83
+        return x.mul(0.) if stride == 1 else x[:, :, ::stride, ::stride].mul(0.)
+    if name == 'avg_pool_3x3':              # operations.py:9
+        return F.avg_pool2d(x, 3, stride, 1, count_include_pad=False)
+    if name == 'max_pool_3x3':              # operations.py:10
+        return F.max_pool2d(x, 3, stride, 1)
     raise KeyError(name)
 
 

@@ -48,7 +48,7 @@ def gen_ops():
         ours, x = util.make_op_case(name)
         kind, args = spec["kind"], spec["args"]
         if kind == "OPS":
-            ref = ref_ops.OPS[args[0]](args[1], 1, BN, 1e-5, 0.1, True)
+            ref = ref_ops.OPS[args[0]](args[1], args[2] if len(args) > 2 else 1, BN, 1e-5, 0.1, True)
         else:
             ref = getattr(ref_ops, kind)(*args, BN)
         ref.load_state_dict(ours.state_dict(), strict=True)

@@ -21,7 +21,7 @@ def _oracle_op(name, m, x):
     sd = _sd(m)
     kind, args = spec["kind"], spec["args"]
     if kind == "OPS":
-        return orc.apply_primitive(sd, "m", args[0], x)
+        return orc.apply_primitive(sd, "m", args[0], x, args[2] if len(args) > 2 else 1)
     if kind == "ReLUConvBN":
         return orc.relu_conv_bn(sd, "m", x, args[3], args[4])
     if kind == "FactorizedReduce":

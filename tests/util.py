@@ -30,6 +30,13 @@ OP_CASES = {
     "dil_conv_5x5_c40": dict(kind="OPS", args=("dil_conv_5x5", 40), x=(2, 40, 13, 17)),
     "dil_conv_5x5_c80": dict(kind="OPS", args=("dil_conv_5x5", 80), x=(1, 80, 9, 11)),
     "dil_conv_3x3_c20": dict(kind="OPS", args=("dil_conv_3x3", 20), x=(1, 20, 7, 9)),
+    "avg_pool_3x3_c40": dict(kind="OPS", args=("avg_pool_3x3", 40), x=(2, 40, 13, 17)),
+    "max_pool_3x3_c40": dict(kind="OPS", args=("max_pool_3x3", 40), x=(2, 40, 13, 17)),
+    "skip_connect_c40": dict(kind="OPS", args=("skip_connect", 40), x=(2, 40, 13, 17)),
+    "none_c40": dict(kind="OPS", args=("none", 40), x=(2, 40, 13, 17)),
+    "avg_pool_3x3_c24_st2": dict(kind="OPS", args=("avg_pool_3x3", 24, 2), x=(1, 24, 13, 18)),
+    "max_pool_3x3_c24_st2": dict(kind="OPS", args=("max_pool_3x3", 24, 2), x=(1, 24, 13, 18)),
+    "none_c24_st2": dict(kind="OPS", args=("none", 24, 2), x=(1, 24, 13, 18)),
     "relu_conv_bn_1x1": dict(kind="ReLUConvBN", args=(200, 40, 1, 1, 0), x=(2, 200, 9, 10)),
     "relu_conv_bn_3x3_s2": dict(kind="ReLUConvBN", args=(24, 48, 3, 2, 1), x=(1, 24, 11, 14)),
     "factorized_reduce_even": dict(kind="FactorizedReduce", args=(128, 40), x=(2, 128, 12, 16)),
@@ -60,7 +67,7 @@ def make_op(name):
     torch.manual_seed(100 + sorted(OP_CASES).index(name))
     kind, args = spec["kind"], spec["args"]
     if kind == "OPS":
-        m = add_b200.OPS[args[0]](args[1], 1, BN, 1e-5, 0.1, True)
+        m = add_b200.OPS[args[0]](args[1], args[2] if len(args) > 2 else 1, BN, 1e-5, 0.1, True)
     else:
         m = getattr(add_b200, kind)(*args, BN)
     return _randomized(m, 11)
