@@ -74,6 +74,15 @@ def gen_ops():
     with torch.no_grad():
         g["edm/y"] = f32(ref(x.clone()))
     g["edm/wsum"] = np.float64(util.weight_checksum(ours.state_dict()))
+    # a Cell whose genotype uses every primitive (pools, skip_connect, none) — reference Cell, ADD.py:14-116
+    ours, xpp, xp = util.make_cell_case()
+    cc = util.CELL_CASE
+    ref = RefCell(BN, 5, cc["prev_prev_C"], cc["prev_C"], util.MIXED_CELL.copy(), 1, cc["C_out"], 0, False, True)
+    ref.load_state_dict(ours.state_dict(), strict=True); ref.eval()
+    with torch.no_grad():
+        _, concat, dense = ref(xpp, xp)
+    g["cell_mixed/concat"] = f32(concat); g["cell_mixed/dense"] = f32(dense)
+    g["cell_mixed/wsum"] = np.float64(util.weight_checksum(ours.state_dict()))
     # confidence scalars
     lg = util.make_logits_case()
     g["conf/entropy"] = np.float64(ref_ops.normalized_shannon_entropy(lg))

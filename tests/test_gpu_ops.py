@@ -37,6 +37,17 @@ def test_op_bf16(name):
     assert util.rel_err(y.float(), ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, F32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_mixed_cell(dtype, tol):
+    """A whole Cell whose genotype uses every primitive (pools, skip_connect, none and the convs), fp32 and bf16."""
+    m, xpp, xp = util.make_cell_case()
+    m = m.to(DEV)
+    cl = torch.channels_last
+    _, concat, dense = m(xpp.to(DEV).to(dtype).contiguous(memory_format=cl), xp.to(DEV).to(dtype).contiguous(memory_format=cl))
+    assert util.rel_err(concat.float(), torch.from_numpy(OPS["cell_mixed/concat"])) < tol
+    assert util.rel_err(dense.float(), torch.from_numpy(OPS["cell_mixed/dense"])) < tol
+
+
 def test_aspp_decoder_edm_fp32():
     m, x = util.make_aspp_case()
     y = m.to(DEV)(x.to(DEV))

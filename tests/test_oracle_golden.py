@@ -57,6 +57,17 @@ def test_aspp_decoder_edm_match_reference():
     assert util.rel_err(y, torch.from_numpy(OPS["edm/y"])) < TOL
 
 
+def test_mixed_cell_matches_reference():
+    """Cell with pools / skip_connect / none edges next to the convs (every OPS primitive) vs the reference Cell."""
+    m, xpp, xp = util.make_cell_case()
+    assert util.weight_checksum(m.state_dict()) == pytest.approx(float(OPS["cell_mixed/wsum"]), rel=1e-12)
+    arch = orc.Arch([1], [], util.MIXED_CELL.copy(), 19, 24, 5, 0)
+    with torch.no_grad():
+        _, concat, dense = orc.cell_forward(_sd(m), "m", arch, 0, False, True, xpp, xp)
+    assert util.rel_err(concat, torch.from_numpy(OPS["cell_mixed/concat"])) < TOL
+    assert util.rel_err(dense, torch.from_numpy(OPS["cell_mixed/dense"])) < TOL
+
+
 def test_confidence_scalars_match_reference():
     lg = util.make_logits_case()
     assert orc.normalized_shannon_entropy(lg) == pytest.approx(float(OPS["conf/entropy"]), rel=1e-5)

@@ -97,6 +97,20 @@ def make_decoder_case():
     return m, x, low, (33, 49)
 
 
+# a cell genotype that uses every primitive (pools, skip_connect, none next to the convs): rows [branch, primitive]
+MIXED_CELL = np.array([[0, 1], [1, 4], [2, 2], [4, 3], [5, 6], [8, 0], [9, 5], [12, 2], [14, 7], [19, 1]], dtype=np.int64)
+CELL_CASE = dict(prev_prev_C=48, prev_C=64, C_out=24, x_pp=(2, 48, 11, 14), x_p=(2, 64, 11, 14))
+
+
+def make_cell_case():
+    from add_b200.ADD import Cell
+    torch.manual_seed(204)
+    m = Cell(BN, 5, CELL_CASE["prev_prev_C"], CELL_CASE["prev_C"], MIXED_CELL.copy(), 1, CELL_CASE["C_out"], 0, False, True)
+    m = _randomized(m, 14)
+    g = torch.Generator().manual_seed(606)
+    return m, torch.randn(*CELL_CASE["x_pp"], generator=g), torch.randn(*CELL_CASE["x_p"], generator=g)
+
+
 def make_edm():
     torch.manual_seed(203)
     return add_b200.EDM().eval()
