@@ -1,21 +1,15 @@
 """Primitive table and the shipped cell genotype (reference: modeling/genotypes.py:5-14 and
 searched_arch/autodeeplab/genotype.npy — the file every reference script loads, eval.py:43,68)."""
-from collections import namedtuple
+import collections
 
 import numpy as np
 
-Genotype = namedtuple('Genotype', 'cell cell_concat')
+# index -> op name, in the order the genotype's primitive indices refer to (reference table, genotypes.py:5-14)
+PRIMITIVES = ['none'] + [f'{kind}_pool_3x3' for kind in ('max', 'avg')] + ['skip_connect'] + \
+             [f'{kind}_conv_{k}x{k}' for kind in ('sep', 'dil') for k in (3, 5)]
+assert PRIMITIVES[4:] == ['sep_conv_3x3', 'sep_conv_5x5', 'dil_conv_3x3', 'dil_conv_5x5']
 
-PRIMITIVES = [
-    'none',
-    'max_pool_3x3',
-    'avg_pool_3x3',
-    'skip_connect',
-    'sep_conv_3x3',
-    'sep_conv_5x5',
-    'dil_conv_3x3',
-    'dil_conv_5x5',
-]
+Genotype = collections.namedtuple('Genotype', ['cell', 'cell_concat'])
 
 # rows = [branch_index, primitive_index]; int64 [10, 2] exactly as stored in genotype.npy
 AUTODEEPLAB_CELL = np.array(

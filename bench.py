@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--exit-mode", default="reference", choices=["reference", "forward"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-images", type=int, default=2, help="images in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-images", type=int, default=12, help="images in the bounded CPU-baseline sample")
     ap.add_argument("--label-dtype", default="uint8", choices=["uint8", "int64"],
                     help="dtype of the HOST labels fed to the e2e loop (uint8 = Cityscapes PNG depth, widened on the device)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel launch table (JSON) here")
