@@ -196,24 +196,8 @@ class ADD(AddModule):
         self.stem1 = nn.Sequential(_conv_holder(64, 64, 3, 1, 1), BatchNorm(64, eps=eps, momentum=momentum))
         self.stem2 = nn.Sequential(nn.ReLU(inplace=True), _conv_holder(64, 128, 3, 2, 1), BatchNorm(128, eps=eps, momentum=momentum))
 
-        self.cells = nn.ModuleList()
         na = self.network_arch
-        for i in range(self.num_net):
-            level, prev_level, prev_prev_level = na[i], na[i - 1], na[i - 2]
-            downup = int(prev_level - level)
-            if i == 0:
-                downup = int(0 - level)
-                cell = Cell(BatchNorm, B, 64, 128, self.cell_arch, na[i], F_ * fm[level], downup, False, True)
-            elif i == 1:
-                cell = Cell(BatchNorm, B, 128, FB * fm[prev_level], self.cell_arch, na[i], F_ * fm[level], downup, False, True)
-            elif i == 2:
-                cell = Cell(BatchNorm, B, FB * fm[prev_prev_level], FB * fm[prev_level], self.cell_arch, na[i],
-                            F_ * fm[level], downup, False, True)
-            else:
-                dense_channels = [F_ * fm[s] for s in na[:i - 1]]
-                cell = Cell(BatchNorm, B, dense_channels, FB * fm[prev_level], self.cell_arch, na[i],
-                            F_ * fm[level], downup, True, i < self.num_net - 2)
-            self.cells.append(cell)
+        self.cells = nn.ModuleList(self._build_cells(BatchNorm, F_, B))
 
         self._aspp_mult = {1: 2, 2: 1, 3: 0.5}[na[-1]]
         self.low_level_conv = nn.Sequential(nn.ReLU(), _conv_holder(FB * 2 ** na[low_level_layer], LOW_LEVEL_C, 1),
@@ -229,6 +213,30 @@ class ADD(AddModule):
             elif d > 0:
                 self.conv_aspp.append(ReLUConvBN(FB * 2 ** na[c], FB * 2 ** na[-1], 1, 1, 0, BatchNorm, eps=eps, momentum=momentum, affine=True))
         self._init_weight()
+
+    DENSE = True          # ADD: cells >= 3 read the projected outputs of all earlier cells (ADD.py:205-238)
+
+    def _build_cells(self, BatchNorm, F_, B):
+        """reference ADD.py:171-238 (dense wiring); the siblings without dense links override DENSE."""
+        na, fm, FB = self.network_arch, {0: 1, 1: 2, 2: 4, 3: 8}, F_ * B
+        cells = []
+        for i in range(self.num_net):
+            level, prev_level, prev_prev_level = na[i], na[i - 1], na[i - 2]
+            downup = int(prev_level - level)
+            if i == 0:
+                downup = int(0 - level)
+                cell = Cell(BatchNorm, B, 64, 128, self.cell_arch, na[i], F_ * fm[level], downup, False, self.DENSE)
+            elif i == 1:
+                cell = Cell(BatchNorm, B, 128, FB * fm[prev_level], self.cell_arch, na[i], F_ * fm[level], downup, False, self.DENSE)
+            elif i == 2 or not self.DENSE:
+                cell = Cell(BatchNorm, B, FB * fm[prev_prev_level], FB * fm[prev_level], self.cell_arch, na[i],
+                            F_ * fm[level], downup, False, self.DENSE)
+            else:
+                dense_channels = [F_ * fm[s] for s in na[:i - 1]]
+                cell = Cell(BatchNorm, B, dense_channels, FB * fm[prev_level], self.cell_arch, na[i],
+                            F_ * fm[level], downup, True, i < self.num_net - 2)
+            cells.append(cell)
+        return cells
 
     # ---- init / bookkeeping --------------------------------------------------------------------
     def _init_weight(self):
@@ -284,7 +292,11 @@ class ADD(AddModule):
             st.update(two=[stem0, stem1], dense=[], cur=None, low_cat=None, size=(H, W))
         for i in range(first, last + 1):
             cell = self.cells[i]
-            if i < 3:
+            if not self.DENSE:       # Baselin_Model / AutoDeepLab: every cell reads the two previous outputs only
+                concat, _ = cell.emit_cell(b, st["two"][0], st["two"][1])
+                st["two"] = [st["two"][1], concat]
+                st["cur"] = concat
+            elif i < 3:
                 concat, dense = cell.emit_cell(b, st["two"][0], st["two"][1])
                 st["two"] = [st["two"][1], concat]
                 st["dense"].append(dense)
@@ -305,7 +317,7 @@ class ADD(AddModule):
                 st["low_cat"] = cat
 
     def _feature(self, st: dict, i: int) -> View:
-        return st["cur"] if i > 2 else st["two"][1]
+        return st["cur"] if (i > 2 or not self.DENSE) else st["two"][1]
 
     def _emit_exit_lowres(self, b: Builder, y: View, st: dict, i: int, aspp_size, conv_aspp_iter: int,
                           resize: bool = True, relu_feature: bool = False) -> View:

@@ -14,6 +14,7 @@ from .operations import (OPS, ReLUConvBN, DilConv, SepConv, Identity, Zero, Fact
 from .aspp_train import ASPP_train
 from .decoder import Decoder
 from .ADD import ADD, Cell, EDM
+from .baseline_model import Baselin_Model, AutoDeepLab, Cell_baseline, Cell_AutoDeepLab
 from .metrics import Evaluator
 from .factory import build_add, Args, synthetic_batch
 from .pipeline import HostPipeline

@@ -204,6 +204,11 @@ class _EdmRunner:
                             torch.empty((self.n, self.H, self.W), dtype=torch.int64, device=device))
         self.last_launches = 0
         self._side: Optional[torch.cuda.Stream] = None
+        # pinned staging for the gate's host round trip (N floats down, a few index vectors up): no pageable copies
+        self._conf_pin = torch.empty(self.n, dtype=torch.float32).pin_memory()
+        self._idx_pin = torch.empty((16, self.n), dtype=torch.int32).pin_memory()
+        self._idx_np = self._idx_pin.numpy()
+        self._idx_slot = 0
 
     # ---- per-plan output tail -------------------------------------------------------------------
     def emit_head_output(self, b: Builder, logits: View, m: int, owner) -> torch.Tensor:
@@ -230,6 +235,14 @@ class _EdmRunner:
             self.heads[key] = _Head(self, k, m, seg)
         return self.heads[key]
 
+    def _put_idx(self, dst: torch.Tensor, values) -> None:
+        """Asynchronous H2D of a short index vector through a rotating pinned row."""
+        row = self._idx_slot
+        self._idx_slot = (row + 1) % self._idx_pin.shape[0]
+        m = len(values)
+        self._idx_np[row, :m] = values
+        dst.copy_(self._idx_pin[row, :m], non_blocking=True)
+
     # ---- one batch ------------------------------------------------------------------------------
     def run(self, x: torch.Tensor, threshold: float, target: Optional[torch.Tensor] = None):
         """Returns (outputs per image, exit flag per image, confidence per image).  outputs[j] is a
@@ -253,7 +266,7 @@ class _EdmRunner:
                 seg.gather.run()
                 self.last_plans.append(seg.gather)
             if k == len(self.exits) and self.mode == "evaluate":
-                seg.idx_gt.copy_(torch.tensor(active, dtype=torch.int32), non_blocking=True)
+                self._put_idx(seg.idx_gt, active)
             seg.main.run()
             self.last_plans.append(seg.main)
             launches += seg.n_launches
@@ -261,16 +274,21 @@ class _EdmRunner:
                 for j, img in enumerate(active):
                     outs[img] = seg.out[j:j + 1] if self.mode == "logits" else seg.out[j]
                 break
-            conf = seg.conf.cpu()                      # host decision = the reference's implicit sync (ADD.py:421)
-            ex = [j for j in range(len(active)) if not (float(conf[j]) > threshold)]
-            co = [j for j in range(len(active)) if float(conf[j]) > threshold]
+            # host decision = the reference's implicit sync (ADD.py:421): N floats come down through pinned memory
+            m_act = len(active)
+            self._conf_pin[:m_act].copy_(seg.conf, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            vals = self._conf_pin[:m_act].tolist()
+            ex = [j for j in range(m_act) if not (vals[j] > threshold)]
+            co = [j for j in range(m_act) if vals[j] > threshold]
+            conf = self._conf_pin[:m_act].clone()
             for j, img in enumerate(active):
                 confs[img] = conf[j].view(1, 1)
             if ex:
                 head = self.head(k, len(ex), seg)
-                head.idx.copy_(torch.tensor(ex, dtype=torch.int32), non_blocking=True)
+                self._put_idx(head.idx, ex)
                 if self.mode == "evaluate":
-                    head.idx_gt.copy_(torch.tensor([active[j] for j in ex], dtype=torch.int32), non_blocking=True)
+                    self._put_idx(head.idx_gt, [active[j] for j in ex])
                 if co and _OVERLAP_HEADS:
                     # the early-exit head (throughput-bound: ASPP on the up-sampled map) and the remaining trunk
                     # (latency-bound small kernels) only READ this segment's state: replay them side by side
@@ -291,7 +309,7 @@ class _EdmRunner:
             if not co:
                 break
             nxt = self.segment(k + 1, len(co), seg)
-            nxt.idx.copy_(torch.tensor(co, dtype=torch.int32), non_blocking=True)
+            self._put_idx(nxt.idx, co)
             active = [active[j] for j in co]
             seg = nxt
         if pending_side:

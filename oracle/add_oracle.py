@@ -361,6 +361,51 @@ def add_forward(sd: SD, arch: Arch, x: torch.Tensor) -> List[torch.Tensor]:
     return out
 
 
+def _plain_trunk(sd: SD, arch: Arch, x: torch.Tensor):
+    """Cell stack of the non-dense siblings: every cell reads only the two previous outputs
+    (baseline_model.py:228-239 ≡ autodeeplab.py:188-197).  Yields (i, feature, low_level) after every cell."""
+    n = len(arch.network_arch)
+    stem = F.relu(_bn(sd, 'stem0.1', F.conv2d(x, sd['stem0.0.weight'], None, 2, 1)))
+    stem0 = F.relu(_bn(sd, 'stem1.1', F.conv2d(stem, sd['stem1.0.weight'], None, 1, 1)))   # stem2's in-place ReLU (Q7)
+    stem1 = _bn(sd, 'stem2.2', F.conv2d(stem0, sd['stem2.1.weight'], None, 2, 1))
+    two = [stem0, stem1]
+    low_level = None
+    for i in range(n):
+        downup = _cell_kind(arch, i)[0]
+        two = [two[1], cell_forward(sd, f'cells.{i}', arch, downup, False, False, two[0], two[1])]
+        if i == arch.low_level_layer:
+            low_level = _bn(sd, 'low_level_conv.2', F.conv2d(F.relu(two[1]), sd['low_level_conv.1.weight']))
+        yield i, two[1], low_level
+
+
+def baseline_forward(sd: SD, arch: Arch, x: torch.Tensor) -> List[torch.Tensor]:
+    """baseline_model.py:224-254 (Baselin_Model.forward): ADD.forward's exits on the non-dense cell stack."""
+    size = (x.shape[2], x.shape[3])
+    s = 2.0 ** (-1 * (arch.network_arch[-1] + 2))
+    aspp_size = (int((float(size[0]) - 1.0) * s + 1.0), int((float(size[1]) - 1.0) * s + 1.0))
+    n = len(arch.network_arch)
+    out, it = [], 0
+    for i, y, low in _plain_trunk(sd, arch, x):
+        if i in arch.C_index or i == n - 1:
+            if y.shape[2] < aspp_size[0] or y.shape[3] < aspp_size[1]:
+                y = _bilinear(y, aspp_size)
+            if arch.network_arch[i] != arch.network_arch[-1]:
+                y = _conv_aspp(sd, arch, it, i, y)
+                it += 1
+            y = aspp_train(sd, 'aspp', y, aspp_mult(arch))
+            out.append(decoder(sd, 'decoder', y, low, size))
+    return out
+
+
+def autodeeplab_forward(sd: SD, arch: Arch, x: torch.Tensor) -> torch.Tensor:
+    """autodeeplab.py:186-204 (AutoDeepLab.forward): one exit after the last cell, the feature goes to ASPP as is."""
+    size = (x.shape[2], x.shape[3])
+    y = low = None
+    for _, y, low in _plain_trunk(sd, arch, x):
+        pass
+    return decoder(sd, 'decoder', aspp_train(sd, 'aspp', y, aspp_mult(arch)), low, size)
+
+
 def add_get_feature(sd: SD, arch: Arch, x: torch.Tensor):
     """ADD.py:327-377 — (exit-1 logits, raw feature at C_index[0]); aspp_size uses 2^-L (Q3)."""
     size = (x.shape[2], x.shape[3])

@@ -138,6 +138,34 @@ def gen_nets():
     print("nets.npz", len(g), "entries", os.path.getsize(OUT / "nets.npz") / 1e6, "MB")
 
 
+def gen_siblings():
+    """Baselin_Model (baseline_model.py:93-254) and AutoDeepLab (autodeeplab.py:94-204): the unmodified reference."""
+    from modeling.baseline_model import Baselin_Model as RefBaseline
+    from modeling.autodeeplab import AutoDeepLab as RefAutoDeepLab
+    g = {}
+    for cname, spec in util.SIBLING_CASES.items():
+        ours = util.make_sibling(spec)
+        na, ci, low = util.add_b200.NETWORKS[spec["network"]][spec["C"]]
+        ns = SimpleNamespace(F=spec["F"], B=5, sync_bn=False)
+        if spec["cls"] == "Baselin_Model":
+            ref = RefBaseline(na, ci, util.cell_arch(), 19, ns, low)
+        else:
+            ref = RefAutoDeepLab(na, util.cell_arch(), 19, ns, low)
+        ref.load_state_dict(ours.state_dict(), strict=True)
+        ref.eval()
+        x, _ = util.make_input(1, *spec["size"])
+        with torch.no_grad():
+            outs = ref(x)
+        outs = outs if spec["cls"] == "Baselin_Model" else [outs[1]]
+        for e, o in enumerate(outs):
+            g[f"{cname}/forward/{e}"] = f32(o)
+        g[f"{cname}/wsum"] = np.float64(util.weight_checksum(ours.state_dict()))
+        print(cname, "done")
+    np.savez_compressed(OUT / "siblings.npz", **g)
+    print("siblings.npz", len(g), "entries")
+
+
 if __name__ == "__main__":
     gen_ops()
     gen_nets()
+    gen_siblings()

@@ -161,3 +161,22 @@ def test_host_pipeline_matches_direct_calls():
     for (cm_g, fl), (x, gt) in zip(pipe2.evaluate((x.pin_memory(), gt.pin_memory()) for x, gt in batches[:2]), batches[:2]):
         assert fl is None
         assert torch.equal(cm_g, net.evaluate(x.to(DEV), gt.to(DEV)).cpu())
+
+
+@pytest.mark.parametrize("cname", sorted(util.SIBLING_CASES))
+@pytest.mark.parametrize("precision,tol,agree_min", [("fp32", 1e-3, 0.999), ("bf16", 1e-1, 0.95)])
+def test_sibling_models(cname, precision, tol, agree_min):
+    """Baselin_Model / AutoDeepLab drop-ins (ADD's kernels and plans, non-dense wiring) vs the reference goldens."""
+    sibs = np.load(util.ROOT / "tests/golden/siblings.npz")
+    spec = util.SIBLING_CASES[cname]
+    net = util.make_sibling(spec).to(DEV)
+    net.set_precision(precision)
+    x, _ = util.make_input(1, *spec["size"])
+    outs = net(x.to(DEV))
+    if spec["cls"] == "AutoDeepLab":
+        assert outs[0] is None
+        outs = [outs[1]]
+    for e, o in enumerate(outs):
+        ref = torch.from_numpy(sibs[f"{cname}/forward/{e}"])
+        assert util.rel_err(o, ref) < tol
+        assert _agree(o.cpu(), ref) >= agree_min

@@ -118,3 +118,24 @@ def test_network_matches_reference(cname):
                     y, ee, cv = orc.add_dynamic_inference(sd, arch, x, thr, 'edm', edm_sd)
                 assert ee == (1 if label == "exit" else 0)
                 assert util.rel_err(y, torch.from_numpy(NETS[f"{tag}/dynamic_edm/{label}/y"])) < 1e-4
+
+
+SIBS = np.load(util.ROOT / "tests/golden/siblings.npz")
+
+
+@pytest.mark.parametrize("cname", sorted(util.SIBLING_CASES))
+def test_sibling_models_match_reference(cname):
+    """Baselin_Model / AutoDeepLab (no dense links) restated in the oracle vs the unmodified reference."""
+    spec = util.SIBLING_CASES[cname]
+    net = util.make_sibling(spec)
+    assert util.weight_checksum(net.state_dict()) == pytest.approx(float(SIBS[f"{cname}/wsum"]), rel=1e-12)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    na, ci, low = util.add_b200.NETWORKS[spec["network"]][spec["C"]]
+    x, _ = util.make_input(1, *spec["size"])
+    with torch.no_grad():
+        if spec["cls"] == "Baselin_Model":
+            outs = orc.baseline_forward(sd, orc.Arch(na, ci, low_level_layer=low), x)
+        else:
+            outs = [orc.autodeeplab_forward(sd, orc.Arch(na, [], low_level_layer=low), x)]
+    for e, o in enumerate(outs):
+        assert util.rel_err(o, torch.from_numpy(SIBS[f"{cname}/forward/{e}"])) < TOL

@@ -52,6 +52,23 @@ NET_CASES = {
 }
 
 
+SIBLING_CASES = {
+    "baselin-searched-C2": dict(cls="Baselin_Model", network="searched-dense", C=2, F=20, size=(33, 65)),
+    "autodeeplab-net": dict(cls="AutoDeepLab", network="autodeeplab-dense", C=2, F=20, size=(48, 80)),
+}
+
+
+def make_sibling(spec):
+    """Baselin_Model / AutoDeepLab with the reference drivers' network paths, seeded, BN-randomised."""
+    na, ci, low = add_b200.NETWORKS[spec["network"]][spec["C"]]
+    torch.manual_seed(1)
+    if spec["cls"] == "Baselin_Model":
+        m = add_b200.Baselin_Model(na, ci, add_b200.AUTODEEPLAB_CELL.copy(), 19, add_b200.Args(spec["F"], 5), low)
+    else:
+        m = add_b200.AutoDeepLab(na, add_b200.AUTODEEPLAB_CELL.copy(), 19, add_b200.Args(spec["F"], 5), low)
+    return _randomized(m, 22)
+
+
 def weight_checksum(sd) -> float:
     return float(sum(v.double().abs().sum().item() for k, v in sorted(sd.items()) if v.dtype.is_floating_point))
 
