@@ -313,7 +313,8 @@ class ADD(AddModule):
             if i == self.low_level_layer:
                 src = st["two"][1]
                 cat = self.decoder.new_cat(b, src.n, src.h, src.w)
-                b.conv(src, cat.slice(ASPP_C, LOW_LEVEL_C), self.cw_low, 1, 0, 1, RELU_IN, "ADD.low_level_conv")
+                # stored post-ReLU: the decoder's `_conv` (its only reader) starts with ReLU (decoder.py:13)
+                b.conv(src, cat.slice(ASPP_C, LOW_LEVEL_C), self.cw_low, 1, 0, 1, RELU_IN | RELU_OUT, "ADD.low_level_conv")
                 st["low_cat"] = cat
 
     def _feature(self, st: dict, i: int) -> View:
@@ -322,19 +323,24 @@ class ADD(AddModule):
     def _emit_exit_lowres(self, b: Builder, y: View, st: dict, i: int, aspp_size, conv_aspp_iter: int,
                           resize: bool = True, relu_feature: bool = False) -> View:
         """[resize →] [conv_aspp →] ASPP → decoder convs; returns fp32 low-res logits (ADD.py:316-323)."""
+        # ASPP starts with ReLU (aspp_train.py:35) and is the only reader of what the resize / level adapter produce here,
+        # so those store relu(.) and the ASPP convs skip their ReLU-on-load pass (it costs shared-memory bandwidth on
+        # the critical path of the 3x3s: ncu r01y, tensor pipe 61 % busy)
+        relud = False
         if resize and (y.h < aspp_size[0] or y.w < aspp_size[1]):
             r = b.scratch(y.n, aspp_size[0], aspp_size[1], y.c)
             # EDM's in-place ReLU (Q4) makes the exit interpolate relu(y)
-            b.bilinear(y, r, RELU_IN if relu_feature else 0, "ADD.exit_resize")
-            y = r
+            last_producer = self.network_arch[i] == self.network_arch[-1]
+            b.bilinear(y, r, (RELU_IN if relu_feature else 0) | (RELU_OUT if last_producer else 0), "ADD.exit_resize")
+            y, relud = r, last_producer
         if self.network_arch[i] != self.network_arch[-1]:
             mod = self.conv_aspp[conv_aspp_iter]
             n_, c_, h_, w_ = mod.out_shape(y.n, y.c, y.h, y.w)
             a_in = b.scratch(n_, h_, w_, c_)
-            mod.emit(b, y, a_in, 0)
-            y = a_in
+            mod.emit(b, y, a_in, RELU_OUT)
+            y, relud = a_in, True
         a = b.scratch(y.n, y.h, y.w, ASPP_C)
-        self.aspp.emit(b, y, a, 0)
+        self.aspp.emit(b, y, a, IN_RELUD if relud else 0)
         logits = self.decoder.emit_lowres(b, a, st["low_cat"])
         b.release(a)
         return logits

@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from . import runtime as rt
 from .operations import AddModule, _conv_holder
-from .runtime import Builder, ConvWeights, View, RELU_IN, RELU_OUT
+from .runtime import Builder, ConvWeights, View, RELU_IN, RELU_OUT, IN_RELUD
 
 
 class ASPP_train(AddModule):
@@ -47,14 +47,16 @@ class ASPP_train(AddModule):
         """aspp_train.py:34-61."""
         self._ensure_prepared()
         d = self._depth
+        rin = 0 if flags & IN_RELUD else RELU_IN      # IN_RELUD: the producer already stored relu(x) (aspp_train.py:35)
+        flags &= ~IN_RELUD
         cat = b.scratch(x.n, x.h, x.w, 4 * d)
-        b.conv(x, cat.slice(0, d), self.cw[0], 1, 0, 1, RELU_IN | RELU_OUT, "ASPP.aspp1")
+        b.conv(x, cat.slice(0, d), self.cw[0], 1, 0, 1, rin | RELU_OUT, "ASPP.aspp1")
         for i, dil in enumerate(self.dils):
-            b.conv(x, cat.slice(d * (i + 1), d), self.cw[i + 1], 1, dil, dil, RELU_IN | RELU_OUT, f"ASPP.aspp{i + 2}")
+            b.conv(x, cat.slice(d * (i + 1), d), self.cw[i + 1], 1, dil, dil, rin | RELU_OUT, f"ASPP.aspp{i + 2}")
         # image-pool branch (aspp_train.py:49-57): GAP -> 1x1+BN+ReLU -> broadcast is constant over the image, so it
         # enters the final 1x1 as a per-image bias instead of 256 broadcast channels of the concatenation
         pooled = b.raw((x.n, self._C), torch.float32)
-        b.gap(x, pooled, RELU_IN, "ASPP.gap")
+        b.gap(x, pooled, rin, "ASPP.gap")
         bias_n = b.raw((x.n, self._out), torch.float32)
         b.aspp_pool_bias(pooled, self.cw[4], self.w_out_pool, self.cw_out.bias, bias_n, "ASPP.pool_bias")
         b.conv(cat, y, self.cw_out_main, 1, 0, 1, flags, "ASPP.conv1", image_bias=bias_n)

@@ -152,7 +152,12 @@ __device__ __forceinline__ void issue_tap_ring_dispatch(int ks, uint32_t tmem_d,
 // MT = M-tiles (128 pixels each) that share every weight tile: with N_pad = 256 the weight tile (32 KB) is 2/3 of a
 // stage's L2->smem traffic and the ASPP / decoder 3x3s ran AT the L2 bandwidth ceiling (1085 TF/s x 48 KB per
 // 128x256x64 MACs = 12.4 TB/s); MT = 2 computes two adjacent pixel tiles per weight tile (1.5x less traffic).
-template <int MT>
+// CL = thread-block cluster size (1 or 2).  CL = 2: the two CTAs of a cluster walk the SAME sequence of weight tiles
+// in lockstep (different pixel units); each fetches HALF of every weight tile and TMA-multicasts it into both CTAs'
+// ring slot, so a weight tile crosses L2 -> SM once per cluster instead of once per CTA (ncu r01y: the ASPP 3x3s
+// moved 10.6 TB/s from L2, ~85 % of the measured ~12.4 TB/s L2 ceiling, tensor pipe 61 % busy).  A slot is recycled
+// when BOTH CTAs' MMAs have consumed it: the empty barrier counts CL arrivals, the MMA commit is multicast.
+template <int MT, int CL>
 __global__ void __launch_bounds__(TCP_THREADS)
 conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -180,7 +185,7 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, CL);
       mbar_init(bar_relu + 8 * s, 128);
     }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
@@ -196,14 +201,19 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // the peer's barriers are initialised before anyone arrives on them remotely
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   pdl_launch_dependents();        // (waits for the previous kernel: producer before its first activation load,
                                   //  epilogue warps before their first y access — see pdl_wait() below)
   const int BW = 1 << p.bw_log2, BH = TC_BM >> p.bw_log2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int n_units = (p.n_tiles + MT - 1) / MT;                   // a unit = MT consecutive tiles
   const int n_img = p.n_tiles / tiles_per_img;
+  // every CTA runs the same number of units (lockstep within a cluster); surplus units are computed on zero-filled
+  // tiles and never stored
+  const int units_per_cta = (n_units + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -214,7 +224,8 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
       }
       pdl_wait();
       int s = 0; uint32_t ph = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int uj = 0; uj < units_per_cta; ++uj) {
+        const int u = (int)blockIdx.x + uj * (int)gridDim.x;
         int tn[MT], xin[MT], yin[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
@@ -232,7 +243,13 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
 #pragma unroll
           for (int m = 0; m < MT; ++m)
             tma_load_4d(a_dst + m * TC_A_BYTES, &map_x, bar_full + 8 * s, kc * TC_BK, xin[m] + kx * p.dil, yin[m] + ky * p.dil, tn[m]);
-          if (!p.b_resident) tma_load_3d(a_dst + MT * TC_A_BYTES, &map_w, bar_full + 8 * s, 0, 0, it);
+          if (!p.b_resident) {
+            if (CL > 1)      // my half of the weight rows, into both CTAs' slot s
+              tma_load_3d_multicast(a_dst + MT * TC_A_BYTES + crank * (p.b_bytes / CL), &map_w, bar_full + 8 * s, 0,
+                                    (int)crank * (p.n_pad / CL), it, (uint16_t)((1u << CL) - 1u));
+            else
+              tma_load_3d(a_dst + MT * TC_A_BYTES, &map_w, bar_full + 8 * s, 0, 0, it);
+          }
           if (++kc == p.kchunks) { kc = 0; if (++kx == p.taps_w) { kx = 0; ++ky; } }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -244,7 +261,8 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       if (p.b_resident) mbar_wait(bar_bres, 0);
       int s = 0; uint32_t ph = 0; int ti = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
+      for (int uj = 0; uj < units_per_cta; ++uj, ++ti) {
+        const int u = (int)blockIdx.x + uj * (int)gridDim.x;
         const int ab = nbuf == 2 ? (ti & 1) : 0;
         const uint32_t tph = nbuf == 2 ? ((uint32_t)(ti >> 1) & 1u) : ((uint32_t)ti & 1u);
         mbar_wait(bar_tempty + 8 * ab, tph ^ 1u);
@@ -263,7 +281,8 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
             const uint64_t adesc = make_kmajor_sw128_desc(a_src + m * TC_A_BYTES);
             issue_tap_ring_dispatch(ksteps, tmem_base + (uint32_t)(ab * MT + m) * tmem_cols, adesc, bdesc, idesc, it > 0 ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * s);
+          if (CL > 1) umma_commit_multicast(bar_empty + 8 * s, (uint16_t)((1u << CL) - 1u));
+          else umma_commit(bar_empty + 8 * s);
           if (++kc == p.kchunks) kc = 0;
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -275,7 +294,8 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     if (relu_in) {
       const int et = threadIdx.x - 64;
       int s = 0; uint32_t ph = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int uj = 0; uj < units_per_cta; ++uj) {
+        const int u = (int)blockIdx.x + uj * (int)gridDim.x;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(bar_full + 8 * s, ph);
           relu_sweep(ring_base + s * stage_bytes, MT * TC_A_BYTES, et);
@@ -291,7 +311,8 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     asm volatile("bar.sync 1, 128;" ::: "memory");
     pdl_wait();
     int ti = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
+    for (int uj = 0; uj < units_per_cta; ++uj, ++ti) {
+        const int u = (int)blockIdx.x + uj * (int)gridDim.x;
       const int ab = nbuf == 2 ? (ti & 1) : 0;
       const uint32_t tph = nbuf == 2 ? ((uint32_t)(ti >> 1) & 1u) : ((uint32_t)ti & 1u);
       mbar_wait_relaxed(bar_tfull + 8 * ab, tph);
@@ -317,6 +338,7 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)nbuf * MT * tmem_cols) : "memory");
   }
@@ -754,6 +776,7 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
 }
 
 // ---- host side -----------------------------------------------------------------------------------
+int g_conv_cluster = 1;             // 1 = cluster-of-2 weight multicast for the N_pad = 256 convs (mode bit 8 clears)
 int g_halo_pairs = 1;               // 1 = row pairs in the persistent halo kernel (mode bit 7 clears)
 int g_conv_mt2 = 1;                 // 1 = two pixel tiles per weight tile for the weight-heavy convs (mode bit 6 clears)
 int g_halo_stream_persistent = 0;   // 1 = use the persistent halo kernel also when the weights stream through a ring (tuning)
@@ -897,19 +920,37 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
       const size_t psmem = fixed + (size_t)st * sbytes;
       static std::once_flag ponce;
       std::call_once(ponce, [] {
-        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv2d_tc_persistent_kernel<2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       });
       const long long units = (grid + mt - 1) / mt;
       long long g = (long long)sms * (two ? 2 : 1) * g_add_grid_pct / 100;
       if (g > units) g = units;
       if (g < 1) g = 1;
-      if (mt == 2)
-        launch_kernel(conv2d_tc_persistent_kernel<2>, dim3((unsigned)g), dim3(TCP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
-      else
-        launch_kernel(conv2d_tc_persistent_kernel<1>, dim3((unsigned)g), dim3(TCP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
+      // cluster of 2 with multicast weight halves: the N_pad = 256 convs (ASPP / decoder 3x3) that sit at the L2 ceiling
+      const bool cl2 = g_conv_cluster && mt == 2 && p.n_pad == 256 && g >= 2 && units >= 4ll * sms;
+      if (cl2) {
+        g &= ~1ll;                                        // whole clusters
+        CUtensorMap map_wh;
+        cuuint64_t dims[3] = {(cuuint64_t)TC_BK, (cuuint64_t)p.n_pad, (cuuint64_t)(p.taps * p.kchunks)};
+        cuuint64_t strides[2] = {(cuuint64_t)TC_BK * 2, (cuuint64_t)p.n_pad * TC_BK * 2};
+        cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.n_pad / 2), 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (encode(&map_wh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return ADD_ERR_UNSUPPORTED;
+        launch_kernel_cluster(conv2d_tc_persistent_kernel<2, 2>, dim3((unsigned)g), dim3(TCP_THREADS), psmem,
+                              static_cast<cudaStream_t>(stream), 2, map_x, map_wh, p);
+      } else if (mt == 2) {
+        launch_kernel(conv2d_tc_persistent_kernel<2, 1>, dim3((unsigned)g), dim3(TCP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
+      } else {
+        launch_kernel(conv2d_tc_persistent_kernel<1, 1>, dim3((unsigned)g), dim3(TCP_THREADS), psmem, static_cast<cudaStream_t>(stream), map_x, map_w, p);
+      }
       ADD_RETURN_LAUNCH();
     }
   }
@@ -966,6 +1007,7 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
 /* Tuning / experiment switch for the halo-resident A path (see conv2d_tc_halo_kernel). */
 extern "C" int add_conv2d_tc_set_halo_mode(int mode) {
   g_persistent = (mode & 16) ? 0 : 1;                 // bit 4 set = one tile per CTA (A/B runs)
+  g_conv_cluster = (mode & 256) ? 0 : 1;              // bit 8 set = no clusters / multicast
   g_halo_pairs = (mode & 128) ? 0 : 1;                // bit 7 set = no row pairs in the persistent halo kernel
   g_conv_mt2 = (mode & 64) ? 0 : 1;                   // bit 6 set = one pixel tile per weight tile everywhere
   g_halo_stream_persistent = (mode & 32) ? 1 : 0;     // bit 5 set = persistent halo kernel with streamed weights

@@ -49,9 +49,11 @@ class Decoder(AddModule):
         `cat[..., 256:304]` must already hold the low-level feature.  Only H is compared when
         deciding whether to resize (Q8)."""
         self._ensure_prepared()
-        b.bilinear(x, cat.slice(0, ASPP_C), 0, "Decoder.up" if x.h != cat.h else "Decoder.copy")
+        # `_conv` starts with ReLU and is the only reader of the concat, so both producers store relu(.) (the low-level
+        # slice is written with RELU_OUT by its producer) and the 3x3 needs no ReLU-on-load pass over its A tiles
+        b.bilinear(x, cat.slice(0, ASPP_C), RELU_OUT, "Decoder.up" if x.h != cat.h else "Decoder.copy")
         t1 = b.scratch(cat.n, cat.h, cat.w, 256)
-        b.conv(cat, t1, self.cw1, 1, 1, 1, RELU_IN | RELU_OUT, "Decoder.conv1")
+        b.conv(cat, t1, self.cw1, 1, 1, 1, RELU_OUT, "Decoder.conv1")
         t2 = b.scratch(cat.n, cat.h, cat.w, 256)
         b.conv(t1, t2, self.cw2, 1, 1, 1, RELU_OUT, "Decoder.conv2")
         pad_c = (self.n_class + 3) // 4 * 4
@@ -72,7 +74,7 @@ class Decoder(AddModule):
         if x.shape[2] == low_level.shape[2] and x.shape[3] != low_level.shape[3]:
             raise RuntimeError("Decoder: equal H but different W — torch.cat fails in the reference too (Q8)")
         cat = self.new_cat(b, lv.n, lv.h, lv.w)
-        b.bilinear(lv, cat.slice(ASPP_C, LOW_LEVEL_C), 0, "Decoder.low_copy")
+        b.bilinear(lv, cat.slice(ASPP_C, LOW_LEVEL_C), RELU_OUT, "Decoder.low_copy")
         logits = self.emit_lowres(b, xv, cat)
         H, W = int(size[0]), int(size[1])
         out = torch.empty((xv.n, self.n_class, H, W), device=x.device, dtype=torch.float32)

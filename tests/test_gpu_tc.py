@@ -74,6 +74,9 @@ CASES = [
     (64, 64, 3, 1, 1, 1, 90, 300, RELU_OUT),
     (80, 80, 3, 1, 2, 2, 120, 127, RELU_IN),
     (80, 80, 5, 1, 4, 2, 100, 128, RELU_IN | ACCUMULATE),
+    # large enough (>= 4 x SMs units of two tiles) for the cluster-of-2 path: weight halves TMA-multicast to both CTAs
+    (400, 256, 3, 1, 6, 6, 64, 1280, RELU_IN | RELU_OUT),
+    (304, 256, 3, 1, 1, 1, 75, 1100, RELU_OUT),
     # row pairs (r, r + dil): odd heights leave unpaired / out-of-image rows
     (40, 40, 5, 1, 4, 2, 125, 253, RELU_IN),
     (40, 40, 3, 1, 2, 2, 63, 127, RELU_IN | ACCUMULATE),

@@ -32,6 +32,7 @@ def cases():
             ("stem1_64to64_3x3", "conv", (64, 64, 3, 1, 1, 1, 8, 512, 1024, RELU_OUT)),
             ("stem2_64to128_s2", "conv", (64, 128, 3, 2, 1, 1, 8, 512, 1024, RELU_IN)),
             ("aspp_400to256_d12", "conv", (400, 256, 3, 1, 12, 12, 4, 256, 512, RELU_IN | RELU_OUT)),
+            ("aspp_400to256_d12_norelu", "conv", (400, 256, 3, 1, 12, 12, 4, 256, 512, RELU_OUT)),
             ("dec_304to256_3x3", "conv", (304, 256, 3, 1, 1, 1, 4, 128, 256, RELU_IN | RELU_OUT))]
     return out
 
