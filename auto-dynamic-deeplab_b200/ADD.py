@@ -91,9 +91,12 @@ class Cell(AddModule):
     def scale_dimension(self, dim, scale):
         return _scale_dimension(dim, scale)
 
-    def emit_cell(self, b: Builder, prev_prev, prev: View) -> Tuple[View, Optional[View]]:
+    def emit_cell(self, b: Builder, prev_prev, prev: View, concat_relud: bool = False) -> Tuple[View, Optional[View]]:
         """Emit the whole cell.  prev_prev: View (dense_in False) or list of Views.
-        Returns (concat [N,h,w,B*C], dense [N,h,w,C] or None)."""
+        Returns (concat [N,h,w,B*C], dense [N,h,w,C] or None).
+        concat_relud: the caller guarantees that every reader of the concat outside this cell starts with ReLU
+        (next cell's ReLUConvBN / FactorizedReduce, low_level_conv — not a bilinear resize, not an exit); the node
+        sums are then stored as relu(sum) by their last edge and all readers skip the ReLU-on-load pass."""
         C, n = self.C_out, prev.n
         temps: List[View] = []
         s1_in = prev
@@ -110,6 +113,7 @@ class Cell(AddModule):
         # s0 / s1 are read only by the cell's ops, which all start with ReLU (operations.py:33,47): store relu(s)
         # once (RELU_OUT) and let the five ops that read them skip their ReLU-on-load pass
         pre_flags = RELU_OUT if self._all_relu_first else 0
+        concat_relud = concat_relud and self._all_relu_first
         self.preprocess.emit(b, s1_in, s1, pre_flags)
         s0 = b.scratch(n, h, w, C)
         temps += [s0, s1]
@@ -133,14 +137,17 @@ class Cell(AddModule):
                     self.pre_preprocess[i].emit(b, src, cat.slice(i * C, C), 0)
             self.pre_preprocess_1x1.emit(b, cat, s0, pre_flags)
         concat = b.alloc(n, h, w, self.B * C)
+        s0.relud = s1.relud = bool(pre_flags)
         states = [s0, s1] + [concat.slice(i * C, C) for i in range(self.B)]
         for i, edges in enumerate(self._steps):  # ADD.py:97-110
             dst = states[2 + i]
             if not edges:
                 raise NotImplementedError("cell step without inputs (sum of empty list) is not supported")
             for e, (j, k) in enumerate(edges):
-                self._ops[k].emit(b, states[j], dst, (ACCUMULATE if e > 0 else 0) |
-                                  (IN_RELUD if (j < 2 and self._all_relu_first) else 0))
+                last = e == len(edges) - 1
+                self._ops[k].emit(b, states[j], dst, (ACCUMULATE if e > 0 else 0) | (RELU_OUT if (last and concat_relud) else 0))
+            dst.relud = concat_relud              # later edges of this cell read relu(node sum) without a ReLU pass
+        concat.relud = concat_relud
         dense = None
         if self.dense_out:
             dense = b.alloc(n, h, w, C)
@@ -292,30 +299,46 @@ class ADD(AddModule):
             st.update(two=[stem0, stem1], dense=[], cur=None, low_cat=None, size=(H, W))
         for i in range(first, last + 1):
             cell = self.cells[i]
+            cr = self._concat_may_be_relud(i)
             if not self.DENSE:       # Baselin_Model / AutoDeepLab: every cell reads the two previous outputs only
-                concat, _ = cell.emit_cell(b, st["two"][0], st["two"][1])
+                concat, _ = cell.emit_cell(b, st["two"][0], st["two"][1], cr)
                 st["two"] = [st["two"][1], concat]
                 st["cur"] = concat
             elif i < 3:
-                concat, dense = cell.emit_cell(b, st["two"][0], st["two"][1])
+                concat, dense = cell.emit_cell(b, st["two"][0], st["two"][1], cr)
                 st["two"] = [st["two"][1], concat]
                 st["dense"].append(dense)
                 if i == 2:
                     st["cur"] = concat
             elif i < self.num_net - 2:
-                concat, dense = cell.emit_cell(b, list(st["dense"][:-1]), st["cur"])
+                concat, dense = cell.emit_cell(b, list(st["dense"][:-1]), st["cur"], cr)
                 st["cur"] = concat
                 st["dense"].append(dense)
             elif i == self.num_net - 1:
-                st["cur"], _ = cell.emit_cell(b, list(st["dense"]), st["cur"])
+                st["cur"], _ = cell.emit_cell(b, list(st["dense"]), st["cur"], cr)
             else:
-                st["cur"], _ = cell.emit_cell(b, list(st["dense"][:-1]), st["cur"])
+                st["cur"], _ = cell.emit_cell(b, list(st["dense"][:-1]), st["cur"], cr)
             if i == self.low_level_layer:
                 src = st["two"][1]
                 cat = self.decoder.new_cat(b, src.n, src.h, src.w)
                 # stored post-ReLU: the decoder's `_conv` (its only reader) starts with ReLU (decoder.py:13)
                 b.conv(src, cat.slice(ASPP_C, LOW_LEVEL_C), self.cw_low, 1, 0, 1, RELU_IN | RELU_OUT, "ADD.low_level_conv")
                 st["low_cat"] = cat
+
+    def _concat_may_be_relud(self, i: int) -> bool:
+        """True when every reader of cell i's concat outside the cell starts with ReLU: not an exit feature (resized /
+        returned raw), the next cell does not up-sample it (ADD.py:71-77 interpolates the raw tensor) and no later cell
+        reads it through a bilinear resize as its prev_prev input (ADD.py:83-86)."""
+        if i in self.C_index or i >= self.num_net - 1:
+            return False
+        if self.cells[i + 1].downup_sample == 1:
+            return False
+        reads_as_prev_prev = (i + 2 < self.num_net) if not self.DENSE else (i == 0 and self.num_net > 2)
+        # the prev_prev reader resizes whenever the heights differ (down/up-sampling does not round-trip on even
+        # sizes), so only a run of same-resolution cells is safe
+        if reads_as_prev_prev and (self.cells[i + 1].downup_sample != 0 or self.cells[i + 2].downup_sample != 0):
+            return False
+        return True
 
     def _feature(self, st: dict, i: int) -> View:
         return st["cur"] if (i > 2 or not self.DENSE) else st["two"][1]

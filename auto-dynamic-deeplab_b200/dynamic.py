@@ -48,7 +48,7 @@ def _alloc_state_like(b: Builder, st: dict, m: int, need_two: bool) -> dict:
         key = id(v.buf)
         if key not in made:
             made[key] = View(b.raw((m,) + tuple(v.buf.shape[1:]), v.buf.dtype))
-        return View(made[key].buf, v.c_off, v.c)
+        return View(made[key].buf, v.c_off, v.c, v.relud)
 
     new = dict(two=[like(v) if need_two else None for v in st["two"]], dense=[like(v) for v in st["dense"]],
                cur=like(st["cur"]) if st.get("cur") is not None else None,

@@ -60,13 +60,16 @@ def require_cuda(t: torch.Tensor, what: str = "input") -> None:
 
 class View:
     """Channel-slice view of a dense NHWC buffer (torch tensor of shape [N,H,W,Ctot])."""
-    __slots__ = ("buf", "c_off", "c")
+    __slots__ = ("buf", "c_off", "c", "relud")
 
-    def __init__(self, buf: torch.Tensor, c_off: int = 0, c: Optional[int] = None):
+    def __init__(self, buf: torch.Tensor, c_off: int = 0, c: Optional[int] = None, relud: bool = False):
         assert buf.dim() == 4 and buf.is_contiguous()
         self.buf = buf
         self.c_off = c_off
         self.c = buf.shape[3] - c_off if c is None else c
+        # relud: the buffer holds relu(value) because its producer stored it with RELU_OUT and every reader starts with
+        # ReLU; convs reading it skip their ReLU-on-load pass (exact: relu is idempotent), raw readers must not see it
+        self.relud = relud
         assert 0 <= c_off and c_off + self.c <= buf.shape[3]
 
     n = property(lambda s: s.buf.shape[0])
@@ -75,7 +78,7 @@ class View:
     dtype = property(lambda s: s.buf.dtype)
 
     def slice(self, off: int, c: int) -> "View":
-        return View(self.buf, self.c_off + off, c)
+        return View(self.buf, self.c_off + off, c, self.relud)
 
     def desc(self) -> AddTensor:
         b = self.buf
@@ -286,6 +289,9 @@ class Builder:
         """image_bias: fp32 [N, Cout] per-image bias replacing cw.bias (ASPP pool branch, see aspp_pool_bias)."""
         assert x.c == cw.cin and y.c == cw.cout, (x.c, cw.cin, y.c, cw.cout, tag)
         self.keep.append(cw)
+        if x.relud:
+            assert flags & RELU_IN, f"{tag}: a post-ReLU buffer read by a conv that does not start with ReLU"
+            flags &= ~RELU_IN
         bias_ptr, bias_stride = _ptr(cw.bias), 0
         extra_reads = ()
         if image_bias is not None:
@@ -329,6 +335,8 @@ class Builder:
     def sepconv_half(self, x: View, y: View, w_dw: torch.Tensor, pw: ConvWeights, k: int, flags: int,
                      tag: str = "sephalf") -> None:
         self.keep.extend((w_dw, pw))
+        if x.relud and (flags & RELU_IN):
+            flags &= ~RELU_IN
         p = x.n * x.h * x.w
         ex = x.buf.element_size()
         # tensor-core path: bf16 NHWC input (TMA halo box), pointwise GEMM on tcgen05
@@ -351,6 +359,7 @@ class Builder:
 
     def pool3x3(self, x: View, y: View, mode: int, stride: int, flags: int = 0, tag: str = "pool3x3") -> None:
         """mode 0 = avg_pool_3x3 (count_include_pad=False), 1 = max_pool_3x3 (operations.py:9-10)."""
+        assert not x.relud, f"{tag}: raw read of a buffer that was stored post-ReLU"
         e = x.buf.element_size()
         meta = dict(kernel="pool3x3", flops=9 * y.n * y.h * y.w * y.c,
                     bytes=(x.n * x.h * x.w + y.n * y.h * y.w * (2 if flags & ACCUMULATE else 1)) * x.c * e)
@@ -359,6 +368,7 @@ class Builder:
 
     def scale(self, x: View, y: View, scale: float, stride: int = 1, flags: int = 0, tag: str = "scale") -> None:
         """y (+)= scale * x[::stride, ::stride]: skip_connect (1.0) / none (0.0) (operations.py:8,11)."""
+        assert not x.relud, f"{tag}: raw read of a buffer that was stored post-ReLU"
         e = x.buf.element_size()
         meta = dict(kernel="scale", flops=y.n * y.h * y.w * y.c,
                     bytes=y.n * y.h * y.w * y.c * e * (3 if flags & ACCUMULATE else 2))
@@ -366,6 +376,7 @@ class Builder:
                    reads=(x, y) if flags & ACCUMULATE else (x,), writes=(y,))
 
     def bilinear(self, x: View, y: View, flags: int = 0, tag: str = "bilinear") -> None:
+        assert not x.relud or (flags & RELU_IN), f"{tag}: raw read of a buffer that was stored post-ReLU"
         meta = dict(kernel="bilinear", flops=8 * y.n * y.h * y.w * y.c,
                     bytes=(x.n * x.h * x.w * x.buf.element_size() + y.n * y.h * y.w * y.buf.element_size()) * x.c)
         self._emit(lib.add_bilinear_fwd, (self._d(x), self._d(y), flags), tag, meta, reads=(x,), writes=(y,))
