@@ -559,21 +559,89 @@ constexpr int TCHP_MAX_STAGES = 16;          // weight ring depth when the taps 
 // their kh halo rows (kh + 1 rows are loaded instead of 2 kh) and EVERY weight tile: for the 5x5s the weight stream
 // (25 x 6 KB per tile through a ring that smem limits to ~36 KB in flight = 37 GB/s per SM, ncu r01u) was the
 // bound, so two tiles per weight tile doubles the useful work per streamed byte.
+// Row quads (p.mt == 4, r02e): rows r, r+dil, r+2dil, r+3dil share kh+3 halo rows and every weight tile (a quarter of
+// the weight stream per output row, (kh+3)/4 halo rows per output row instead of kh).
+// Row-granular halo barriers (r02e): with streamed weights only ONE halo buffer fits next to the ring, and with one
+// full/empty barrier per buffer the next unit's halo load and ReLU sweep could not start before the last MMA of the
+// current unit had retired (load -> sweep -> MMAs strictly in series: 11 us per row pair of a 5x5 at C=40, of which
+// ~3.5 us MMA).  Each halo ROW now has its own full / relu / empty barriers: the issuer releases row ky as soon as the
+// taps of kernel row ky are issued (no later tap reads it), the producer refills it for the next unit and the sweep
+// follows row by row, so load, sweep and MMAs of consecutive units overlap inside a single buffer.
+constexpr int TCHP_MAX_ROWS = 8;             // halo rows per buffer: kh + mt - 1 <= 8
 __device__ __forceinline__ void halo_unit_rows(int u, int units_per_col, int tiles_x, int dil, int mt, int& n, int& tx, int& r0) {
-  // u -> (image n, column strip tx, first output row r0); mt == 2: rows are paired (r0, r0 + dil), r0 = blk*2*dil + off
+  // u -> (image n, column strip tx, first output row r0); mt > 1: rows are grouped (r0, r0 + dil, .., r0 + (mt-1) dil),
+  // r0 = blk*mt*dil + off
   const int per_img = units_per_col * tiles_x;
   n = u / per_img;
   const int r = u - n * per_img;
   const int j = r / tiles_x;
   tx = r - j * tiles_x;
-  r0 = mt == 2 ? (j / dil) * 2 * dil + (j % dil) : j;
+  r0 = mt > 1 ? (j / dil) * mt * dil + (j % dil) : j;
+}
+
+// One (unit, channel chunk) of the persistent halo kernel: every tap of the kh x kw kernel for MT output rows, with
+// streamed or resident weights and row-group halo barriers.  Templated on (MT, KS) so the MT x KS MMAs of a tap are
+// straight-line code: the single issuing thread is the pipeline's metronome, and with the run-time `switch (ksteps)`
+// plus a run-time row loop per tap it spent ~87 cycles per tcgen05.mma that occupies the tensor pipe for 24
+// (ncu r3d: tensor pipe 24 % busy on the 5x5 at C=40, issuer warp sampled in issue code, not in waits).
+struct HaloIssueState { int s2; uint32_t bph; };
+template <int MT, int KS>
+__device__ __forceinline__ void halo_issue_chunk(const TcParams& p, int kh, int G, int hrows, uint32_t bar_ready, uint32_t bar_done,
+                                                 uint32_t hph, uint32_t bar_bfull, uint32_t bar_bempty, HaloIssueState& st,
+                                                 uint32_t tmem_d, uint32_t tmem_cols, uint64_t adesc0, uint64_t bdesc0,
+                                                 uint32_t bidx, uint32_t bidx_step, uint32_t bstep, uint32_t row_step,
+                                                 uint32_t tap_step, uint32_t idesc, uint32_t acc) {
+  int ready = 0;                                // halo row groups [0, ready) of this buffer are loaded (and swept)
+  uint32_t a_row = 0;
+  const int kw = p.taps_w;
+  const bool resident = p.b_resident != 0;
+  for (int ky = 0; ky < kh; ++ky, a_row += row_step) {
+    const int need = G == 1 ? ky + MT : 1;      // kernel row ky reads halo rows ky .. ky + MT - 1
+    if (ready < need) {
+      for (; ready < need; ++ready) mbar_wait(bar_ready + 8 * ready, hph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    uint32_t a_off = a_row;
+    for (int kx = 0; kx < kw; ++kx, a_off += tap_step) {
+      uint64_t bdesc;
+      if (resident) {
+        bdesc = bdesc0 + bidx; bidx += bidx_step;
+      } else {
+        mbar_wait(bar_bfull + 8 * st.s2, st.bph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        bdesc = bdesc0 + (uint32_t)st.s2 * bstep;
+      }
+      const uint64_t a = adesc0 + a_off;
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m)            // output rows share the weight k-slice: halo rows m further down
+          umma_bf16(tmem_d + (uint32_t)m * tmem_cols, a + (uint32_t)m * row_step + 2 * k, bdesc + 2 * k, idesc, k == 0 ? acc : 1u);
+      }
+      acc = 1u;
+      if (!resident) {
+        umma_commit(bar_bempty + 8 * st.s2);
+        if (++st.s2 == p.stages) { st.s2 = 0; st.bph ^= 1; }
+      }
+    }
+    // no later tap reads halo row ky: free it once the MMAs issued so far have retired (the last kernel row frees the
+    // remaining MT - 1 rows too); a whole-buffer group is freed after the last kernel row
+    if (G == 1) {
+      umma_commit(bar_done + 8 * ky);
+      if (ky == kh - 1)
+        for (int j = kh; j < hrows; ++j) umma_commit(bar_done + 8 * j);
+    } else if (ky == kh - 1) {
+      umma_commit(bar_done);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(TCHP_THREADS, 1)
 conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // halo full/empty/relu [2], b_full[s], b_empty[s], tfull[2], tempty[2], bres
-  __shared__ __align__(8) uint64_t bars[6 + 2 * TCHP_MAX_STAGES + 5];
+  // halo full/empty/relu [2][rows], b_full[s], b_empty[s], tfull[2], tempty[2], bres
+  constexpr int HB = 2 * TCHP_MAX_ROWS;
+  __shared__ __align__(8) uint64_t bars[3 * HB + 2 * TCHP_MAX_STAGES + 5];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
 
@@ -582,27 +650,37 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
   const int hrows = kh + (MT - 1);                                         // halo rows per (unit, chunk)
   const int iters = p.taps * p.kchunks;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t halo_bytes = (uint32_t)hrows * p.halo_pitch * 128u;
+  const uint32_t row_bytes = (uint32_t)p.halo_pitch * 128u;
+  const uint32_t halo_bytes = (uint32_t)hrows * row_bytes;
+  // barrier granularity: one group of G halo rows per full/relu/empty barrier.  Two halo buffers already overlap
+  // load / sweep / MMAs of consecutive units, so the buffer is one group (one wait and one commit per chunk, as
+  // before); a single buffer is released row by row (G = 1).
+  const int G = p.halo_bufs >= 2 ? hrows : 1;
+  const int ngroups = hrows / G;
+  const uint32_t group_bytes = (uint32_t)G * row_bytes;
   const uint32_t b_base = smem_base + (uint32_t)p.halo_bufs * halo_bytes;  // ring slots, or the resident image
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool relu_in = (p.flags & ADD_RELU_IN) != 0;
   const uint32_t tmem_cols = (uint32_t)p.tmem_cols;
   const int nbuf = (2u * MT * tmem_cols <= 512u) ? 2 : 1;                  // accumulator sets
 
+  // per-row halo barriers: index (buffer hb, row j) -> 8 * (hb * TCHP_MAX_ROWS + j)
   const uint32_t bar_hfull = smem_u32(&bars[0]);
-  const uint32_t bar_hempty = smem_u32(&bars[2]);
-  const uint32_t bar_hrelu = smem_u32(&bars[4]);
-  const uint32_t bar_bfull = smem_u32(&bars[6]);
-  const uint32_t bar_bempty = smem_u32(&bars[6 + TCHP_MAX_STAGES]);
-  const uint32_t bar_tfull = smem_u32(&bars[6 + 2 * TCHP_MAX_STAGES]);
-  const uint32_t bar_tempty = smem_u32(&bars[6 + 2 * TCHP_MAX_STAGES + 2]);
-  const uint32_t bar_bres = smem_u32(&bars[6 + 2 * TCHP_MAX_STAGES + 4]);
+  const uint32_t bar_hempty = smem_u32(&bars[HB]);
+  const uint32_t bar_hrelu = smem_u32(&bars[2 * HB]);
+  const uint32_t bar_bfull = smem_u32(&bars[3 * HB]);
+  const uint32_t bar_bempty = smem_u32(&bars[3 * HB + TCHP_MAX_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[3 * HB + 2 * TCHP_MAX_STAGES]);
+  const uint32_t bar_tempty = smem_u32(&bars[3 * HB + 2 * TCHP_MAX_STAGES + 2]);
+  const uint32_t bar_bres = smem_u32(&bars[3 * HB + 2 * TCHP_MAX_STAGES + 4]);
 
   if (threadIdx.x == 0) {
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < HB; ++h) {
       mbar_init(bar_hfull + 8 * h, 1);
       mbar_init(bar_hempty + 8 * h, 1);
       mbar_init(bar_hrelu + 8 * h, 128);
+    }
+    for (int h = 0; h < 2; ++h) {
       mbar_init(bar_tfull + 8 * h, 1);
       mbar_init(bar_tempty + 8 * h, 4);
     }
@@ -637,12 +715,15 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
         int n, tx, r0;
         halo_unit_rows(u, upc, p.tiles_x, p.dil, MT, n, tx, r0);
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(bar_hempty + 8 * hb, ph ^ 1);
-          mbar_expect_tx(bar_hfull + 8 * hb, halo_bytes);
           const uint32_t dst = smem_base + hb * halo_bytes;
-          for (int j = 0; j < hrows; ++j)
-            tma_load_4d(dst + j * p.halo_pitch * 128, &map_x, bar_hfull + 8 * hb, kc * TC_BK, tx * TC_BM - p.pad,
-                        r0 - p.pad + j * p.dil, n);
+          const uint32_t bo = 8u * (uint32_t)(hb * TCHP_MAX_ROWS);
+          for (int g = 0; g < ngroups; ++g) {
+            mbar_wait(bar_hempty + bo + 8 * g, ph ^ 1);
+            mbar_expect_tx(bar_hfull + bo + 8 * g, group_bytes);
+            for (int j = g * G; j < (g + 1) * G; ++j)
+              tma_load_4d(dst + j * row_bytes, &map_x, bar_hfull + bo + 8 * g, kc * TC_BK, tx * TC_BM - p.pad,
+                          r0 - p.pad + j * p.dil, n);
+          }
           if (++hb == p.halo_bufs) { hb = 0; ph ^= 1; }
         }
       }
@@ -670,7 +751,8 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
     if (elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       if (p.b_resident) mbar_wait(bar_bres, 0);
-      int hb = 0; uint32_t hph = 0; int s2 = 0; uint32_t bph = 0; int ti = 0;
+      int hb = 0; uint32_t hph = 0; int ti = 0;
+      HaloIssueState ist; ist.s2 = 0; ist.bph = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
         const int ab = nbuf == 2 ? (ti & 1) : 0;
         const uint32_t tph = nbuf == 2 ? ((uint32_t)(ti >> 1) & 1u) : ((uint32_t)ti & 1u);
@@ -678,8 +760,8 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
         for (int kc = 0; kc < p.kchunks; ++kc) {
           const int krem = p.Cin - kc * TC_BK;
           const int ksteps = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
-          mbar_wait((relu_in ? bar_hrelu : bar_hfull) + 8 * hb, hph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t bar_ready = (relu_in ? bar_hrelu : bar_hfull) + 8u * (uint32_t)(hb * TCHP_MAX_ROWS);
+          const uint32_t bar_done = bar_hempty + 8u * (uint32_t)(hb * TCHP_MAX_ROWS);
           // The single issuing thread is the pipeline's metronome: keep its per-MMA instruction count minimal.
           // Descriptors differ only in their 14-bit address field.
           const uint32_t halo = smem_base + hb * halo_bytes;
@@ -691,34 +773,26 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
           const uint32_t bidx_step = (uint32_t)p.kchunks * bstep;
           uint32_t acc = kc > 0 ? 1u : 0u;
           const uint32_t tmem_d = tmem_base + (uint32_t)(ab * MT) * tmem_cols;
-          if (MT == 1 && p.b_resident && issue_chunk_resident_dispatch(kh, p.taps_w, ksteps, tmem_d, adesc0, bdesc0 + bidx, row_step,
-                                                                       tap_step, bidx_step, idesc, acc)) {
-            // fully unrolled instance issued
-          } else {
-            uint32_t a_row = 0;
-            for (int ky = 0; ky < kh; ++ky, a_row += row_step) {
-              uint32_t a_off = a_row;
-              for (int kx = 0; kx < p.taps_w; ++kx, a_off += tap_step) {
-                uint64_t bdesc;
-                if (p.b_resident) {
-                  bdesc = bdesc0 + bidx; bidx += bidx_step;
-                } else {
-                  mbar_wait(bar_bfull + 8 * s2, bph);
-                  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                  bdesc = bdesc0 + (uint32_t)s2 * bstep;
-                }
-                issue_tap_ring_dispatch(ksteps, tmem_d, adesc0 + a_off, bdesc, idesc, acc);
-                if (MT == 2)       // second output row: same weights, halo rows one further down
-                  issue_tap_ring_dispatch(ksteps, tmem_d + tmem_cols, adesc0 + a_off + row_step, bdesc, idesc, acc);
-                acc = 1u;
-                if (!p.b_resident) {
-                  umma_commit(bar_bempty + 8 * s2);
-                  if (++s2 == p.stages) { s2 = 0; bph ^= 1; }
-                }
-              }
-            }
+          const bool unrolled = MT == 1 && p.b_resident && kh == 3 && p.taps_w == 3;
+          if (unrolled) {
+            for (int g = 0; g < ngroups; ++g) mbar_wait(bar_ready + 8 * g, hph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
-          umma_commit(bar_hempty + 8 * hb);     // halo buffer free once this chunk's MMAs have read it
+          if (unrolled && issue_chunk_resident_dispatch(kh, p.taps_w, ksteps, tmem_d, adesc0, bdesc0 + bidx, row_step,
+                                                        tap_step, bidx_step, idesc, acc)) {
+            // fully unrolled instance issued
+            for (int g = 0; g < ngroups; ++g) umma_commit(bar_done + 8 * g);
+          } else {
+#define HIC(MT_, KS_) case MT_ * 8 + KS_: halo_issue_chunk<MT_, KS_>(p, kh, G, hrows, bar_ready, bar_done, hph, bar_bfull, bar_bempty, \
+                                                          ist, tmem_d, tmem_cols, adesc0, bdesc0, bidx, bidx_step, bstep, row_step, tap_step, idesc, acc); break;
+            switch (MT * 8 + ksteps) {
+              HIC(1, 1) HIC(1, 2) HIC(1, 3) HIC(1, 4)
+              HIC(2, 1) HIC(2, 2) HIC(2, 3) HIC(2, 4)
+              HIC(4, 1) HIC(4, 2) HIC(4, 3) HIC(4, 4)
+              default: break;
+            }
+#undef HIC
+          }
           if (++hb == p.halo_bufs) { hb = 0; hph ^= 1; }
         }
         umma_commit(bar_tfull + 8 * ab);
@@ -731,9 +805,12 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
       int hb = 0; uint32_t ph = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x)
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(bar_hfull + 8 * hb, ph);
-          relu_sweep(smem_base + hb * halo_bytes, halo_bytes, et);
-          mbar_arrive(bar_hrelu + 8 * hb);
+          const uint32_t bo = 8u * (uint32_t)(hb * TCHP_MAX_ROWS);
+          for (int g = 0; g < ngroups; ++g) {
+            mbar_wait(bar_hfull + bo + 8 * g, ph);
+            relu_sweep(smem_base + hb * halo_bytes + g * group_bytes, group_bytes, et);
+            mbar_arrive(bar_hrelu + bo + 8 * g);
+          }
           if (++hb == p.halo_bufs) { hb = 0; ph ^= 1; }
         }
     }
@@ -778,6 +855,7 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
 // ---- host side -----------------------------------------------------------------------------------
 int g_conv_cluster = 1;             // 1 = cluster-of-2 weight multicast for the N_pad = 256 convs (mode bit 8 clears)
 int g_halo_pairs = 1;               // 1 = row pairs in the persistent halo kernel (mode bit 7 clears)
+int g_halo_quads = 1;               // 1 = row quads for the streamed-weight 5x5s (mode bit 9 clears)
 int g_conv_mt2 = 1;                 // 1 = two pixel tiles per weight tile for the weight-heavy convs (mode bit 6 clears)
 int g_halo_stream_persistent = 0;   // 1 = use the persistent halo kernel also when the weights stream through a ring (tuning)
 int g_persistent = 1;  // 1 = persistent warp-specialised kernel for the non-halo path (default), 0 = one tile per CTA
@@ -964,8 +1042,17 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
     // or the map is tall enough that pairing leaves every SM busy
     const bool resident1 = 2 * (size_t)kh * p.halo_pitch * 128u + (size_t)iters * p.b_bytes + 1024 <= budget;
     q.mt = (g_halo_pairs && 2 * p.tmem_cols <= 512 && (!resident1 || grid >= 4ll * sms)) ? 2 : 1;
+    // row quads when the weights have to stream anyway (5x5s): a quarter of the weight stream per output row, as long
+    // as the quads still cover most of the SMs, the quad's halo leaves room for a >= 8-deep weight ring and four
+    // accumulators fit in TMEM
+    if (g_halo_pairs && g_halo_quads && q.mt == 2 && kh + 3 <= TCHP_MAX_ROWS && 4 * p.tmem_cols <= 512 &&
+        2 * (size_t)(kh + 1) * p.halo_pitch * 128u + (size_t)iters * p.b_bytes + 1024 > budget &&
+        (size_t)(kh + 3) * p.halo_pitch * 128u + 8 * (size_t)p.b_bytes + 1024 <= budget &&
+        (long long)ceil_div(y->h, 4 * dil) * dil * p.tiles_x * y->n >= (long long)sms * 4 / 5)
+      q.mt = 4;
+    if (kh + q.mt - 1 > TCHP_MAX_ROWS) return ADD_ERR_UNSUPPORTED;
     const size_t hbytes = (size_t)(kh + q.mt - 1) * p.halo_pitch * 128u;
-    const int upc = q.mt == 2 ? ceil_div(y->h, 2 * dil) * dil : y->h;             // units per column strip
+    const int upc = q.mt > 1 ? ceil_div(y->h, q.mt * dil) * dil : y->h;           // units per column strip
     q.tiles_y = upc;
     const long long units = (long long)upc * p.tiles_x * y->n;
     q.n_tiles = (int)units;
@@ -986,7 +1073,7 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
       q.stages = (int)sb;
       psmem = (size_t)q.halo_bufs * hbytes + (size_t)(sb > 0 ? sb : 0) * p.b_bytes + 1024;
     }
-    if (ok && (q.b_resident || q.mt == 2 || g_halo_stream_persistent)) {
+    if (ok && (q.b_resident || q.mt >= 2 || g_halo_stream_persistent)) {
       static std::once_flag hponce;
       std::call_once(hponce, [] {
         cudaFuncSetAttribute(conv2d_tc_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
@@ -1009,6 +1096,7 @@ extern "C" int add_conv2d_tc_set_halo_mode(int mode) {
   g_persistent = (mode & 16) ? 0 : 1;                 // bit 4 set = one tile per CTA (A/B runs)
   g_conv_cluster = (mode & 256) ? 0 : 1;              // bit 8 set = no clusters / multicast
   g_halo_pairs = (mode & 128) ? 0 : 1;                // bit 7 set = no row pairs in the persistent halo kernel
+  g_halo_quads = (mode & 512) ? 0 : 1;                // bit 9 set = no row quads (pairs only)
   g_conv_mt2 = (mode & 64) ? 0 : 1;                   // bit 6 set = one pixel tile per weight tile everywhere
   g_halo_stream_persistent = (mode & 32) ? 1 : 0;     // bit 5 set = persistent halo kernel with streamed weights
   mode &= 15;

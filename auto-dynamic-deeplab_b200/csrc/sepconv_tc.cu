@@ -318,13 +318,21 @@ sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, con
     stage_bias(bias_s, p.e, threadIdx.x, 128);
     asm volatile("bar.sync 1, 128;" ::: "memory");
     pdl_wait();
+    const bool pre_ok = epilogue_prefetchable(p.e);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1; const uint32_t ph = (uint32_t)(it >> 1) & 1u;
       const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
       const int ty = r / p.e.tiles_x, tx = r - ty * p.e.tiles_x;
-      mbar_wait_relaxed(bar_tfull + 8 * b, ph);
-      epilogue_store(p.e, tmem_base + b * tmem_cols, bias_s, warp, lane, n, ty * SC_TH, tx * SC_TW);
+      if (pre_ok) {         // += : this pixel's old y words are fetched while the depthwise / MMA of the tile still run
+        uint4 old[EPI_PRE_MAX];
+        epilogue_prefetch_old(p.e, warp, lane, n, ty * SC_TH, tx * SC_TW, old);
+        mbar_wait_relaxed(bar_tfull + 8 * b, ph);
+        epilogue_store(p.e, tmem_base + b * tmem_cols, bias_s, warp, lane, n, ty * SC_TH, tx * SC_TW, &old);
+      } else {
+        mbar_wait_relaxed(bar_tfull + 8 * b, ph);
+        epilogue_store(p.e, tmem_base + b * tmem_cols, bias_s, warp, lane, n, ty * SC_TH, tx * SC_TW);
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * b);

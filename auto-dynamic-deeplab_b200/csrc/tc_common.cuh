@@ -221,10 +221,73 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
   }
 }
 
+// ---- epilogue ------------------------------------------------------------------------------------
+// One 16-channel chunk of one pixel, bf16 output: (+= old y) -> round -> ReLU -> 16-byte stores.  `have_old`: the
+// caller already holds the old y words of the two 8-channel groups (prefetched), else they are loaded here.
+__device__ __forceinline__ void epi_chunk_bf16(const TcParams& p, float (&f)[16], bf16* dst, int c0, bool accum, bool relu_out,
+                                               bool have_old, const uint4& o0, const uint4& o1) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    if (c0 + 8 * g + 8 <= p.Cout) {
+      if (accum) {
+        const uint4 old = have_old ? (g == 0 ? o0 : o1) : *reinterpret_cast<const uint4*>(dst + 8 * g);
+        const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[8 * g + 2 * j] += __uint_as_float(ow[j] << 16);
+          f[8 * g + 2 * j + 1] += __uint_as_float(ow[j] & 0xffff0000u);
+        }
+      }
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * g + 2 * j], f[8 * g + 2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        // ReLU on the rounded pair: rounding is monotonic and keeps the sign, so this equals round(relu(x))
+        if (relu_out) asm("max.bf16x2 %0, %0, %1;" : "+r"(pk[j]) : "r"(0u));
+      }
+      *reinterpret_cast<uint4*>(dst + 8 * g) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    } else if (c0 + 8 * g < p.Cout) {
+      for (int j = 8 * g; j < 8 * g + 8; ++j)
+        if (c0 + j < p.Cout) {
+          float o = f[j];
+          if (accum) o += __bfloat162float(dst[j]);
+          if (relu_out) o = fmaxf(o, 0.f);
+          dst[j] = __float2bfloat16_rn(o);
+        }
+    }
+  }
+}
+
+// Accumulate-into-slice (`ADD_ACCUMULATE`, the cell's node sum) needs the old y values.  Loaded inside the chunk
+// loop they cost one exposed global-memory round trip PER 16-channel chunk (launch table r02d: a SepConv half with
+// += took 29 us against 15 us without).  For the narrow outputs of the cell ops (Cout <= 80, bf16) all of a pixel's
+// old words are instead fetched up front in one batch — before the wait on the accumulator barrier where the caller
+// can (epilogue_prefetch_old), else at the top of epilogue_store — so the round trip is paid once and overlaps the MMA.
+constexpr int EPI_PRE_MAX = 10;   // 8-channel (16-byte) groups held in registers: Cout <= 80
+__device__ __forceinline__ bool epilogue_prefetchable(const TcParams& p) {
+  return (p.flags & ADD_ACCUMULATE) && !p.y_is_f32 && p.Cout <= 8 * EPI_PRE_MAX && !(p.flags & 0x100u);
+}
+__device__ __forceinline__ void epilogue_prefetch_old(const TcParams& p, int warp, int lane, int n, int y0, int x0,
+                                                      uint4 (&old)[EPI_PRE_MAX]) {
+  const int BW = 1 << p.bw_log2;
+  const int r = (warp & 3) * 32 + lane;
+  const int oy = y0 + (r >> p.bw_log2), ox = x0 + (r & (BW - 1));
+  const bool valid = (oy < p.Ho) && (ox < p.Wo);
+  const size_t pix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
+  const bf16* src = static_cast<const bf16*>(p.y) + pix * p.ys;
+#pragma unroll
+  for (int g = 0; g < EPI_PRE_MAX; ++g) {
+    if (valid && 8 * g + 8 <= p.Cout) old[g] = *reinterpret_cast<const uint4*>(src + 8 * g);
+    else old[g] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // TMEM accumulator -> +bias -> (+= y) -> ReLU -> bf16/fp32 stores.  Called by the four epilogue warps
-// after the accumulator-complete barrier.  bias_s: shared-memory bias (stage_bias).
+// after the accumulator-complete barrier.  bias_s: shared-memory bias (stage_bias).  `pre`: old y words from
+// epilogue_prefetch_old for this very tile, or nullptr.
 __device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_base, const float* bias_s, int warp, int lane,
-                                               int n, int y0, int x0) {
+                                               int n, int y0, int x0, const uint4 (*pre)[EPI_PRE_MAX] = nullptr) {
   const int BW = 1 << p.bw_log2;
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int q = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -233,6 +296,33 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_
   const bool valid = (oy < p.Ho) && (ox < p.Wo);
   const size_t pix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
   const bool relu_out = p.flags & ADD_RELU_OUT, accum = p.flags & ADD_ACCUMULATE;
+  if (epilogue_prefetchable(p)) {
+    // narrow accumulate path: old words in registers, chunk loop unrolled so they are indexed statically
+    uint4 old_local[EPI_PRE_MAX];
+    if (!pre) epilogue_prefetch_old(p, warp, lane, n, y0, x0, old_local);
+    const uint4* old = pre ? &(*pre)[0] : &old_local[0];
+    bf16* base = static_cast<bf16*>(p.y) + pix * p.ys;
+#pragma unroll
+    for (int ci = 0; ci < EPI_PRE_MAX / 2; ++ci) {
+      const int c0 = 16 * ci;
+      if (c0 < p.n_pad) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
+            f[4 * j] = __uint_as_float(v[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+          }
+          epi_chunk_bf16(p, f, base + c0, c0, true, relu_out, true, old[2 * ci], old[2 * ci + 1]);
+        }
+      }
+    }
+    return;
+  }
   for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
     uint32_t v[16];
     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -265,38 +355,8 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, uint32_t tmem_
         }
       }
     } else {
-      bf16* dst = static_cast<bf16*>(p.y) + pix * p.ys + c0;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (c0 + 8 * g + 8 <= p.Cout) {
-          if (accum) {
-            const uint4 old = *reinterpret_cast<const uint4*>(dst + 8 * g);
-            const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              f[8 * g + 2 * j] += __uint_as_float(ow[j] << 16);
-              f[8 * g + 2 * j + 1] += __uint_as_float(ow[j] & 0xffff0000u);
-            }
-          }
-          uint32_t pk[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * g + 2 * j], f[8 * g + 2 * j + 1]);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            // ReLU on the rounded pair: rounding is monotonic and keeps the sign, so this equals round(relu(x))
-            if (relu_out) asm("max.bf16x2 %0, %0, %1;" : "+r"(pk[j]) : "r"(0u));
-          }
-          *reinterpret_cast<uint4*>(dst + 8 * g) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        } else if (c0 + 8 * g < p.Cout) {
-          for (int j = 8 * g; j < 8 * g + 8; ++j)
-            if (c0 + j < p.Cout) {
-              float o = f[j];
-              if (accum) o += __bfloat162float(dst[j]);
-              if (relu_out) o = fmaxf(o, 0.f);
-              dst[j] = __float2bfloat16_rn(o);
-            }
-        }
-      }
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      epi_chunk_bf16(p, f, static_cast<bf16*>(p.y) + pix * p.ys + c0, c0, accum, relu_out, false, z, z);
     }
   }
 }

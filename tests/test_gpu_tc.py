@@ -82,6 +82,11 @@ CASES = [
     (40, 40, 3, 1, 2, 2, 63, 127, RELU_IN | ACCUMULATE),
     (64, 64, 3, 1, 1, 1, 131, 200, RELU_OUT),
     (80, 80, 5, 1, 4, 2, 63, 127, 0),
+    # row quads (r, r + dil, r + 2 dil, r + 3 dil) for the streamed-weight 5x5s once the quads cover the SMs; per-row halo
+    # barriers; heights that are not a multiple of 4 * dil; two channel chunks with a single accumulator set
+    (40, 40, 5, 1, 4, 2, 131, 300, RELU_IN | ACCUMULATE),
+    (80, 80, 5, 1, 4, 2, 250, 128, RELU_IN),
+    (40, 40, 5, 1, 2, 1, 243, 256, 0),
 ]
 
 
