@@ -55,6 +55,7 @@ _SIGS = {
     "add_sepconv_half_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_void_p]),
     "add_sepconv_half_tc_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_void_p]),
     "add_sepconv_tc_set_mode": (c_int, [c_int]),
+    "add_bilinear_set_mode": (c_int, [c_int]),
     "add_pool3x3_fwd": (c_int, [TP, TP, c_int, c_int, c_uint32, c_void_p]),
     "add_scale_fwd": (c_int, [TP, TP, c_float, c_int, c_uint32, c_void_p]),
     "add_bilinear_fwd": (c_int, [TP, TP, c_uint32, c_void_p]),

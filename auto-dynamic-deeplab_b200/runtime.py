@@ -180,9 +180,11 @@ if _os.environ.get("ADD_GRID_PCT"):
     check(lib.add_set_persistent_grid_pct(int(_os.environ["ADD_GRID_PCT"])), "set_persistent_grid_pct")
 if _os.environ.get("ADD_TC_HALO_MODE"):
     set_tc_halo_mode(int(_os.environ["ADD_TC_HALO_MODE"]))
+if _os.environ.get("ADD_SEPCONV_MODE"):
+    check(lib.add_sepconv_tc_set_mode(int(_os.environ["ADD_SEPCONV_MODE"])), "sepconv_tc_set_mode")
 
 
-_GRAPH_STREAMS = {"n": int(_os.environ.get("ADD_GRAPH_STREAMS", "4"))}
+_GRAPH_STREAMS = {"n": int(_os.environ.get("ADD_GRAPH_STREAMS", "2"))}   # r3: 2 streams 822 img/s, 3: 808, 4: 800, 1: 779
 
 
 def graph_streams() -> int:

@@ -133,6 +133,9 @@ int add_scale_fwd(const add_tensor_t* x, const add_tensor_t* y, float scale, int
 
 /* ---- bilinear resize, align_corners=False (F.interpolate: ADD.py:76,84,89,317; decoder.py:24) */
 int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, uint32_t flags, void* stream);
+/* add_bilinear_fwd scheduling: 1 = exact x2 / x4 bf16 upscales use a kernel whose threads own the S x S output block
+ * that shares four source pixels (default; results identical to the generic kernel), 0 = generic kernel everywhere. */
+int add_bilinear_set_mode(int mode);
 
 /* ---- batch compaction for per-image early exit (ADD.py:421-432 applied to a batch): whole-image
  * slabs dst[j] = src[idx[j]], j < count; idx lives on the device so the launch is graph-replayable. */

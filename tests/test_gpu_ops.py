@@ -85,6 +85,41 @@ def test_bilinear_matches_numpy_oracle(hw_in, hw_out):
     assert np.abs(got - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("scale", [2, 4])
+@pytest.mark.parametrize("hw_in", [(2, 2), (5, 9), (16, 33)])
+@pytest.mark.parametrize("flags", [0, 1, 3], ids=["plain", "relu_in", "relu_in_out"])
+def test_bilinear_integer_upscale_equals_generic_kernel(scale, hw_in, flags):
+    """bf16 x2 / x4 upscales take the shared-source block kernel: bit-identical to the generic per-pixel kernel
+    (same source indices, weights and expression), channel-slice input and output views left untouched outside."""
+    from add_b200._lib import lib as _lib
+    from add_b200.runtime import Builder, View
+    g = torch.Generator().manual_seed(11)
+    h, w = hw_in
+    c = 40
+    x_buf = torch.randn(2, h, w, c + 16, generator=g).to(torch.bfloat16).to(DEV)
+    outs = []
+    for mode in (1, 0):
+        assert _lib.add_bilinear_set_mode(mode) == 0
+        try:
+            y_buf = torch.full((2, h * scale, w * scale, c + 24), 7.0, dtype=torch.bfloat16, device=DEV)
+            b = Builder(torch.device(DEV), torch.bfloat16)
+            b.bilinear(View(x_buf, 8, c), View(y_buf, 16, c), flags)
+            torch.cuda.synchronize()
+            outs.append(y_buf)
+        finally:
+            _lib.add_bilinear_set_mode(1)
+    assert torch.equal(outs[0], outs[1])
+    assert bool((outs[0][..., :16] == 7).all()) and bool((outs[0][..., 16 + c:] == 7).all())
+    xin = x_buf[..., 8:8 + c].float().permute(0, 3, 1, 2)
+    if flags & 1:
+        xin = torch.relu(xin)
+    ref = torch.nn.functional.interpolate(xin, scale_factor=scale, mode="bilinear", align_corners=False)
+    if flags & 2:
+        ref = torch.relu(ref)
+    got = outs[0][..., 16:16 + c].float().permute(0, 3, 1, 2)
+    assert float((got - ref).abs().max()) <= 2 ** -7 * max(1.0, float(ref.abs().max()))
+
+
 def test_conv_small_vs_numpy_direct():
     """Independent of ATen: fp64-accumulated direct convolution (dilated, strided, negative pad)."""
     g = torch.Generator().manual_seed(10)

@@ -176,6 +176,10 @@ SEP_CASES = [
     (40, 40, 3, 131, 250, RELU_IN | RELU_OUT),
     (80, 80, 3, 90, 127, RELU_IN | RELU_OUT),
     (80, 80, 5, 70, 130, ACCUMULATE),
+    # many tiles per CTA: A / TMEM / halo rings wrapping several times
+    (40, 40, 3, 260, 500, RELU_IN | ACCUMULATE),
+    (40, 40, 5, 250, 400, RELU_OUT),
+    (80, 80, 3, 200, 260, 0),
 ]
 
 
