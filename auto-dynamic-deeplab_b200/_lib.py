@@ -56,6 +56,11 @@ _SIGS = {
     "add_sepconv_half_tc_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_void_p]),
     "add_sepconv_tc_set_mode": (c_int, [c_int]),
     "add_bilinear_set_mode": (c_int, [c_int]),
+    "add_bn_stats_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "add_bn_stats_fwd": (c_int, [TP, c_void_p, c_void_p, c_int64, c_void_p]),
+    "add_bn_finalize": (c_int, [c_void_p, c_void_p, c_float, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    "add_bn_apply_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
     "add_pool3x3_fwd": (c_int, [TP, TP, c_int, c_int, c_uint32, c_void_p]),
     "add_scale_fwd": (c_int, [TP, TP, c_float, c_int, c_uint32, c_void_p]),
     "add_bilinear_fwd": (c_int, [TP, TP, c_uint32, c_void_p]),

@@ -20,10 +20,7 @@ from .runtime import Builder, ConvWeights, View, RELU_IN, RELU_OUT, ACCUMULATE, 
 from ._lib import lib, check
 
 
-class SynchronizedBatchNorm2d(nn.BatchNorm2d):
-    """Parameter/statistics holder with the reference's class name
-    (modeling/sync_batchnorm/batchnorm.py:180).  In eval mode — the only mode on this path — it is
-    exactly `F.batch_norm` with running stats (batchnorm.py:50-53) and is folded into the conv."""
+from .sync_batchnorm import SynchronizedBatchNorm2d  # noqa: E402  (reference name, modeling/sync_batchnorm/batchnorm.py:180)
 
 
 class AddModule(nn.Module):

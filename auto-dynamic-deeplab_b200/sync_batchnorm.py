@@ -1,0 +1,102 @@
+"""SynchronizedBatchNorm2d — drop-in for modeling/sync_batchnorm/batchnorm.py:180 with a B200 forward.
+
+Eval mode inside the ADD plans never reaches this module's `forward`: BN is folded into the neighbouring conv.
+Called on its own (and in training mode) it runs three libadd_b200 kernels:
+
+    add_bn_stats_fwd   per-channel [sum, square-sum] of this rank's shard        (batchnorm.py:59-61)
+    all_reduce         ONE collective of the packed [sum | ssum | count] vector  (batchnorm.py:90-111: the reference
+                       does ReduceAddCoalesced + Broadcast between DataParallel threads; with one process per GPU it
+                       is a single NCCL all-reduce over NVLink per BN layer — gloo in the CPU tests)
+    add_bn_finalize    mean, inv_std, running-statistics update                  (batchnorm.py:113-125)
+    add_bn_apply_fwd   y = (x - mean) * (inv_std * weight) + bias                (batchnorm.py:68-75)
+
+Semantics follow the reference exactly: with a process group of more than one rank (or `force_sync=True`) the
+statistics are synchronised and inv_std = clamp(var, eps)^-1/2; otherwise it is `F.batch_norm` with local batch
+statistics (inv_std = (var + eps)^-1/2) — what the reference does on one device and under DDP.
+No autograd: backward is the remaining part of the training row."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from ._lib import lib, check, AddTensor, ADD_F32, ADD_BF16, RELU_OUT
+
+
+def pack_stats(sums: torch.Tensor, count: int) -> torch.Tensor:
+    """[sum(C) | ssum(C)] + element count -> the fp32 vector that is all-reduced (2C+1 floats)."""
+    out = torch.empty(sums.numel() + 1, dtype=torch.float32, device=sums.device)
+    out[:-1] = sums
+    out[-1] = float(count)
+    return out
+
+
+def reduce_stats(packed: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Sum the packed statistics over all ranks, in place (no-op without an initialised group of > 1 ranks)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed
+
+
+def _desc(t: torch.Tensor) -> AddTensor:
+    """NHWC view descriptor of a logical-NCHW channels_last tensor."""
+    n, c, h, w = t.shape
+    return AddTensor(t.data_ptr(), n, h, w, c, c, ADD_BF16 if t.dtype == torch.bfloat16 else ADD_F32)
+
+
+class SynchronizedBatchNorm2d(nn.BatchNorm2d):
+    """Same constructor, parameters and state_dict keys as the reference class (a `_BatchNorm` subclass)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, process_group=None, force_sync=False):
+        super().__init__(num_features, eps=eps, momentum=momentum, affine=affine)
+        self.process_group = process_group
+        self.force_sync = force_sync        # take the synchronised formulas even with one rank (tests)
+
+    def _synced(self) -> bool:
+        return self.force_sync or (dist.is_available() and dist.is_initialized() and
+                                   dist.get_world_size(self.process_group) > 1)
+
+    def forward(self, x: torch.Tensor, relu: bool = False) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("add_b200 runs on CUDA tensors only (no CPU fallback)")
+        if x.dim() != 4 or x.shape[1] != self.num_features:
+            raise ValueError(f"expected [N, {self.num_features}, H, W], got {tuple(x.shape)}")
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.contiguous(memory_format=torch.channels_last)          # zero copy when already NHWC
+        n, c, h, w = x.shape
+        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        xd = _desc(x)
+        w_ptr = self.weight.data_ptr() if self.affine else None
+        b_ptr = self.bias.data_ptr() if self.affine else None
+        stats = torch.empty(2 * c, dtype=torch.float32, device=x.device)     # [mean | inv_std]
+        mean, inv_std = stats[:c], stats[c:]
+        if self.training:
+            ws_bytes = lib.add_bn_stats_workspace_bytes(n, h, w, c)
+            check(ws_bytes if ws_bytes < 0 else 0, "bn_stats_workspace_bytes")
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            packed = torch.empty(2 * c + 1, dtype=torch.float32, device=x.device)
+            check(lib.add_bn_stats_fwd(ctypes.byref(xd), packed.data_ptr(), ws.data_ptr(), ws_bytes, stream), "bn_stats")
+            packed[-1] = float(n * h * w)
+            sync = self._synced()
+            if sync:
+                reduce_stats(packed, self.process_group)
+            if self.num_batches_tracked is not None:
+                self.num_batches_tracked += 1
+            momentum = self.momentum if self.momentum is not None else 1.0 / float(self.num_batches_tracked)
+            rm = self.running_mean.data_ptr() if self.track_running_stats else None
+            rv = self.running_var.data_ptr() if self.track_running_stats else None
+            check(lib.add_bn_finalize(packed.data_ptr(), packed.data_ptr() + 8 * c, 0.0, c, float(self.eps), float(momentum),
+                                      1 if sync else 0, rm, rv, mean.data_ptr(), inv_std.data_ptr(), stream), "bn_finalize")
+        else:
+            # eval: F.batch_norm with the running statistics (batchnorm.py:50-53); C-length vectors, plumbing
+            mean.copy_(self.running_mean)
+            torch.rsqrt(self.running_var + self.eps, out=inv_std)
+        y = torch.empty_like(x)                                      # keeps channels_last
+        yd = _desc(y)
+        check(lib.add_bn_apply_fwd(ctypes.byref(xd), ctypes.byref(yd), mean.data_ptr(), inv_std.data_ptr(), w_ptr, b_ptr,
+                                   RELU_OUT if relu else 0, stream), "bn_apply")
+        return y

@@ -37,7 +37,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_cuda"],
+                    help="b200 = this repo; reference = the reference's CPU path (oracle port); torch_cuda = informational "
+                         "stock PyTorch/cuDNN comparator on cuda:0")
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--width", type=int, default=2048)
@@ -201,6 +203,61 @@ def main_reference(a):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main_torch_cuda(a):
+    """Informational comparator ("also report stock PyTorch-CUDA images/sec as the GPU reference to beat"):
+    the oracle restatement of ADD.dynamic_inference — plain torch.nn.functional calls, i.e. the cuDNN / ATen kernels
+    the reference itself would run on this GPU — per image like eval.py:195-221 (batch 1, host gate decision, argmax,
+    bincount confusion matrix), alternating early-exit / full-depth images.  Two passes: fp32 (TF32 off) and bf16
+    weights + activations, both channels_last.  None of libadd_b200 is on this path."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import add_b200
+    orc, sd, edm_sd, arch = cpu_reference_setup(a)
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    x, gt = add_b200.synthetic_batch(2, a.height, a.width)
+    res = {}
+    for name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        def cast(v):
+            v = v.to(dev)
+            if v.is_floating_point():
+                v = v.to(dt)
+                if v.dim() == 4:
+                    v = v.contiguous(memory_format=torch.channels_last)
+            return v
+        sdd = {k: cast(v) for k, v in sd.items()}
+        edd = {k: cast(v) for k, v in edm_sd.items()}
+        xd = [cast(x[j:j + 1]) for j in range(2)]
+        gd = [gt[j:j + 1].to(dev) for j in range(2)]
+
+        def one(j, thr):
+            with torch.no_grad():
+                y, ee, conf = orc.add_dynamic_inference(sdd, arch, xd[j], thr, 'edm', edd)
+                pred = torch.argmax(y, 1)
+                m = (gd[j] >= 0) & (gd[j] < 19)
+                return torch.bincount(19 * gd[j][m] + pred[m], minlength=361).view(19, 19)
+        for s_ in range(max(a.warmup, 3) * 2):
+            one(s_ % 2, 1e30 if s_ % 2 == 0 else -1e30)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_img = 2 * max(a.steps, 2)
+        for s_ in range(n_img):
+            one(s_ % 2, 1e30 if s_ % 2 == 0 else -1e30)
+        torch.cuda.synchronize()
+        res[name] = n_img / (time.perf_counter() - t0)
+    line = {"metric": METRIC, "value": res["bf16"], "unit": UNIT, "impl": "torch_cuda", "n_gpus": 1, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+            "config": dict(workload_name(a), note="stock PyTorch (cuDNN/ATen) eager on cuda:0, batch 1 per call as in eval.py:195-221, "
+                           "channels_last, alternating early-exit / full-depth images"),
+            "images_per_s": res, "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(), "gpu_launches": 0}
     print(json.dumps(line))
     return 0
 
@@ -386,4 +443,5 @@ def main_b200(a):
 
 if __name__ == "__main__":
     args = parse()
-    sys.exit(main_reference(args) if args.impl == "reference" else main_b200(args))
+    sys.exit(main_reference(args) if args.impl == "reference" else main_torch_cuda(args) if args.impl == "torch_cuda"
+             else main_b200(args))

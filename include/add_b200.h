@@ -131,6 +131,28 @@ int add_pool3x3_fwd(const add_tensor_t* x, const add_tensor_t* y, int mode, int 
  * none / Zero (scale 0: IEEE x*0 like the reference's x.mul(0.), operations.py:74-83). */
 int add_scale_fwd(const add_tensor_t* x, const add_tensor_t* y, float scale, int stride, uint32_t flags, void* stream);
 
+/* ---- training-mode BatchNorm forward -------------------------------------------------------
+ * The reference's SynchronizedBatchNorm (modeling/sync_batchnorm/batchnorm.py:48-78, 113-125) splits a training
+ * forward into per-device [sum, square-sum] (:59-61), one reduce + broadcast over the devices (:90-111), the
+ * mean / inv_std / running-statistics update (:113-125) and the normalisation (:68-75).  Same split here; the reduce is
+ * ONE all-reduce of the packed [sum(C) | ssum(C) | count] vector done by the host side with torch.distributed.
+ *
+ * add_bn_stats_fwd: sums[0..C) = per-channel sum of x over (n,h,w), sums[C..2C) = sum of x^2 (fp32, deterministic
+ *   two-stage reduction).  workspace >= add_bn_stats_workspace_bytes(n,h,w,c).  C % 4 == 0, C <= 1024.
+ * add_bn_finalize: from (possibly all-reduced) sums and the element count (count_dev: device pointer to the fp32 count,
+ *   e.g. the all-reduced sums + 2C; NULL -> `count`): mean = sum/n, sumvar = ssum - sum*mean,
+ *   running_mean = (1-m) running_mean + m mean, running_var = (1-m) running_var + m sumvar/(n-1)   (either may be NULL),
+ *   inv_std = clamp(sumvar/n, eps)^-1/2 when sync != 0 (batchnorm.py:125), (sumvar/n + eps)^-1/2 when sync == 0
+ *   (F.batch_norm, the :50-53 path the reference takes on one device or under DDP).
+ * add_bn_apply_fwd: y = (x - mean) * (inv_std * weight) + bias [ReLU with ADD_RELU_OUT]; weight / bias may be NULL
+ *   (affine=False); with mean = running_mean and inv_std = (running_var + eps)^-1/2 it is eval-mode F.batch_norm. */
+int64_t add_bn_stats_workspace_bytes(int n, int h, int w, int c);
+int add_bn_stats_fwd(const add_tensor_t* x, float* sums, void* workspace, int64_t workspace_bytes, void* stream);
+int add_bn_finalize(const float* sums, const float* count_dev, float count, int c, float eps, float momentum, int sync,
+                    float* running_mean, float* running_var, float* mean, float* inv_std, void* stream);
+int add_bn_apply_fwd(const add_tensor_t* x, const add_tensor_t* y, const float* mean, const float* inv_std,
+                     const float* weight, const float* bias, uint32_t flags, void* stream);
+
 /* ---- bilinear resize, align_corners=False (F.interpolate: ADD.py:76,84,89,317; decoder.py:24) */
 int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, uint32_t flags, void* stream);
 /* add_bilinear_fwd scheduling: 1 = exact x2 / x4 bf16 upscales use a kernel whose threads own the S x S output block

@@ -569,6 +569,44 @@ def np_conv2d_nchw(x: np.ndarray, w: np.ndarray, stride=1, pad=0, dil=1, groups=
 # synthetic weights / inputs shared by tests, smoke() and bench.py
 # --------------------------------------------------------------------------------------
 
+def sync_batchnorm_train(shards: Sequence[torch.Tensor], weight: Optional[torch.Tensor], bias: Optional[torch.Tensor],
+                         running_mean: torch.Tensor, running_var: torch.Tensor, momentum: float = 0.1,
+                         eps: float = BN_EPS, sync: bool = True):
+    """Training-mode forward of SynchronizedBatchNorm2d over the per-device shards of one step.
+
+    sync=True : modeling/sync_batchnorm/batchnorm.py:55-75 (per-device sum / square-sum, :59-61), :90-111 (reduce over
+                the devices, sizes added up) and :113-125 (`_compute_mean_std`: mean = sum/n, sumvar = ssum - sum*mean,
+                running stats from the UNBIASED variance, inv_std = clamp(sumvar/n, eps)^-1/2), output :68-75.
+    sync=False: the :50-53 path (one device, or DDP where the replication callback never fires — SURVEY §2.2):
+                F.batch_norm(training=True) on each shard independently; running stats updated shard after shard.
+    Returns (outputs, new_running_mean, new_running_var, mean, inv_std); mean / inv_std are None for sync=False."""
+    rm, rv = running_mean.clone(), running_var.clone()
+    if not sync:
+        outs = [F.batch_norm(x, rm, rv, weight, bias, True, momentum, eps) for x in shards]
+        return outs, rm, rv, None, None
+    C = shards[0].shape[1]
+    flat = [x.reshape(x.shape[0], C, -1) for x in shards]
+    size = sum(f.shape[0] * f.shape[2] for f in flat)
+    sum_ = sum(f.sum(dim=0).sum(dim=-1) for f in flat)
+    ssum = sum((f ** 2).sum(dim=0).sum(dim=-1) for f in flat)
+    assert size > 1
+    mean = sum_ / size
+    sumvar = ssum - sum_ * mean
+    unbias_var = sumvar / (size - 1)
+    bias_var = sumvar / size
+    rm = (1 - momentum) * rm + momentum * mean
+    rv = (1 - momentum) * rv + momentum * unbias_var
+    inv_std = bias_var.clamp(eps) ** -0.5
+    outs = []
+    for x, f in zip(shards, flat):
+        if weight is not None:
+            o = (f - mean.view(1, C, 1)) * (inv_std * weight).view(1, C, 1) + bias.view(1, C, 1)
+        else:
+            o = (f - mean.view(1, C, 1)) * inv_std.view(1, C, 1)
+        outs.append(o.view(x.shape))
+    return outs, rm, rv, mean, inv_std
+
+
 def randomize_bn_(sd: SD, seed: int = 7) -> SD:
     """Give every BN non-trivial affine params and running stats so BN folding is exercised."""
     g = torch.Generator().manual_seed(seed)

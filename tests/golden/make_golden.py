@@ -165,7 +165,52 @@ def gen_siblings():
     print("siblings.npz", len(g), "entries")
 
 
+def gen_syncbn():
+    """SynchronizedBatchNorm2d in training mode, the unmodified reference class (batchnorm.py:180).  The DataParallel
+    thread rendezvous (comm.py) is host control flow, not arithmetic: the fixture drives the reference's own pieces in
+    the order `forward` / `_data_parallel_master` run them — per-shard sums (:59-61), sizes and sums added over the
+    devices (:100-102; ReduceAddCoalesced is a plain sum), `_compute_mean_std` (:113-125, which also updates the running
+    statistics) and the output expression (:68-75).  Also the one-device path (:50-53) through `forward` itself."""
+    from modeling.sync_batchnorm.batchnorm import SynchronizedBatchNorm2d as RefSyncBN, _sum_ft, _unsqueeze_ft
+    g = {}
+    for cname, spec in util.SYNCBN_CASES.items():
+        shards, state = util.make_syncbn_case(cname)
+        C = spec["C"]
+        for mode in ("sync", "local"):
+            bn = RefSyncBN(C, eps=spec["eps"], momentum=spec["momentum"], affine=spec["affine"])
+            bn.load_state_dict(state, strict=True)
+            bn.train()
+            with torch.no_grad():
+                if mode == "local":
+                    outs = [bn(x) for x in shards]                      # not parallel -> F.batch_norm (:50-53)
+                else:
+                    flat = [x.view(x.size(0), C, -1) for x in shards]
+                    size = sum(f.size(0) * f.size(2) for f in flat)
+                    sum_ = sum(_sum_ft(f) for f in flat)
+                    ssum = sum(_sum_ft(f ** 2) for f in flat)
+                    mean, inv_std = bn._compute_mean_std(sum_, ssum, size)
+                    outs = []
+                    for x, f in zip(shards, flat):
+                        if bn.affine:
+                            o = (f - _unsqueeze_ft(mean)) * _unsqueeze_ft(inv_std * bn.weight) + _unsqueeze_ft(bn.bias)
+                        else:
+                            o = (f - _unsqueeze_ft(mean)) * _unsqueeze_ft(inv_std)
+                        outs.append(o.view(x.size()))
+                    g[f"{cname}/{mode}/mean"] = f32(mean)
+                    g[f"{cname}/{mode}/inv_std"] = f32(inv_std)
+            for i, o in enumerate(outs):
+                g[f"{cname}/{mode}/y{i}"] = f32(o)
+            g[f"{cname}/{mode}/running_mean"] = f32(bn.running_mean)
+            g[f"{cname}/{mode}/running_var"] = f32(bn.running_var)
+    np.savez_compressed(OUT / "syncbn.npz", **g)
+    print("syncbn.npz", len(g), "arrays")
+
+
 if __name__ == "__main__":
+    if "--only-syncbn" in sys.argv:
+        gen_syncbn()
+        sys.exit(0)
     gen_ops()
     gen_nets()
     gen_siblings()
+    gen_syncbn()

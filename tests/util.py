@@ -184,3 +184,29 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max|a-b| / max|b| — the parity metric of BASELINE.json (max-norm relative)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ---- SynchronizedBatchNorm2d, training mode (SURVEY §8f row 1) -----------------------------------
+# shards = the per-device inputs of one step (unequal batch sizes on purpose); affine / eps / momentum vary
+SYNCBN_CASES = {
+    "c8_2shards": dict(C=8, shards=[(2, 5, 7), (3, 5, 7)], eps=1e-5, momentum=0.1, affine=True, seed=31),
+    "c40_3shards": dict(C=40, shards=[(1, 9, 6), (2, 9, 6), (1, 9, 6)], eps=1e-5, momentum=0.1, affine=True, seed=32),
+    "c16_noaffine": dict(C=16, shards=[(2, 4, 4), (2, 4, 4)], eps=1e-3, momentum=0.3, affine=False, seed=33),
+    "c12_tiny_var": dict(C=12, shards=[(2, 3, 5), (1, 3, 5)], eps=1e-2, momentum=0.1, affine=True, seed=34, scale=1e-2),
+}
+
+
+def make_syncbn_case(name):
+    """(list of fp32 NCHW shards, BatchNorm state_dict) for SYNCBN_CASES[name]; `c12_tiny_var` has per-channel variance
+    below eps, where clamp(var, eps) (synchronised path) and var + eps (F.batch_norm) differ most."""
+    spec = SYNCBN_CASES[name]
+    g = torch.Generator().manual_seed(spec["seed"])
+    C = spec["C"]
+    sc = spec.get("scale", 1.0)
+    shards = [(torch.randn(n, C, h, w, generator=g) * sc + torch.randn(1, C, 1, 1, generator=g)) for (n, h, w) in spec["shards"]]
+    state = {"running_mean": torch.randn(C, generator=g) * 0.1, "running_var": torch.rand(C, generator=g) + 0.5,
+             "num_batches_tracked": torch.tensor(0)}
+    if spec["affine"]:
+        state["weight"] = torch.rand(C, generator=g) + 0.5
+        state["bias"] = torch.randn(C, generator=g) * 0.2
+    return shards, state
