@@ -69,21 +69,33 @@ bilinear_kernel(const TI* __restrict__ x, TO* __restrict__ y, int H, int W, int 
   }
 }
 
-// ---- exact integer upscale (x2, x4), bf16, 8 channels per thread ------------------------------------
+// ---- upscale, bf16, 8 channels per thread: one thread per SOURCE cell -----------------------------------
 // The generic kernel is ISSUE-bound, not HBM-bound, when it upsamples (ncu r01y: issue slots 67-71 % busy at 54-70 %
-// of DRAM peak; the x4 exit resize ran at 1.8 TB/s): every output pixel pays two integer divisions, two source-index
-// computations, four 16-byte gathers, 32 bf16->fp32 conversions and 48 FLOPs for 16 bytes stored.  With an exact
-// integer scale S the S x S outputs o = S*j + S/2 .. S*j + S/2 + S-1 (both axes) share their four source pixels
-// (j, j+1): a thread owns that block for 8 channels — sources loaded and converted once, the horizontal lerp shared
-// by the S rows — about 4x fewer instructions per output.  Source indices and weights still come from bilinear_src
-// and each output is the same expression as in bilinear_pixel, so results are identical to the generic kernel's;
-// blocks that touch the border (clamped sources) take the generic per-pixel path.
-template <int S>
+// of DRAM peak; the ~x4 exit resize 63x127 -> 256x512 ran at 1.75 TB/s): every output pixel pays two integer
+// divisions, two source-index computations, four 16-byte gathers, 32 bf16->fp32 conversions and 48 FLOPs for the 16
+// bytes it stores.  All outputs whose source index pair is (y0, x0) read the same four source pixels, so here a thread
+// owns a source cell (y0, x0) for 8 channels: sources loaded and converted once, the horizontal lerp of a column
+// shared by the cell's rows — for a x4 upscale ~4x fewer instructions per output.  Which outputs belong to a cell, and
+// their weights, come from bilinear_src itself (the index is monotone in the output coordinate, so a cell's outputs
+// are a contiguous range found by walking from an under-estimate); every output is the same expression as in
+// bilinear_pixel.  Results are bit-identical to the generic kernel's, borders (clamped sources) included.
+__device__ __forceinline__ int bilinear_first_out(int cell, float scale, int in_size, int out_size) {
+  // smallest output index whose source index i0 is >= cell
+  int e = (int)floorf((static_cast<float>(cell) + 0.5f) / scale - 0.5f) - 1;
+  e = e < 0 ? 0 : e;
+  while (e < out_size) {
+    int i0, i1; float l0, l1;
+    bilinear_src(e, scale, in_size, i0, i1, l0, l1);
+    if (i0 >= cell) break;
+    ++e;
+  }
+  return e;
+}
+
 __global__ void __launch_bounds__(256)
-bilinear_up_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int H, int W, int C, int xs, int ys, uint32_t flags) {
-  const int Ho = S * H, Wo = S * W;
-  const float sc = 1.f / (float)S;
-  const unsigned cv = (unsigned)C / 8, row = (unsigned)(W + 1) * cv, total = (unsigned)(H + 1) * row;
+bilinear_up_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int H, int W, int C, int xs,
+                   int Ho, int Wo, int ys, float sh, float sw, uint32_t flags) {
+  const unsigned cv = (unsigned)C / 8, row = (unsigned)W * cv, total = (unsigned)H * row;
   const int n = blockIdx.y;
   const bf16* xn = x + (size_t)n * H * W * xs;
   bf16* yn = y + (size_t)n * Ho * Wo * ys;
@@ -91,48 +103,36 @@ bilinear_up_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int H, int 
   for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
     const unsigned byu = idx / row, rem = idx - byu * row, bxu = rem / cv;
     const int c = (int)(rem - bxu * cv) * 8;
-    const int by = (int)byu - 1, bx = (int)bxu - 1;               // source cell (by, bx) .. (by+1, bx+1)
-    const int oy0 = S * by + S / 2, ox0 = S * bx + S / 2;         // first output of the block
-    if (by >= 0 && by < H - 1 && bx >= 0 && bx < W - 1) {
-      float a[8], b[8], cc[8], d[8];
-      VecIO<8>::load(xn + ((size_t)by * W + bx) * xs + c, a);
-      VecIO<8>::load(xn + ((size_t)by * W + bx + 1) * xs + c, b);
-      VecIO<8>::load(xn + ((size_t)(by + 1) * W + bx) * xs + c, cc);
-      VecIO<8>::load(xn + ((size_t)(by + 1) * W + bx + 1) * xs + c, d);
-      if (relu_in) {
+    const int by = (int)byu, bx = (int)bxu;                      // source cell: rows (by, by1), columns (bx, bx1)
+    const int by1 = by + (by < H - 1 ? 1 : 0), bx1 = bx + (bx < W - 1 ? 1 : 0);
+    const int oy_lo = bilinear_first_out(by, sh, H, Ho), ox_lo = bilinear_first_out(bx, sw, W, Wo);
+    float a[8], b[8], cc[8], d[8];
+    VecIO<8>::load(xn + ((size_t)by * W + bx) * xs + c, a);
+    VecIO<8>::load(xn + ((size_t)by * W + bx1) * xs + c, b);
+    VecIO<8>::load(xn + ((size_t)by1 * W + bx) * xs + c, cc);
+    VecIO<8>::load(xn + ((size_t)by1 * W + bx1) * xs + c, d);
+    if (relu_in) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a[i] = fmaxf(a[i], 0.f); b[i] = fmaxf(b[i], 0.f); cc[i] = fmaxf(cc[i], 0.f); d[i] = fmaxf(d[i], 0.f); }
-      }
-      float hl0[S], hl1[S];
+      for (int i = 0; i < 8; ++i) { a[i] = fmaxf(a[i], 0.f); b[i] = fmaxf(b[i], 0.f); cc[i] = fmaxf(cc[i], 0.f); d[i] = fmaxf(d[i], 0.f); }
+    }
+    for (int ox = ox_lo; ox < Wo; ++ox) {
+      int x0, x1; float wl0, wl1;
+      bilinear_src(ox, sw, W, x0, x1, wl0, wl1);
+      if (x0 != bx) break;
+      float top[8], bot[8];
 #pragma unroll
-      for (int ry = 0; ry < S; ++ry) { int i0, i1; bilinear_src(oy0 + ry, sc, H, i0, i1, hl0[ry], hl1[ry]); }
+      for (int i = 0; i < 8; ++i) { top[i] = wl0 * a[i] + wl1 * b[i]; bot[i] = wl0 * cc[i] + wl1 * d[i]; }
+      for (int oy = oy_lo; oy < Ho; ++oy) {
+        int y0, y1; float hl0, hl1;
+        bilinear_src(oy, sh, H, y0, y1, hl0, hl1);
+        if (y0 != by) break;
+        float r[8];
 #pragma unroll
-      for (int rx = 0; rx < S; ++rx) {
-        int i0, i1; float wl0, wl1;
-        bilinear_src(ox0 + rx, sc, W, i0, i1, wl0, wl1);
-        float top[8], bot[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { top[i] = wl0 * a[i] + wl1 * b[i]; bot[i] = wl0 * cc[i] + wl1 * d[i]; }
-#pragma unroll
-        for (int ry = 0; ry < S; ++ry) {
-          float r[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float o = hl0[ry] * top[i] + hl1[ry] * bot[i];
-            r[i] = relu_out ? fmaxf(o, 0.f) : o;
-          }
-          VecIO<8>::store(yn + ((size_t)(oy0 + ry) * Wo + ox0 + rx) * ys + c, r);
+        for (int i = 0; i < 8; ++i) {
+          const float o = hl0 * top[i] + hl1 * bot[i];
+          r[i] = relu_out ? fmaxf(o, 0.f) : o;
         }
-      }
-    } else {
-      for (int ry = 0; ry < S; ++ry) {
-        const int oy = oy0 + ry;
-        if (oy < 0 || oy >= Ho) continue;
-        for (int rx = 0; rx < S; ++rx) {
-          const int ox = ox0 + rx;
-          if (ox < 0 || ox >= Wo) continue;
-          bilinear_pixel<bf16, bf16, 8>(xn, yn, oy, ox, c, H, W, xs, Wo, ys, sc, sc, flags);
-        }
+        VecIO<8>::store(yn + ((size_t)oy * Wo + ox) * ys + c, r);
       }
     }
   }
@@ -268,11 +268,11 @@ edm_mlp_kernel(const float* __restrict__ pooled, const float* __restrict__ w0, c
   }
 }
 
-int g_bilinear_up = 1;      // 1 = block kernel for exact x2 / x4 upscales (default), 0 = generic kernel everywhere (A/B)
+int g_bilinear_up = 1;      // 1 = source-cell kernel for >= 1.5x bf16 upscales (default), 0 = generic kernel everywhere (A/B)
 
 }  // namespace
 
-/* 1 = shared-source block kernel for exact x2 / x4 bf16 upscales (default); 0 = generic per-pixel kernel (A/B runs). */
+/* 1 = source-cell kernel for >= 1.5x bf16 upscales (default); 0 = generic per-pixel kernel everywhere (A/B runs). */
 extern "C" int add_bilinear_set_mode(int mode) { g_bilinear_up = mode ? 1 : 0; return ADD_OK; }
 
 extern "C" int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, uint32_t flags, void* stream) {
@@ -284,18 +284,15 @@ extern "C" int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, ui
   const bool v8 = x->dtype == ADD_BF16 && y->dtype == ADD_BF16 && x->c % 8 == 0 && x->pix_stride % 8 == 0 &&
                   y->pix_stride % 8 == 0 && ((uintptr_t)x->ptr % 16) == 0 && ((uintptr_t)y->ptr % 16) == 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int up = (v8 && x->h >= 2 && x->w >= 2 && y->h == 2 * x->h && y->w == 2 * x->w) ? 2
-               : (v8 && x->h >= 2 && x->w >= 2 && y->h == 4 * x->h && y->w == 4 * x->w) ? 4 : 0;
-  if (up && g_bilinear_up) {
-    const long long tot = (long long)(x->h + 1) * (x->w + 1) * (x->c / 8);
+  // upscales by >= 1.5x in both directions (bf16, 16-byte vectors): one thread per source cell
+  if (v8 && g_bilinear_up && 2 * y->h >= 3 * x->h && 2 * y->w >= 3 * x->w) {
+    const long long tot = (long long)x->h * x->w * (x->c / 8);
     long long gb = (tot + 255) / 256;
     const long long capu = (148ll * 16 + y->n - 1) / y->n;
     if (gb > capu) gb = capu;
     dim3 gridu((unsigned)gb, (unsigned)y->n);
-    if (up == 2)
-      bilinear_up_kernel<2><<<gridu, 256, 0, s>>>((const bf16*)x->ptr, (bf16*)y->ptr, x->h, x->w, x->c, x->pix_stride, y->pix_stride, flags);
-    else
-      bilinear_up_kernel<4><<<gridu, 256, 0, s>>>((const bf16*)x->ptr, (bf16*)y->ptr, x->h, x->w, x->c, x->pix_stride, y->pix_stride, flags);
+    bilinear_up_kernel<<<gridu, 256, 0, s>>>((const bf16*)x->ptr, (bf16*)y->ptr, x->h, x->w, x->c, x->pix_stride, y->h, y->w,
+                                            y->pix_stride, sh, sw, flags);
     ADD_RETURN_LAUNCH();
   }
   const long long total = (long long)y->h * y->w * (y->c / (v8 ? 8 : 4));

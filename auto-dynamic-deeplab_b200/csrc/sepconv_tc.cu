@@ -298,8 +298,11 @@ sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, con
       int it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const int b = it & 1; const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-        mbar_wait_relaxed(bar_afull + 8 * b, ph);      // (a tight spin here was 12 % of the SM's issued instructions, ncu r3f)
-        mbar_wait_relaxed(bar_tempty + 8 * b, ph ^ 1u);
+        // tight spin: polling with a sleep (mbar_wait_relaxed) frees ~12 % of the SM's issue slots (ncu r3f) but puts up to
+        // 128 ns between the depthwise warps' arrival and the MMA of every tile; measured neutral in the bench and the
+        // microbench and +4 us per launch in the cold-cache ncu list (r03a), so the spin stays
+        mbar_wait(bar_afull + 8 * b, ph);
+        mbar_wait(bar_tempty + 8 * b, ph ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int kc = 0; kc < p.kchunks; ++kc) {
           const int krem = C - kc * TC_BK;

@@ -180,6 +180,8 @@ if _os.environ.get("ADD_GRID_PCT"):
     check(lib.add_set_persistent_grid_pct(int(_os.environ["ADD_GRID_PCT"])), "set_persistent_grid_pct")
 if _os.environ.get("ADD_TC_HALO_MODE"):
     set_tc_halo_mode(int(_os.environ["ADD_TC_HALO_MODE"]))
+if _os.environ.get("ADD_BILINEAR_MODE"):
+    check(lib.add_bilinear_set_mode(int(_os.environ["ADD_BILINEAR_MODE"])), "bilinear_set_mode")
 if _os.environ.get("ADD_SEPCONV_MODE"):
     check(lib.add_sepconv_tc_set_mode(int(_os.environ["ADD_SEPCONV_MODE"])), "sepconv_tc_set_mode")
 

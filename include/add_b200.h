@@ -155,8 +155,8 @@ int add_bn_apply_fwd(const add_tensor_t* x, const add_tensor_t* y, const float* 
 
 /* ---- bilinear resize, align_corners=False (F.interpolate: ADD.py:76,84,89,317; decoder.py:24) */
 int add_bilinear_fwd(const add_tensor_t* x, const add_tensor_t* y, uint32_t flags, void* stream);
-/* add_bilinear_fwd scheduling: 1 = exact x2 / x4 bf16 upscales use a kernel whose threads own the S x S output block
- * that shares four source pixels (default; results identical to the generic kernel), 0 = generic kernel everywhere. */
+/* add_bilinear_fwd scheduling: 1 = bf16 upscales by >= 1.5x use a kernel whose threads own a SOURCE cell and produce
+ * every output that interpolates it (default; results identical to the generic kernel), 0 = generic kernel everywhere. */
 int add_bilinear_set_mode(int mode);
 
 /* ---- batch compaction for per-image early exit (ADD.py:421-432 applied to a batch): whole-image

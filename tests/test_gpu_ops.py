@@ -85,12 +85,14 @@ def test_bilinear_matches_numpy_oracle(hw_in, hw_out):
     assert np.abs(got - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("scale", [2, 4])
-@pytest.mark.parametrize("hw_in", [(2, 2), (5, 9), (16, 33)])
+@pytest.mark.parametrize("hw_in,hw_out", [((2, 2), (8, 8)), ((5, 9), (20, 36)), ((16, 33), (32, 66)), ((63, 127), (256, 512)),
+                                          ((63, 127), (125, 253)), ((32, 64), (63, 127)), ((1, 5), (4, 20)), ((3, 3), (5, 6)),
+                                          ((7, 1), (29, 3))])
 @pytest.mark.parametrize("flags", [0, 1, 3], ids=["plain", "relu_in", "relu_in_out"])
-def test_bilinear_integer_upscale_equals_generic_kernel(scale, hw_in, flags):
-    """bf16 x2 / x4 upscales take the shared-source block kernel: bit-identical to the generic per-pixel kernel
-    (same source indices, weights and expression), channel-slice input and output views left untouched outside."""
+def test_bilinear_upscale_kernel_equals_generic_kernel(hw_in, hw_out, flags):
+    """bf16 upscales by >= 1.5x take the source-cell kernel: bit-identical to the generic per-pixel kernel (same
+    source indices, weights and expression; clamped borders, 1-pixel sources, non-integer scales such as the
+    63x127 -> 256x512 exit resize), channel-slice input and output views left untouched outside."""
     from add_b200._lib import lib as _lib
     from add_b200.runtime import Builder, View
     g = torch.Generator().manual_seed(11)
@@ -101,7 +103,7 @@ def test_bilinear_integer_upscale_equals_generic_kernel(scale, hw_in, flags):
     for mode in (1, 0):
         assert _lib.add_bilinear_set_mode(mode) == 0
         try:
-            y_buf = torch.full((2, h * scale, w * scale, c + 24), 7.0, dtype=torch.bfloat16, device=DEV)
+            y_buf = torch.full((2, hw_out[0], hw_out[1], c + 24), 7.0, dtype=torch.bfloat16, device=DEV)
             b = Builder(torch.device(DEV), torch.bfloat16)
             b.bilinear(View(x_buf, 8, c), View(y_buf, 16, c), flags)
             torch.cuda.synchronize()
@@ -113,7 +115,7 @@ def test_bilinear_integer_upscale_equals_generic_kernel(scale, hw_in, flags):
     xin = x_buf[..., 8:8 + c].float().permute(0, 3, 1, 2)
     if flags & 1:
         xin = torch.relu(xin)
-    ref = torch.nn.functional.interpolate(xin, scale_factor=scale, mode="bilinear", align_corners=False)
+    ref = torch.nn.functional.interpolate(xin, list(hw_out), mode="bilinear", align_corners=False)
     if flags & 2:
         ref = torch.relu(ref)
     got = outs[0][..., 16:16 + c].float().permute(0, 3, 1, 2)

@@ -33,7 +33,11 @@ def cases():
             ("stem2_64to128_s2", "conv", (64, 128, 3, 2, 1, 1, 8, 512, 1024, RELU_IN)),
             ("aspp_400to256_d12", "conv", (400, 256, 3, 1, 12, 12, 4, 256, 512, RELU_IN | RELU_OUT)),
             ("aspp_400to256_d12_norelu", "conv", (400, 256, 3, 1, 12, 12, 4, 256, 512, RELU_OUT)),
-            ("dec_304to256_3x3", "conv", (304, 256, 3, 1, 1, 1, 4, 128, 256, RELU_IN | RELU_OUT))]
+            ("dec_304to256_3x3", "conv", (304, 256, 3, 1, 1, 1, 4, 128, 256, RELU_IN | RELU_OUT)),
+            ("bil_exit_63x127to256x512_c400", "bil", (400, 4, 63, 127, 256, 512)),
+            ("bil_cellup_63x127to125x253_c400", "bil", (400, 4, 63, 127, 125, 253)),
+            ("bil_dense_32x64to63x127_c160", "bil", (160, 4, 32, 64, 63, 127)),
+            ("bil_down_256x512to128x256_c256", "bil", (256, 4, 256, 512, 128, 256))]
     return out
 
 
@@ -68,6 +72,12 @@ def main():
                 x = View(torch.randn(n, h, w, cin, device=DEV).to(torch.bfloat16)); b.keep.append(x.buf)
                 y = b.alloc(n, h, w, cout)
                 m.emit(b, x, y, 0)
+        elif kind == "bil":
+            C, n, h, w, ho, wo = a
+            for _ in range(nbuf):
+                x = View(torch.randn(n, h, w, C, device=DEV).to(torch.bfloat16)); b.keep.append(x.buf)
+                y = b.alloc(n, ho, wo, C)
+                b.bilinear(x, y, 0, name)
         else:
             cin, cout, k, stride, pad, dil, n, h, w, flags = a
             flags |= int(os.environ.get("ADD_MB_FLAGS", "0"), 0)
