@@ -442,6 +442,21 @@ class ADD(AddModule):
         return run_dynamic_evaluate(self, x, target, threshold, edm, exit_mode, bind_inputs)
 
 
+    def dynamic_evaluate_begin(self, x: torch.Tensor, target: torch.Tensor, threshold=1.0, edm=False,
+                               exit_mode: str = "reference", bind_inputs: bool = False):
+        """dynamic_evaluate split at the first gate (the host decision): enqueue the trunk, return a handle for
+        dynamic_evaluate_finish.  Interleaving begin(batch i+1) before finish(batch i) — on DIFFERENT input buffers with
+        bind_inputs=True, e.g. HostPipeline's slots — keeps the GPU busy while the host decides."""
+        from .dynamic import begin_dynamic_evaluate
+        self._check_eval()
+        rt.require_cuda(x)
+        return begin_dynamic_evaluate(self, x, target, threshold, edm, exit_mode, bind_inputs)
+
+    def dynamic_evaluate_finish(self, handle):
+        from .dynamic import finish_dynamic_evaluate
+        return finish_dynamic_evaluate(self, handle)
+
+
 class _NetPlan:
     """Recorded launch plans + static I/O buffers for one (kind, input shape, precision)."""
 

@@ -17,7 +17,7 @@ from .ADD import ADD, Cell, EDM
 from .baseline_model import Baselin_Model, AutoDeepLab, Cell_baseline, Cell_AutoDeepLab
 from .metrics import Evaluator
 from .factory import build_add, Args, synthetic_batch
-from .pipeline import HostPipeline
+from .pipeline import HostPipeline, ResidentPipeline
 from .parallel import shard_range, env_rank_world, all_reduce_confusion
 
 __version__ = "0.1.0"

@@ -248,6 +248,33 @@ class _EdmRunner:
         """Returns (outputs per image, exit flag per image, confidence per image).  outputs[j] is a
         [1,nc,H,W] fp32 logits tensor ('logits') or an int64 [nc,nc] confusion matrix ('evaluate');
         they alias plan buffers that the next call overwrites."""
+        return self.finish(self.begin(x, threshold, target))
+
+    # The gate is a host decision (the reference's implicit sync, ADD.py:421): after the trunk graph the host reads N
+    # floats, picks the plans for the exiting / continuing images and launches them — ~0.15 ms per step during which
+    # the GPU is idle (tools/bubble_test.py).  begin() enqueues everything up to the first gate and returns; finish()
+    # waits for that gate's values and enqueues the rest.  A caller that owns several runners (HostPipeline's slots)
+    # calls begin() of batch i+1 BEFORE finish() of batch i, so the GPU works on the next trunk while the host decides.
+    def begin(self, x: torch.Tensor, threshold: float, target: Optional[torch.Tensor] = None):
+        gen = self._steps(x, threshold, target)
+        try:
+            return [gen, next(gen), None]                 # [coroutine, event of the pending gate, result]
+        except StopIteration as stop:
+            return [None, None, stop.value]
+
+    def finish(self, state):
+        gen, ev, result = state
+        while gen is not None:
+            ev.synchronize()                              # the gate values are in pinned host memory
+            try:
+                ev = next(gen)
+            except StopIteration as stop:
+                gen, result = None, stop.value
+        return result
+
+    def _steps(self, x: torch.Tensor, threshold: float, target: Optional[torch.Tensor] = None):
+        """Coroutine behind begin()/finish(): yields a CUDA event after each gate's D2H copy is enqueued and expects
+        to be resumed once that event has completed."""
         n = self.n
         outs: List[Optional[torch.Tensor]] = [None] * n
         flags = [0] * n
@@ -277,7 +304,9 @@ class _EdmRunner:
             # host decision = the reference's implicit sync (ADD.py:421): N floats come down through pinned memory
             m_act = len(active)
             self._conf_pin[:m_act].copy_(seg.conf, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
+            gate_ev = torch.cuda.Event()
+            gate_ev.record(torch.cuda.current_stream(self.device))
+            yield gate_ev
             vals = self._conf_pin[:m_act].tolist()
             ex = [j for j in range(m_act) if not (vals[j] > threshold)]
             co = [j for j in range(m_act) if vals[j] > threshold]
@@ -422,6 +451,21 @@ def run_dynamic(net, x: torch.Tensor, threshold, confidence, edm, exit_mode: str
     outs, flags, confs = r.run(x, float(threshold))
     net.last_dynamic_launches = r.last_launches
     return outs, flags, confs
+
+
+def begin_dynamic_evaluate(net, x: torch.Tensor, target: torch.Tensor, threshold, edm, exit_mode: str = "reference",
+                           bind_inputs: bool = False):
+    """First half of run_dynamic_evaluate: enqueue the trunk up to the first gate and return a handle."""
+    r = _get_runner(net, x, edm, "evaluate", exit_mode, target, bind_inputs)
+    return r, r.begin(x, float(threshold), target)
+
+
+def finish_dynamic_evaluate(net, handle):
+    """Second half: wait for the gate values, enqueue the exit heads / remaining trunk.  Returns (cm, flags, confs)."""
+    r, state = handle
+    outs, flags, confs = r.finish(state)
+    net.last_dynamic_launches = r.last_launches
+    return torch.stack(outs), flags, confs
 
 
 def run_dynamic_evaluate(net, x: torch.Tensor, target: torch.Tensor, threshold, edm, exit_mode: str = "reference",

@@ -23,9 +23,10 @@ class HostPipeline:
     edm=None  → multi-exit `ADD.evaluate` (eval.py:165-193, every exit scored);
     edm given → EDM-gated early exit per image, `ADD.dynamic_evaluate` (eval.py:195-221)."""
 
-    def __init__(self, net, edm=None, threshold: float = 1.0, exit_mode: str = "reference", depth: int = 2):
+    def __init__(self, net, edm=None, threshold: float = 1.0, exit_mode: str = "reference", depth: int = 3):
         self.net, self.edm, self.threshold, self.exit_mode = net, edm, float(threshold), exit_mode
-        self.depth = max(2, int(depth))
+        # 3 slots: batch i+2 is being copied in while the trunk of batch i+1 and the exit heads of batch i compute
+        self.depth = max(2 if edm is None else 3, int(depth))
         self.device = next(net.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("HostPipeline needs the model on a CUDA device (add_b200 has no CPU fallback)")
@@ -62,6 +63,9 @@ class HostPipeline:
         self.h2d_bytes += x.numel() * x.element_size() + gt.numel() * gt.element_size()
 
     def evaluate(self, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]]) -> Iterator[Tuple[torch.Tensor, Optional[list]]]:
+        if self.edm is not None:
+            yield from self._evaluate_gated(batches)
+            return
         main = torch.cuda.current_stream(self.device)
         it = iter(batches)
         nxt = next(it, None)
@@ -78,13 +82,7 @@ class HostPipeline:
             if nxt is not None:                              # enqueue the next copy BEFORE this batch's compute
                 self._prefetch(self._slots[(i + 1) % self.depth], *nxt)
             main.wait_event(slot["ready"])
-            if self.edm is None:
-                cm, flags = self.net.evaluate(slot["x"], slot["gt"]), None
-            else:
-                # the slot buffers are stable: the plans are recorded directly on them (no device-to-device input copy)
-                cm, flags, _ = self.net.dynamic_evaluate(slot["x"], slot["gt"], self.threshold, self.edm, self.exit_mode,
-                                                         bind_inputs=True)
-                cm = cm.unsqueeze(0)
+            cm, flags = self.net.evaluate(slot["x"], slot["gt"]), None
             slot["free"].record(main)
             if slot["out"] is None or slot["out"].shape != cm.shape:
                 slot["out"] = torch.empty(cm.shape, dtype=torch.int64).pin_memory()
@@ -93,3 +91,90 @@ class HostPipeline:
             self.d2h_bytes += cm.numel() * 8
             yield slot["out"], flags
             i += 1
+
+    def _evaluate_gated(self, batches):
+        """EDM-gated early exit, software-pipelined over the slots so that neither host round trip of a step leaves the
+        GPU idle: in iteration i the trunk of batch i+1 is enqueued (`dynamic_evaluate_begin`) BEFORE the host waits
+        for batch i's gate values and launches its exit heads / remaining trunk (`dynamic_evaluate_finish`), and the
+        confusion matrices of batch i are awaited one iteration later.  Stream order:
+            trunk(i+1) | heads(i), rest(i), D2H cm(i) | trunk(i+2) | heads(i+1) ...   with H2D(i+2) on the copy stream.
+        The slot buffers are stable, so the plans are recorded directly on them (no device-to-device input copy)."""
+        main = torch.cuda.current_stream(self.device)
+        it = iter(batches)
+        first = next(it, None)
+        if first is None:
+            return
+        self._ensure_slots(*first)
+        for s in self._slots:
+            s["free"].record(main)
+            s.setdefault("done", torch.cuda.Event())
+        D = self.depth
+
+        def begin(slot):
+            main.wait_event(slot["ready"])
+            return self.net.dynamic_evaluate_begin(slot["x"], slot["gt"], self.threshold, self.edm, self.exit_mode,
+                                                   bind_inputs=True)
+
+        queued = [first]                                    # host batches whose H2D has been enqueued, not yet begun
+        self._prefetch(self._slots[0], *first)
+        nb = next(it, None)
+        if nb is not None:
+            self._prefetch(self._slots[1 % D], *nb)
+            queued.append(nb)
+        handle = begin(self._slots[0])
+        queued.pop(0)
+        i = 0
+        prev = None                                         # (slot, flags) of the batch whose result is still in flight
+        while handle is not None:
+            slot = self._slots[i % D]
+            nb = next(it, None)
+            if nb is not None:                              # batch i+2 -> the slot batch i-1 has left
+                self._prefetch(self._slots[(i + 2) % D], *nb)
+                queued.append(nb)
+            nxt_handle = None
+            if queued:                                      # trunk of batch i+1 goes in front of this batch's decision
+                nxt_handle = begin(self._slots[(i + 1) % D])
+                queued.pop(0)
+            cm, flags, _ = self.net.dynamic_evaluate_finish(handle)
+            cm = cm.unsqueeze(0)
+            slot["free"].record(main)
+            if slot["out"] is None or slot["out"].shape != cm.shape:
+                slot["out"] = torch.empty(cm.shape, dtype=torch.int64).pin_memory()
+            slot["out"].copy_(cm, non_blocking=True)
+            slot["done"].record(main)
+            self.d2h_bytes += cm.numel() * 8
+            if prev is not None:
+                prev[0]["done"].synchronize()               # the previous step's result is on the host
+                yield prev[0]["out"], prev[1]
+            prev = (slot, flags)
+            handle = nxt_handle
+            i += 1
+        if prev is not None:
+            prev[0]["done"].synchronize()
+            yield prev[0]["out"], prev[1]
+
+
+class ResidentPipeline:
+    """The same software pipeline for batches that already live in HBM: `evaluate(batches)` takes DEVICE tensors
+    (x fp32 [N,3,H,W], gt int64 [N,H,W]) that cycle over at least `depth` distinct, stable buffers (the plans are
+    recorded on them), and yields `(cm int64 [N,nc,nc] device tensor, exit flags)` one batch behind the enqueue front.
+    The yielded cm aliases plan buffers of that slot; it is overwritten `depth` batches later."""
+
+    def __init__(self, net, edm, threshold: float = 1.0, exit_mode: str = "reference"):
+        self.net, self.edm, self.threshold, self.exit_mode = net, edm, float(threshold), exit_mode
+
+    def evaluate(self, batches):
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        handle = self.net.dynamic_evaluate_begin(cur[0], cur[1], self.threshold, self.edm, self.exit_mode, bind_inputs=True)
+        while handle is not None:
+            nxt = next(it, None)
+            nxt_handle = None
+            if nxt is not None:
+                nxt_handle = self.net.dynamic_evaluate_begin(nxt[0], nxt[1], self.threshold, self.edm, self.exit_mode,
+                                                             bind_inputs=True)
+            cm, flags, _ = self.net.dynamic_evaluate_finish(handle)
+            yield cm, flags
+            handle = nxt_handle

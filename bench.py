@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--exit-mode", default="reference", choices=["reference", "forward"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="resident arm: one blocking dynamic_evaluate call per step instead of the software pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=12, help="images in the bounded CPU-baseline sample")
     ap.add_argument("--label-dtype", default="uint8", choices=["uint8", "int64"],
@@ -310,6 +312,22 @@ def main_b200(a):
     def step_resident():
         return net.dynamic_evaluate(x_dev, gt_dev, thr, edm, a.exit_mode)
 
+    # resident arm: the batch lives in HBM in three buffers that are cycled through add_b200.ResidentPipeline — the
+    # trunk of step i+1 is enqueued before the host reads step i's gate values, so the gate's host round trip
+    # (~0.15 ms per step, tools/bubble_test.py) does not leave the GPU idle.  --no-pipeline: one blocking call per step.
+    res_bufs = [(x_dev, gt_dev)] if a.no_pipeline else [(x_dev.clone(), gt_dev.clone()) for _ in range(3)]
+    rpipe = add_b200.ResidentPipeline(net, edm, thr, a.exit_mode)
+
+    def run_resident(steps):
+        out = None
+        if a.no_pipeline:
+            for _ in range(steps):
+                out = step_resident()[0]
+            return out
+        for out, _ in rpipe.evaluate(res_bufs[i % len(res_bufs)] for i in range(steps)):
+            pass
+        return out
+
     # e2e: the public host-fed loop (add_b200.HostPipeline = eval.py's `for batch in loader` loop): every step's
     # images + labels come from pinned HOST memory (H2D inside the timed region, double-buffered on a copy
     # stream so batch i+1's copy overlaps batch i's compute) and its confusion matrices go back to the host.
@@ -332,19 +350,17 @@ def main_b200(a):
         torch.cuda.profiler.stop()
         return 0
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(run, steps, warmup, sample_clocks=False):
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
             sampler.start()
-        for _ in range(warmup):
-            fn()
+        run(warmup)
         barrier()
         if sampler:
             sampler.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        last = run(steps)
         e1.record()
         barrier()
         if sampler:
@@ -355,10 +371,11 @@ def main_b200(a):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
+        assert torch.equal(last, cm0), "pipelined resident result differs from the single-call result"
         return ms, clocks
 
-    ms_res, clocks = timed(step_resident, a.steps, max(a.warmup, 3), sample_clocks=True)
-    run_e2e(2)                                                   # warm-up (slot allocation, pinned result buffers)
+    ms_res, clocks = timed(run_resident, a.steps, max(a.warmup, 3), sample_clocks=True)
+    run_e2e(pipe.depth + 1)                                      # warm-up: every slot's plans recorded and captured, pinned result buffers
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h2d0, d2h0 = pipe.h2d_bytes, pipe.d2h_bytes
@@ -427,6 +444,8 @@ def main_b200(a):
                 "dtype": a.precision, "data": "synthetic", "config": dict(workload_name(a), parallelism=f"batch-shard dp{world}",
                                                                            early_exit_flags=flags0, edm_threshold=thr,
                                                                            cuda_graph=not a.no_graph,
+                                                                           resident_pipeline=(None if a.no_pipeline else
+                                                                                              "3 resident input buffers cycled; trunk of step i+1 enqueued before the host reads step i's gate values"),
                                                                            tensor_core_path=bool(rt.tc_available())),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_step,
                         "d2h_bytes_per_step": d2h_step + B * 4, "ms_per_step": ms_e2e / a.steps,

@@ -163,6 +163,37 @@ def test_host_pipeline_matches_direct_calls():
         assert torch.equal(cm_g, net.evaluate(x.to(DEV), gt.to(DEV)).cpu())
 
 
+def test_resident_pipeline_matches_direct_calls():
+    """ResidentPipeline (device batches cycling over three stable buffers; the trunk of batch i+1 is enqueued before
+    the host reads batch i's gate values) yields exactly what blocking dynamic_evaluate calls return, in order,
+    for batches with different exit patterns (7 batches over 3 buffers: every buffer is reused)."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec).to(DEV)
+    edm = util.make_edm().to(DEV)
+    batches = [util.make_input(3, 33, 65, seed=400 + i) for i in range(7)]
+    _, _, confs = net.dynamic_evaluate(batches[0][0].to(DEV), batches[0][1].to(DEV), -1e30, edm)
+    thr = sorted(float(c) for c in confs)[1]
+    want = []
+    for x, gt in batches:
+        cm, flags, _ = net.dynamic_evaluate(x.to(DEV), gt.to(DEV), thr, edm)
+        want.append((cm.cpu().clone(), list(flags)))
+    assert len({tuple(f) for _, f in want}) > 1, "the batches should not all take the same exits"
+    bufs = [(torch.empty_like(batches[0][0], device=DEV), torch.empty_like(batches[0][1], device=DEV)) for _ in range(3)]
+
+    def feed():
+        for i, (x, gt) in enumerate(batches):
+            bx, bg = bufs[i % 3]
+            bx.copy_(x.to(DEV)); bg.copy_(gt.to(DEV))      # stream-ordered after the last compute that read this buffer
+            yield bx, bg
+
+    pipe = add_b200.ResidentPipeline(net, edm, thr)
+    got = [(cm.cpu().clone(), list(flags)) for cm, flags in pipe.evaluate(feed())]
+    assert len(got) == len(want)
+    for (cm_g, fl_g), (cm_w, fl_w) in zip(got, want):
+        assert fl_g == fl_w
+        assert torch.equal(cm_g, cm_w)
+
+
 @pytest.mark.parametrize("cname", sorted(util.SIBLING_CASES))
 @pytest.mark.parametrize("precision,tol,agree_min", [("fp32", 1e-3, 0.999), ("bf16", 1e-1, 0.95)])
 def test_sibling_models(cname, precision, tol, agree_min):
