@@ -268,6 +268,11 @@ def main_torch_cuda(a):
 # our arm
 # --------------------------------------------------------------------------------------------------
 def main_b200(a):
+    # stdout carries exactly ONE JSON line: anything libraries print there meanwhile (NCCL's "NCCL version ..." banner
+    # under torchrun) is diverted to stderr by pointing fd 1 at fd 2 until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -453,7 +458,10 @@ def main_b200(a):
                         "api": "add_b200.HostPipeline.evaluate (pinned host batches, H2D of batch i+1 overlapped with compute of batch i)"},
                 "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
