@@ -54,6 +54,7 @@ _SIGS = {
     "add_conv2d_tc_set_halo_mode": (c_int, [c_int]),
     "add_sepconv_half_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_void_p]),
     "add_sepconv_half_tc_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_void_p]),
+    "add_depthwise_fwd": (c_int, [TP, TP, c_void_p, c_int, c_uint32, c_void_p]),
     "add_sepconv_tc_set_mode": (c_int, [c_int]),
     "add_bilinear_set_mode": (c_int, [c_int]),
     "add_bn_stats_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),

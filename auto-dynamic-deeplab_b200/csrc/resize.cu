@@ -346,10 +346,10 @@ extern "C" int64_t add_global_avgpool_workspace_bytes(int n, int h, int w, int c
 extern "C" int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_t flags, void* workspace,
                                       int64_t workspace_bytes, void* stream) {
   ADD_CHECK_ARG(tensor_ok(x) && out && workspace);
-  ADD_CHECK_SUP(tensor_vec4_ok(x) && x->c / 4 <= GAP_THREADS);
+  const bool v8 = x->dtype == ADD_BF16 && x->c % 8 == 0 && x->pix_stride % 8 == 0 && ((uintptr_t)x->ptr % 16) == 0;
+  ADD_CHECK_SUP(tensor_vec4_ok(x) && x->c / (v8 ? 8 : 4) <= GAP_THREADS);
   if (workspace_bytes < add_global_avgpool_workspace_bytes(x->n, x->h, x->w, x->c)) return ADD_ERR_WORKSPACE;
   const int HW = x->h * x->w, S = gap_splits(HW, x->n);
-  const bool v8 = x->dtype == ADD_BF16 && x->c % 8 == 0 && x->pix_stride % 8 == 0 && ((uintptr_t)x->ptr % 16) == 0;
   const int cv = x->c / (v8 ? 8 : 4);
   dim3 grid(S, x->n);
   size_t smem = (size_t)(GAP_THREADS / cv) * x->c * sizeof(float);

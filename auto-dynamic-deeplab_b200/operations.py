@@ -20,7 +20,7 @@ from .runtime import Builder, ConvWeights, View, RELU_IN, RELU_OUT, ACCUMULATE, 
 from ._lib import lib, check
 
 
-from .sync_batchnorm import SynchronizedBatchNorm2d  # noqa: E402  (reference name, modeling/sync_batchnorm/batchnorm.py:180)
+from .sync_batchnorm import SynchronizedBatchNorm2d, batch_norm_forward  # noqa: E402  (reference name, modeling/sync_batchnorm/batchnorm.py:180)
 
 
 class AddModule(nn.Module):
@@ -62,7 +62,10 @@ class AddModule(nn.Module):
         return n, c, h, w
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        self._check_eval()
+        if self.training:
+            y = self._forward_train(x)
+            rt.bump_generation()          # running statistics moved: folded eval-mode weights / recorded plans are stale
+            return y
         rt.require_cuda(x)
         dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
         b = Builder(x.device, dtype, record=False)
@@ -74,6 +77,19 @@ class AddModule(nn.Module):
 
     def emit(self, b: Builder, x: View, y: View, flags: int = 0) -> None:
         raise NotImplementedError
+
+    # ---- training-mode forward: batch statistics, unfused, eager ------------------------
+    # The conv kernels run with the RAW weights (no BN fold) and every BatchNorm is the three-kernel batch-statistics
+    # forward of sync_batchnorm.batch_norm_forward (synchronised over the process group when there is one).  Forward
+    # only — no autograd graph is built.  Modules that have no training forward yet raise.
+    def _forward_train(self, x: torch.Tensor) -> torch.Tensor:
+        self._check_eval()
+
+    def _train_io(self, x: torch.Tensor):
+        rt.require_cuda(x)
+        dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        b = Builder(x.device, dtype, record=False)
+        return b, rt.as_nhwc_view(x, b, dtype)
 
 
 def _relu_in(flags: int) -> int:
@@ -107,6 +123,13 @@ class ReLUConvBN(AddModule):
         self._ensure_prepared()
         b.conv(x, y, self.cw, self.stride, self.padding, 1, _relu_in(flags), "ReLUConvBN")
 
+    def _forward_train(self, x):
+        b, xv = self._train_io(x)
+        n, c, h, w = self.out_shape(*x.shape)
+        t = b.alloc(n, h, w, c)
+        b.conv(xv, t, ConvWeights(self.op[1].weight), self.stride, self.padding, 1, RELU_IN, "ReLUConvBN.train")
+        return batch_norm_forward(self.op[2], t.nchw())
+
 
 class DilConv(AddModule):
     """ReLU → DENSE C→C k×k dilated conv → BN as one implicit-GEMM launch
@@ -129,6 +152,13 @@ class DilConv(AddModule):
     def emit(self, b, x, y, flags=0):
         self._ensure_prepared()
         b.conv(x, y, self.cw, self.stride, self.padding, self.dilation, _relu_in(flags), "DilConv")
+
+    def _forward_train(self, x):
+        b, xv = self._train_io(x)
+        n, c, h, w = self.out_shape(*x.shape)
+        t = b.alloc(n, h, w, c)
+        b.conv(xv, t, ConvWeights(self.op[1].weight), self.stride, self.padding, self.dilation, RELU_IN, "DilConv.train")
+        return batch_norm_forward(self.op[2], t.nchw())
 
 
 class SepConv(AddModule):
@@ -163,6 +193,18 @@ class SepConv(AddModule):
         b.sepconv_half(x, mid, self.dw1, self.pw1, self.k, _relu_in(flags & IN_RELUD) | RELU_OUT, "SepConv.half1")
         b.sepconv_half(mid, y, self.dw2, self.pw2, self.k, flags & ~IN_RELUD, "SepConv.half2")
         b.release(mid)
+
+    def _forward_train(self, x):
+        def dw(conv):  # [C,1,k,k] -> [k][k][C]
+            return conv.weight.detach().float()[:, 0].permute(1, 2, 0).contiguous()
+        b, xv = self._train_io(x)
+        t1 = b.alloc(xv.n, xv.h, xv.w, self.C)
+        b.sepconv_half(xv, t1, dw(self.op[1]), ConvWeights(self.op[2].weight), self.k, RELU_IN, "SepConv.half1.train")
+        m = batch_norm_forward(self.op[3], t1.nchw(), relu=True)            # BN -> ReLU (op.4) fused in the normalise kernel
+        t2 = b.alloc(xv.n, xv.h, xv.w, self.C)
+        b.sepconv_half(rt.as_nhwc_view(m, b, xv.dtype), t2, dw(self.op[5]), ConvWeights(self.op[6].weight), self.k, 0,
+                       "SepConv.half2.train")
+        return batch_norm_forward(self.op[7], t2.nchw())
 
 
 class Identity(AddModule):
@@ -289,6 +331,16 @@ class _FactorizedReduceBase(AddModule):
         b.conv(x, y.slice(0, half), self.cw1, self.STEP, 0, 1, _relu_in(flags), type(self).__name__ + ".even")
         b.conv(x, y.slice(half, half), self.cw2, self.STEP, -(self.STEP // 2), 1, _relu_in(flags),
                type(self).__name__ + ".odd")
+
+    def _forward_train(self, x):
+        b, xv = self._train_io(x)
+        n, c, h, w = self.out_shape(*x.shape)
+        half = self.C_out // 2
+        t = b.alloc(n, h, w, c)
+        b.conv(xv, t.slice(0, half), ConvWeights(self.conv_1.weight), self.STEP, 0, 1, RELU_IN, type(self).__name__ + ".even.train")
+        b.conv(xv, t.slice(half, half), ConvWeights(self.conv_2.weight), self.STEP, -(self.STEP // 2), 1, RELU_IN,
+               type(self).__name__ + ".odd.train")
+        return batch_norm_forward(self.bn, t.nchw())
 
 
 class FactorizedReduce(_FactorizedReduceBase):

@@ -126,6 +126,14 @@ class ConvWeights:
         self._packed = None
         return self
 
+    def cout_slice(self, c0: int, g: int) -> "ConvWeights":
+        """The conv restricted to output channels [c0, c0 + g) (cached)."""
+        cache = self.__dict__.setdefault("_cout_slices", {})
+        if (c0, g) not in cache:
+            cache[(c0, g)] = ConvWeights.from_folded(self.w[..., c0:c0 + g].contiguous(),
+                                                     None if self.bias is None else self.bias[c0:c0 + g].contiguous())
+        return cache[(c0, g)]
+
     def packed_tc(self) -> torch.Tensor:
         if self._packed is None:
             nbytes = lib.add_conv2d_tc_packed_bytes(self.cin, self.cout, self.kh, self.kw)
@@ -292,6 +300,14 @@ class Builder:
              flags: int = 0, tag: str = "conv", image_bias: Optional[torch.Tensor] = None) -> None:
         """image_bias: fp32 [N, Cout] per-image bias replacing cw.bias (ASPP pool branch, see aspp_pool_bias)."""
         assert x.c == cw.cin and y.c == cw.cout, (x.c, cw.cin, y.c, cw.cout, tag)
+        if (cw.cout > 256 and image_bias is None and x.dtype == torch.bfloat16 and tc_available() and stride <= 2
+                and x.buf.shape[3] % 8 == 0 and x.c_off % 8 == 0):
+            # the tcgen05 kernels hold at most 256 output channels (one TMEM accumulator row of fp32 columns): wider
+            # convs (BASELINE config 5: C = 320 / 640 at F = 40 / 80) run as one launch per 256-channel output group
+            for c0 in range(0, cw.cout, 256):
+                g = min(256, cw.cout - c0)
+                self.conv(x, y.slice(c0, g), cw.cout_slice(c0, g), stride, pad, dil, flags, tag)
+            return
         self.keep.append(cw)
         if x.relud:
             assert flags & RELU_IN, f"{tag}: a post-ReLU buffer read by a conv that does not start with ReLU"
@@ -341,6 +357,18 @@ class Builder:
         self.keep.extend((w_dw, pw))
         if x.relud and (flags & RELU_IN):
             flags &= ~RELU_IN
+        if x.c > 256 and x.dtype == torch.bfloat16 and tc_available() and x.c % 8 == 0:
+            # wider than the fused tensor-core SepConv kernel takes (its pointwise GEMM has K = C <= 256; BASELINE
+            # config 5: C = 320 / 640): stand-alone depthwise (bf16 result = the fused kernel's rounding point), then the
+            # pointwise 1x1 + BN as a tcgen05 conv (split into 256-channel output groups by conv())
+            mid = self.scratch(x.n, x.h, x.w, x.c)
+            e = x.buf.element_size()
+            self._emit(lib.add_depthwise_fwd, (self._d(x), self._d(mid), w_dw.data_ptr(), k, flags & RELU_IN), tag + ".dw",
+                       dict(kernel="depthwise", flops=2 * x.n * x.h * x.w * x.c * k * k, bytes=2 * x.n * x.h * x.w * x.c * e),
+                       reads=(x,), writes=(mid,))
+            self.conv(mid, y, pw, 1, 0, 1, flags & ~RELU_IN, tag + ".pw")
+            self.release(mid)
+            return
         p = x.n * x.h * x.w
         ex = x.buf.element_size()
         # tensor-core path: bf16 NHWC input (TMA halo box), pointwise GEMM on tcgen05

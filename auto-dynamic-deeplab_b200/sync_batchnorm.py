@@ -47,6 +47,58 @@ def _desc(t: torch.Tensor) -> AddTensor:
     return AddTensor(t.data_ptr(), n, h, w, c, c, ADD_BF16 if t.dtype == torch.bfloat16 else ADD_F32)
 
 
+def batch_norm_forward(bn: nn.BatchNorm2d, x: torch.Tensor, relu: bool = False, sync: Optional[bool] = None,
+                       group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """BatchNorm2d forward of any `_BatchNorm` parameter holder through libadd_b200 (no ATen batch_norm): training mode
+    = batch statistics (+ running-statistics update), eval mode = running statistics; optional fused ReLU.
+    sync: True = statistics all-reduced over `group`, inv_std = clamp(var, eps)^-1/2 (batchnorm.py:113-125);
+    False = this rank's statistics, inv_std = (var + eps)^-1/2 (F.batch_norm, batchnorm.py:50-53);
+    None = synchronised iff a process group with more than one rank is initialised."""
+    if not x.is_cuda:
+        raise RuntimeError("add_b200 runs on CUDA tensors only (no CPU fallback)")
+    if x.dim() != 4 or x.shape[1] != bn.num_features:
+        raise ValueError(f"expected [N, {bn.num_features}, H, W], got {tuple(x.shape)}")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous(memory_format=torch.channels_last)          # zero copy when already NHWC
+    n, c, h, w = x.shape
+    stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    xd = _desc(x)
+    w_ptr = bn.weight.data_ptr() if bn.affine else None
+    b_ptr = bn.bias.data_ptr() if bn.affine else None
+    stats = torch.empty(2 * c, dtype=torch.float32, device=x.device)     # [mean | inv_std]
+    mean, inv_std = stats[:c], stats[c:]
+    if bn.training or not bn.track_running_stats:
+        ws_bytes = lib.add_bn_stats_workspace_bytes(n, h, w, c)
+        check(ws_bytes if ws_bytes < 0 else 0, "bn_stats_workspace_bytes")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        packed = torch.empty(2 * c + 1, dtype=torch.float32, device=x.device)
+        check(lib.add_bn_stats_fwd(ctypes.byref(xd), packed.data_ptr(), ws.data_ptr(), ws_bytes, stream), "bn_stats")
+        packed[-1] = float(n * h * w)
+        if sync is None:
+            sync = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if sync:
+            reduce_stats(packed, group)
+        momentum = 0.0
+        rm = rv = None
+        if bn.training and bn.track_running_stats:
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+            momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            rm, rv = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+        check(lib.add_bn_finalize(packed.data_ptr(), packed.data_ptr() + 8 * c, 0.0, c, float(bn.eps), float(momentum),
+                                  1 if sync else 0, rm, rv, mean.data_ptr(), inv_std.data_ptr(), stream), "bn_finalize")
+    else:
+        # eval: F.batch_norm with the running statistics (batchnorm.py:50-53); C-length vectors, plumbing
+        mean.copy_(bn.running_mean)
+        torch.rsqrt(bn.running_var + bn.eps, out=inv_std)
+    y = torch.empty_like(x)                                      # keeps channels_last
+    yd = _desc(y)
+    check(lib.add_bn_apply_fwd(ctypes.byref(xd), ctypes.byref(yd), mean.data_ptr(), inv_std.data_ptr(), w_ptr, b_ptr,
+                               RELU_OUT if relu else 0, stream), "bn_apply")
+    return y
+
+
 class SynchronizedBatchNorm2d(nn.BatchNorm2d):
     """Same constructor, parameters and state_dict keys as the reference class (a `_BatchNorm` subclass)."""
 
@@ -55,48 +107,5 @@ class SynchronizedBatchNorm2d(nn.BatchNorm2d):
         self.process_group = process_group
         self.force_sync = force_sync        # take the synchronised formulas even with one rank (tests)
 
-    def _synced(self) -> bool:
-        return self.force_sync or (dist.is_available() and dist.is_initialized() and
-                                   dist.get_world_size(self.process_group) > 1)
-
     def forward(self, x: torch.Tensor, relu: bool = False) -> torch.Tensor:
-        if not x.is_cuda:
-            raise RuntimeError("add_b200 runs on CUDA tensors only (no CPU fallback)")
-        if x.dim() != 4 or x.shape[1] != self.num_features:
-            raise ValueError(f"expected [N, {self.num_features}, H, W], got {tuple(x.shape)}")
-        if x.dtype not in (torch.float32, torch.bfloat16):
-            x = x.float()
-        x = x.contiguous(memory_format=torch.channels_last)          # zero copy when already NHWC
-        n, c, h, w = x.shape
-        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-        xd = _desc(x)
-        w_ptr = self.weight.data_ptr() if self.affine else None
-        b_ptr = self.bias.data_ptr() if self.affine else None
-        stats = torch.empty(2 * c, dtype=torch.float32, device=x.device)     # [mean | inv_std]
-        mean, inv_std = stats[:c], stats[c:]
-        if self.training:
-            ws_bytes = lib.add_bn_stats_workspace_bytes(n, h, w, c)
-            check(ws_bytes if ws_bytes < 0 else 0, "bn_stats_workspace_bytes")
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-            packed = torch.empty(2 * c + 1, dtype=torch.float32, device=x.device)
-            check(lib.add_bn_stats_fwd(ctypes.byref(xd), packed.data_ptr(), ws.data_ptr(), ws_bytes, stream), "bn_stats")
-            packed[-1] = float(n * h * w)
-            sync = self._synced()
-            if sync:
-                reduce_stats(packed, self.process_group)
-            if self.num_batches_tracked is not None:
-                self.num_batches_tracked += 1
-            momentum = self.momentum if self.momentum is not None else 1.0 / float(self.num_batches_tracked)
-            rm = self.running_mean.data_ptr() if self.track_running_stats else None
-            rv = self.running_var.data_ptr() if self.track_running_stats else None
-            check(lib.add_bn_finalize(packed.data_ptr(), packed.data_ptr() + 8 * c, 0.0, c, float(self.eps), float(momentum),
-                                      1 if sync else 0, rm, rv, mean.data_ptr(), inv_std.data_ptr(), stream), "bn_finalize")
-        else:
-            # eval: F.batch_norm with the running statistics (batchnorm.py:50-53); C-length vectors, plumbing
-            mean.copy_(self.running_mean)
-            torch.rsqrt(self.running_var + self.eps, out=inv_std)
-        y = torch.empty_like(x)                                      # keeps channels_last
-        yd = _desc(y)
-        check(lib.add_bn_apply_fwd(ctypes.byref(xd), ctypes.byref(yd), mean.data_ptr(), inv_std.data_ptr(), w_ptr, b_ptr,
-                                   RELU_OUT if relu else 0, stream), "bn_apply")
-        return y
+        return batch_norm_forward(self, x, relu, True if self.force_sync else None, self.process_group)

@@ -120,6 +120,11 @@ int add_sepconv_half_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, const 
                             const void* w_pw_packed, const float* bias, int k, uint32_t flags,
                             void* stream);
 
+/* Stand-alone depthwise k x k (stride 1, pad k/2; `nn.Conv2d(C, C, k, groups=C)`, operations.py:52,56), w_dw fp32
+ * [k][k][C], ReLU-on-load / ReLU-on-store flags: for SepConv halves wider than add_sepconv_half_tc_fwd takes (C > 256);
+ * the pointwise 1x1 + BN follows as an add_conv2d_tc_fwd over the bf16 result. */
+int add_depthwise_fwd(const add_tensor_t* x, const add_tensor_t* y, const float* w_dw, int k, uint32_t flags, void* stream);
+
 /* add_sepconv_half_tc_fwd scheduling: 1 = persistent warp-specialised pipeline (default), 0 = one tile per CTA. */
 int add_sepconv_tc_set_mode(int mode);
 

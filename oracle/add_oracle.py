@@ -78,9 +78,34 @@ class Arch:
 # primitives
 # --------------------------------------------------------------------------------------
 
+_BN_TRAIN = {"on": False, "momentum": 0.1}
+
+
+class bn_training:
+    """`with bn_training(momentum):` — every BatchNorm of the op functions below runs in TRAINING mode on one device:
+    batch statistics and an in-place update of the `running_mean` / `running_var` tensors of the state dict
+    (F.batch_norm(training=True), the path SynchronizedBatchNorm2d takes when it is not replicated by DataParallel,
+    sync_batchnorm/batchnorm.py:50-53).  SURVEY §8f row 1 (training forward of the operators)."""
+
+    def __init__(self, momentum: float = 0.1):
+        self.momentum = momentum
+
+    def __enter__(self):
+        self.prev = dict(_BN_TRAIN)
+        _BN_TRAIN.update(on=True, momentum=self.momentum)
+        return self
+
+    def __exit__(self, *exc):
+        _BN_TRAIN.update(self.prev)
+        return False
+
+
 def _bn(sd: SD, p: str, x: torch.Tensor, eps: float = BN_EPS) -> torch.Tensor:
     """Eval-mode BatchNorm2d (SynchronizedBatchNorm2d falls through to F.batch_norm in
-    eval / single-device mode: sync_batchnorm/batchnorm.py:50-53)."""
+    eval / single-device mode: sync_batchnorm/batchnorm.py:50-53); batch statistics under `bn_training`."""
+    if _BN_TRAIN["on"]:
+        return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'],
+                            sd.get(p + '.weight'), sd.get(p + '.bias'), True, _BN_TRAIN["momentum"], eps)
     return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'],
                         sd.get(p + '.weight'), sd.get(p + '.bias'), False, 0.0, eps)
 

@@ -206,11 +206,37 @@ def gen_syncbn():
     print("syncbn.npz", len(g), "arrays")
 
 
+def gen_train_ops():
+    """The conv operators in TRAINING mode (module.train(): batch statistics, running statistics updated), the
+    unmodified reference modules on one device."""
+    g = {}
+    for name in util.TRAIN_OP_CASES:
+        spec = util.OP_CASES[name]
+        ours, x = util.make_op_case(name)
+        kind, args = spec["kind"], spec["args"]
+        if kind == "OPS":
+            ref = ref_ops.OPS[args[0]](args[1], args[2] if len(args) > 2 else 1, BN, 1e-5, 0.1, True)
+        else:
+            ref = getattr(ref_ops, kind)(*args, BN)
+        ref.load_state_dict(ours.state_dict(), strict=True)
+        ref.train()
+        with torch.no_grad():
+            y = ref(x)
+        g[name + "/y"] = f32(y)
+        for k, v in ref.state_dict().items():
+            if "running_" in k:
+                g[f"{name}/sd/{k}"] = f32(v)
+    np.savez_compressed(OUT / "train_ops.npz", **g)
+    print("train_ops.npz", len(g), "arrays")
+
+
 if __name__ == "__main__":
     if "--only-syncbn" in sys.argv:
         gen_syncbn()
+        gen_train_ops()
         sys.exit(0)
     gen_ops()
     gen_nets()
     gen_siblings()
     gen_syncbn()
+    gen_train_ops()

@@ -87,6 +87,10 @@ CASES = [
     (40, 40, 5, 1, 4, 2, 131, 300, RELU_IN | ACCUMULATE),
     (80, 80, 5, 1, 4, 2, 250, 128, RELU_IN),
     (40, 40, 5, 1, 2, 1, 243, 256, 0),
+    # more than 256 output channels (BASELINE config 5: C = 320 / 640): one tcgen05 launch per 256-channel output group
+    (320, 320, 3, 1, 2, 2, 8, 16, RELU_IN),
+    (640, 640, 5, 1, 4, 2, 6, 9, RELU_IN | ACCUMULATE),
+    (1600, 256, 1, 1, 0, 1, 5, 12, RELU_IN | RELU_OUT),
 ]
 
 
@@ -240,6 +244,31 @@ def test_sepconv_half_tc_matches_torch(case, out_dtype, mode, contig):
 
 
 # ---- fused stem0 (stem_tc.cu): NCHW fp32 image -> conv3x3 s2 + bias + ReLU -> NHWC bf16 -------------------
+@pytest.mark.parametrize("k", [3, 5])
+@pytest.mark.parametrize("C", [320, 640])
+def test_sepconv_half_wider_than_the_fused_kernel(k, C):
+    """C = 320 / 640 (BASELINE config 5, F = 40 / 80 at the deep strides): wider than the fused tensor-core SepConv
+    kernel takes, so a half runs as a stand-alone depthwise (bf16 result, the fused kernel's rounding point) plus the
+    pointwise 1x1 on the tcgen05 path in 256-channel output groups.  Same reference and tolerance as the fused kernel."""
+    H, W, flags = 9, 14, RELU_IN | RELU_OUT
+    g = torch.Generator().manual_seed(71 + k + C)
+    x_buf = torch.randn(2, H, W, C, generator=g).to(torch.bfloat16).to(DEV)
+    w_dw = (torch.randn(k, k, C, generator=g) / k).to(DEV)
+    w_pw = _bf16_exact(torch.randn(C, C, generator=g) / C ** 0.5).to(DEV)
+    bias = torch.randn(C, generator=g).to(DEV)
+    cw = ConvWeights(w_pw.t().reshape(C, C, 1, 1).contiguous())
+    cw.bias = bias
+    b = Builder(DEV, torch.bfloat16, record=True)
+    y = torch.zeros(2, H, W, C, dtype=torch.bfloat16, device=DEV)
+    b.sepconv_half(View(x_buf, 0, C), View(y, 0, C), w_dw.contiguous(), cw, k, flags)
+    kernels = [l[3]["kernel"] for l in b.launches]
+    assert kernels[0] == "depthwise" and set(kernels[1:]) == {"conv2d_tc"} and len(kernels) == 1 + (C + 255) // 256
+    rt.Plan(b).run_eager()
+    torch.cuda.synchronize()
+    ref = _sep_reference(x_buf, w_dw, w_pw, bias, k, flags, y)
+    assert util.rel_err(y.float(), ref) < 2 ** -7
+
+
 @pytest.mark.parametrize("hw", [(32, 64), (33, 65), (48, 300), (17, 513)])
 def test_stem_tc_matches_torch(hw):
     """vs plain PyTorch fp32 conv on bf16-rounded image and weights (what the kernel multiplies); output is bf16:

@@ -62,12 +62,20 @@ def test_generation_invalidates_on_load():
     assert rt.generation() > g0
 
 
-def test_training_mode_is_refused():
+def test_training_mode_is_refused_where_it_is_not_built():
+    """The conv modules have a batch-statistics training forward (tests/test_train_forward.py); what has none (the
+    pools, whole networks and their plans) refuses `.train()` instead of silently running eval-mode arithmetic."""
     import pytest
-    m, x = util.make_op_case("dil_conv_3x3_c40")
-    m.train()
+    import add_b200
+    m = add_b200.OPS["avg_pool_3x3"](8, 1, torch.nn.BatchNorm2d, 1e-5, 0.1, True).train()
     with pytest.raises(NotImplementedError):
-        m(x)
+        m(torch.zeros(1, 8, 4, 4))
+    net = util.make_net(util.NET_CASES["searched-dense-C2"]).train()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 33, 65))
+    m2, x = util.make_op_case("dil_conv_3x3_c40")
+    with pytest.raises(RuntimeError):          # it has a training forward, but no CPU path exists
+        m2.train()(x)
 
 
 def _fake_plan(specs):

@@ -210,3 +210,9 @@ def make_syncbn_case(name):
         state["weight"] = torch.rand(C, generator=g) + 0.5
         state["bias"] = torch.randn(C, generator=g) * 0.2
     return shards, state
+
+
+# ---- training-mode forward of the conv operators (batch statistics) -------------------
+TRAIN_OP_CASES = ["sep_conv_3x3_c40", "sep_conv_5x5_c40", "sep_conv_3x3_c80", "dil_conv_3x3_c40", "dil_conv_5x5_c40",
+                  "dil_conv_5x5_c80", "relu_conv_bn_1x1", "relu_conv_bn_3x3_s2", "factorized_reduce_even",
+                  "factorized_reduce_odd", "double_factorized_reduce"]

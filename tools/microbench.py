@@ -41,6 +41,19 @@ def cases():
     return out
 
 
+def sweep_cases():
+    """BASELINE config 5: sep_conv / dil_conv 3x3 / 5x5 and ASPP_train at F = 20 / 40 / 80 across strides 4 / 8 / 16 / 32
+    (C = F * stride / 4, spatial = 1024x2048 / stride, 8 images; ASPP input = 5C channels on 4 images)."""
+    out = []
+    for F in (20, 40, 80):
+        for lvl, stride in enumerate((4, 8, 16, 32)):
+            C, h, w = F * (1 << lvl), 1024 // stride, 2048 // stride
+            for op in ("sep_conv_3x3", "sep_conv_5x5", "dil_conv_3x3", "dil_conv_5x5"):
+                out.append((f"F{F}_s{stride}_{op}", "op", (op, C, 8, h, w)))
+            out.append((f"F{F}_s{stride}_aspp_in{5 * C}", "aspp", (5 * C, 4, h, w)))
+    return out
+
+
 import os
 
 
@@ -48,23 +61,42 @@ def main():
     if os.environ.get("ADD_SEPCONV_MODE"):
         from add_b200._lib import lib
         assert lib.add_sepconv_tc_set_mode(int(os.environ["ADD_SEPCONV_MODE"])) == 0
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    argv = sys.argv[1:]
+    args = [a for i, a in enumerate(argv) if not a.startswith("--") and not (i > 0 and argv[i - 1] == "--reps")]
     filt = args[0] if args else ""
     reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 20
     once = "--once" in sys.argv
     nbuf = 1 if once else 4
     torch.manual_seed(0)
-    for name, kind, a in cases():
+    for name, kind, a in (sweep_cases() if "--sweep" in sys.argv else cases()):
         if filt not in name:
             continue
         b = Builder(DEV, torch.bfloat16, record=True)
-        if kind == "op":
+        if kind == "aspp":
+            cin, n, h, w = a
+            try:
+                m = add_b200.ASPP_train(cin, 256, BN, mult=1).eval().to(DEV)
+                for _ in range(nbuf):
+                    x = View(torch.randn(n, h, w, cin, device=DEV).to(torch.bfloat16)); b.keep.append(x.buf)
+                    y = b.alloc(n, h, w, 256)
+                    m.emit(b, x, y, 0)
+            except Exception as e:      # shapes outside what the kernels take are reported, not hidden
+                print(f"{name:22s} unsupported: {type(e).__name__}: {str(e)[:90]}")
+                continue
+            kind = "done"
+        if kind == "done":
+            pass
+        elif kind == "op":
             op, C, n, h, w = a
             m = add_b200.OPS[op](C, 1, BN, 1e-5, 0.1, True).eval().to(DEV)
-            for _ in range(nbuf):
-                x = View(torch.randn(n, h, w, C, device=DEV).to(torch.bfloat16)); b.keep.append(x.buf)
-                y = b.alloc(n, h, w, C)
-                m.emit(b, x, y, 0)
+            try:
+                for _ in range(nbuf):
+                    x = View(torch.randn(n, h, w, C, device=DEV).to(torch.bfloat16)); b.keep.append(x.buf)
+                    y = b.alloc(n, h, w, C)
+                    m.emit(b, x, y, 0)
+            except Exception as e:
+                print(f"{name:22s} unsupported: {type(e).__name__}: {str(e)[:90]}")
+                continue
         elif kind == "pw":
             cin, cout, n, h, w = a
             m = add_b200.ReLUConvBN(cin, cout, 1, 1, 0, BN).eval().to(DEV)
@@ -89,7 +121,11 @@ def main():
                 y = b.alloc(n, ho, wo, cout)
                 b.conv(x, y, cw, stride, pad, dil, flags, name)
         plan = rt.Plan(b)
-        plan.run_eager()
+        try:
+            plan.run_eager()
+        except Exception as e:
+            print(f"{name:22s} unsupported: {type(e).__name__}: {str(e)[:90]}")
+            continue
         torch.cuda.synchronize()
         if once:
             continue
