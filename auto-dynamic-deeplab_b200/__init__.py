@@ -15,6 +15,7 @@ from .aspp_train import ASPP_train
 from .decoder import Decoder
 from .ADD import ADD, Cell, EDM
 from .baseline_model import Baselin_Model, AutoDeepLab, Cell_baseline, Cell_AutoDeepLab
+from .cell_level_search import MixedOp
 from .metrics import Evaluator
 from .factory import build_add, Args, synthetic_batch
 from .pipeline import HostPipeline, ResidentPipeline

@@ -26,6 +26,8 @@ from .sync_batchnorm import SynchronizedBatchNorm2d, batch_norm_forward  # noqa:
 class AddModule(nn.Module):
     """Base: generation-tracked weight cache + the emit/forward protocol."""
 
+    STATELESS = False          # True: no parameters / statistics, so .train() and .eval() compute the same thing
+
     def __init__(self):
         super().__init__()
         self._prep_gen = -1
@@ -62,7 +64,7 @@ class AddModule(nn.Module):
         return n, c, h, w
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self.training:
+        if self.training and not self.STATELESS:
             y = self._forward_train(x)
             rt.bump_generation()          # running statistics moved: folded eval-mode weights / recorded plans are stale
             return y
@@ -223,6 +225,7 @@ class Identity(AddModule):
 
 class Zero(AddModule):
     """operations.py:74-83 ('none'): x[:, :, ::stride, ::stride].mul(0.) — IEEE x*0, so NaN/inf propagate as in torch."""
+    STATELESS = True
 
     def __init__(self, stride):
         super().__init__()
@@ -242,6 +245,7 @@ class _Pool3x3(AddModule):
     """nn.AvgPool2d(3, stride, padding=1, count_include_pad=False) / nn.MaxPool2d(3, stride, padding=1)
     (operations.py:9-10) — parameter-free, one launch."""
     MODE = 0
+    STATELESS = True
 
     def __init__(self, stride):
         super().__init__()

@@ -165,6 +165,23 @@ def apply_primitive(sd: SD, p: str, name: str, x: torch.Tensor, stride: int = 1)
     raise KeyError(name)
 
 
+def mixed_op(sd: SD, p: str, x: torch.Tensor, weights: torch.Tensor, training: bool = True, stride: int = 1) -> torch.Tensor:
+    """cell_level_search.py:10-29 — MixedOp: sum_k w_k * op_k(x) over genotypes.PRIMITIVES (ops built with affine=False,
+    the two pools followed by BatchNorm(affine=False): keys `<p>._ops.<k>.1.running_*`); `training=False` applies only
+    the argmax primitive (:27-28).  BatchNorm mode follows `bn_training` like every op function here."""
+    from_names = ['none', 'max_pool_3x3', 'avg_pool_3x3', 'skip_connect', 'sep_conv_3x3', 'sep_conv_5x5',
+                  'dil_conv_3x3', 'dil_conv_5x5']            # modeling/genotypes.py:5-14
+
+    def one(k):
+        name, q = from_names[k], f'{p}._ops.{k}'
+        if 'pool' in name:
+            return _bn(sd, q + '.1', apply_primitive(sd, q + '.0', name, x, stride))
+        return apply_primitive(sd, q, name, x, stride)
+    if not training:
+        return one(int(torch.argmax(weights)))
+    return sum(w * one(k) for k, w in enumerate(weights))
+
+
 def factorized_reduce(sd: SD, p: str, x: torch.Tensor, step: int = 2) -> torch.Tensor:
     """operations.py:86-101 (step 2) / :104-119 (DoubleFactorizedReduce, step 4):
     ReLU; conv_1 samples the lattice at offset 0, conv_2 the lattice at offset step/2

@@ -230,13 +230,39 @@ def gen_train_ops():
     print("train_ops.npz", len(g), "arrays")
 
 
+def gen_mixed_op():
+    """MixedOp (cell_level_search.py:10-29), the unmodified reference: weighted sum in eval and in training mode
+    (batch statistics, running statistics updated) and the argmax path (`training=False`)."""
+    from modeling.cell_level_search import MixedOp as RefMixedOp
+    g = {}
+    for name, spec in util.MIXED_OP_CASES.items():
+        ours, x, w = util.make_mixed_op_case(name)
+        for mode in ("eval", "train"):
+            ref = RefMixedOp(spec["C"], 1, BN)
+            ref.load_state_dict(ours.state_dict(), strict=True)
+            ref.train(mode == "train")
+            with torch.no_grad():
+                g[f"{name}/{mode}/y"] = f32(ref(x, w))
+                if mode == "eval":
+                    g[f"{name}/eval/y_argmax"] = f32(ref(x, w, training=False))
+            if mode == "train":
+                for k, v in ref.state_dict().items():
+                    if "running_" in k:
+                        g[f"{name}/train/sd/{k}"] = f32(v)
+        g[name + "/w"] = f32(w)
+    np.savez_compressed(OUT / "mixed_op.npz", **g)
+    print("mixed_op.npz", len(g), "arrays")
+
+
 if __name__ == "__main__":
     if "--only-syncbn" in sys.argv:
         gen_syncbn()
         gen_train_ops()
+        gen_mixed_op()
         sys.exit(0)
     gen_ops()
     gen_nets()
     gen_siblings()
     gen_syncbn()
     gen_train_ops()
+    gen_mixed_op()

@@ -63,13 +63,13 @@ def test_generation_invalidates_on_load():
 
 
 def test_training_mode_is_refused_where_it_is_not_built():
-    """The conv modules have a batch-statistics training forward (tests/test_train_forward.py); what has none (the
-    pools, whole networks and their plans) refuses `.train()` instead of silently running eval-mode arithmetic."""
+    """The conv modules have a batch-statistics training forward (tests/test_train_forward.py); what has none (ASPP,
+    decoder, whole networks and their plans) refuses `.train()` instead of silently running eval-mode arithmetic."""
     import pytest
     import add_b200
-    m = add_b200.OPS["avg_pool_3x3"](8, 1, torch.nn.BatchNorm2d, 1e-5, 0.1, True).train()
+    m = add_b200.ASPP_train(40, 32, torch.nn.BatchNorm2d, depth=32).train()
     with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 8, 4, 4))
+        m(torch.zeros(1, 40, 4, 4))
     net = util.make_net(util.NET_CASES["searched-dense-C2"]).train()
     with pytest.raises(NotImplementedError):
         net(torch.zeros(1, 3, 33, 65))

@@ -216,3 +216,27 @@ def make_syncbn_case(name):
 TRAIN_OP_CASES = ["sep_conv_3x3_c40", "sep_conv_5x5_c40", "sep_conv_3x3_c80", "dil_conv_3x3_c40", "dil_conv_5x5_c40",
                   "dil_conv_5x5_c80", "relu_conv_bn_1x1", "relu_conv_bn_3x3_s2", "factorized_reduce_even",
                   "factorized_reduce_odd", "double_factorized_reduce"]
+
+
+# ---- MixedOp (cell_level_search.py:10-29) ------------------------------------------------
+MIXED_OP_CASES = {
+    "c16": dict(C=16, x=(2, 16, 9, 11), seed=41),
+    "c40": dict(C=40, x=(2, 40, 13, 17), seed=42),
+}
+
+
+def make_mixed_op_case(name):
+    """(our MixedOp with randomised conv weights and running statistics, input, softmax edge weights)."""
+    spec = MIXED_OP_CASES[name]
+    torch.manual_seed(spec["seed"])
+    m = add_b200.MixedOp(spec["C"], 1, BN)
+    g = torch.Generator().manual_seed(spec["seed"] + 100)
+    with torch.no_grad():
+        for k, v in m.state_dict().items():
+            if k.endswith("running_mean"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+            elif k.endswith("running_var"):
+                v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+    x = torch.randn(*spec["x"], generator=g)
+    w = torch.softmax(torch.randn(8, generator=g), dim=0)
+    return m, x, w
