@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-Xptxas=-v",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("ADD_NVCC_EXTRA", "").split()
 
 
 def find_nvcc() -> str:

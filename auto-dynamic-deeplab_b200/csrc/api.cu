@@ -35,4 +35,13 @@ extern "C" int add_set_pdl(int on) { g_add_pdl = on ? 1 : 0; return ADD_OK; }
 int g_add_grid_pct = 100;
 /* Tuning: persistent kernels launch (pct/100) x their default CTA count (default 100), leaving room for kernels of
  * other streams of the captured graph to co-reside. */
-extern "C" int add_set_persistent_grid_pct(int pct) { if (pct < 10 || pct > 100) return ADD_ERR_BAD_ARG; g_add_grid_pct = pct; return ADD_OK; }
+int g_add_conv_grid_pct = 100;     /* same, for the small 1x1 / few-tap convs of conv2d_tc_persistent_kernel only */
+extern "C" int add_set_persistent_grid_pct(int pct) {
+  /* pct in 10..100 scales every persistent kernel; 1000 * c + p (c, p in 10..100) scales the small convs by c % and the rest by p % */
+  int conv = 0;
+  if (pct >= 1000) { conv = pct / 1000; pct %= 1000; }
+  if (pct < 10 || pct > 100 || (conv != 0 && (conv < 10 || conv > 100))) return ADD_ERR_BAD_ARG;
+  g_add_grid_pct = pct;
+  g_add_conv_grid_pct = conv ? conv : 100;
+  return ADD_OK;
+}

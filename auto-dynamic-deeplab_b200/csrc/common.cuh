@@ -10,6 +10,7 @@
 // last CUDA runtime/driver error seen by this thread's launches (api.cu); add_last_cuda_error() reports it
 extern thread_local int g_add_last_cuda_error;
 extern int g_add_grid_pct;  // api.cu: persistent-grid scale (tuning)
+extern int g_add_conv_grid_pct;   // api.cu: same, small convs of the persistent conv kernel only
 extern int g_add_pdl;      // api.cu: 1 = launch the tcgen05 kernels with programmatic stream serialization
 #define ADD_RETURN_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ == cudaSuccess) return ADD_OK; \
     g_add_last_cuda_error = (int)e_; return ADD_ERR_CUDA; } while (0)

@@ -857,6 +857,7 @@ int g_conv_cluster = 1;             // 1 = cluster-of-2 weight multicast for the
 int g_halo_pairs = 1;               // 1 = row pairs in the persistent halo kernel (mode bit 7 clears)
 int g_halo_quads = 1;               // 1 = row quads for the streamed-weight 5x5s (mode bit 9 clears)
 int g_conv_mt2 = 1;                 // 1 = two pixel tiles per weight tile for the weight-heavy convs (mode bit 6 clears)
+int g_conv_mt2_small = 0;           // 1 = two pixel tiles per stage also for the resident-weight 1x1s (mode bit 10 sets; experiment)
 int g_halo_stream_persistent = 0;   // 1 = use the persistent halo kernel also when the weights stream through a ring (tuning)
 int g_persistent = 1;  // 1 = persistent warp-specialised kernel for the non-halo path (default), 0 = one tile per CTA
 int g_halo_mode = 1;   // 0 = per-tap A tiles only, 1 = halo-resident A (measured on B200: base_offset must stay 0 — the
@@ -986,7 +987,8 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
     int sms = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     // MT = 2 (two pixel tiles per weight tile) for the weight-heavy big convs: streamed weights, N_pad >= 128, many tiles
-    const int mt = (g_conv_mt2 && !p.b_resident && p.n_pad >= 128 && grid >= 4ll * sms) ? 2 : 1;
+    int mt = (g_conv_mt2 && !p.b_resident && p.n_pad >= 128 && grid >= 4ll * sms) ? 2 : 1;
+    if (g_conv_mt2_small && p.b_resident && p.taps == 1 && grid >= 4ll * sms && 4 * p.tmem_cols <= 512) mt = 2;   // experiment (mode bit 10)
     const size_t sbytes = (size_t)mt * TC_A_BYTES + (p.b_resident ? 0 : p.b_bytes);
     // two CTAs per SM when a 4-deep ring fits in half the shared memory and TMEM (4 accumulators) allows it
     const bool two = mt == 1 && fixed + 4 * sbytes <= 100u * 1024u && 4 * p.tmem_cols <= 512;
@@ -1007,6 +1009,7 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
       });
       const long long units = (grid + mt - 1) / mt;
       long long g = (long long)sms * (two ? 2 : 1) * g_add_grid_pct / 100;
+      if (units <= 16ll * sms) g = g * g_add_conv_grid_pct / 100;      // small problems: leave SMs to the other stream's kernel
       if (g > units) g = units;
       if (g < 1) g = 1;
       // cluster of 2 with multicast weight halves: the N_pad = 256 convs (ASPP / decoder 3x3) that sit at the L2 ceiling
@@ -1097,6 +1100,7 @@ extern "C" int add_conv2d_tc_set_halo_mode(int mode) {
   g_conv_cluster = (mode & 256) ? 0 : 1;              // bit 8 set = no clusters / multicast
   g_halo_pairs = (mode & 128) ? 0 : 1;                // bit 7 set = no row pairs in the persistent halo kernel
   g_halo_quads = (mode & 512) ? 0 : 1;                // bit 9 set = no row quads (pairs only)
+  g_conv_mt2_small = (mode & 1024) ? 1 : 0;           // bit 10 set = two pixel tiles per stage for the resident 1x1s
   g_conv_mt2 = (mode & 64) ? 0 : 1;                   // bit 6 set = one pixel tile per weight tile everywhere
   g_halo_stream_persistent = (mode & 32) ? 1 : 0;     // bit 5 set = persistent halo kernel with streamed weights
   mode &= 15;

@@ -211,13 +211,16 @@ __device__ __forceinline__ void stage_bias(float* bias_s, const TcParams& p, int
 
 // spin on an mbarrier with a short sleep between polls: for waiters with slack (producers, epilogue warps), so
 // their polling does not take issue slots from the compute warps of the same SM sub-partition
+#ifndef ADD_SLEEP_NS
+#define ADD_SLEEP_NS 128
+#endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   while (true) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
-    __nanosleep(128);
+    __nanosleep(ADD_SLEEP_NS);
   }
 }
 

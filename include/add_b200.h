@@ -57,7 +57,8 @@ int  add_device_sm_count(void);       /* SMs of the current device, <0 on error 
 /* 1 (default): the tcgen05 kernels are launched with programmatic dependent launch — their prologue overlaps the
  * previous kernel's tail and they wait for it (griddepcontrol.wait) before touching activations; 0: plain launches. */
 int  add_set_pdl(int on);
-/* Tuning: persistent kernels launch pct % of their default CTA count (10..100; default 100). */
+/* Tuning: persistent kernels launch pct % of their default CTA count (10..100; default 100); 1000 * c + p scales the
+ * small convs of the persistent conv kernel by c % and every other persistent kernel by p %. */
 int  add_set_persistent_grid_pct(int pct);
 
 /* ---- layout / dtype edges --------------------------------------------------------------- */
