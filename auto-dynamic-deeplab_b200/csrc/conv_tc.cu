@@ -857,6 +857,7 @@ int g_conv_cluster = 1;             // 1 = cluster-of-2 weight multicast for the
 int g_halo_pairs = 1;               // 1 = row pairs in the persistent halo kernel (mode bit 7 clears)
 int g_halo_quads = 1;               // 1 = row quads for the streamed-weight 5x5s (mode bit 9 clears)
 int g_conv_mt2 = 1;                 // 1 = two pixel tiles per weight tile for the weight-heavy convs (mode bit 6 clears)
+int g_conv_flatten_1x1 = 1;         // 1 = stride-1 1x1 convs tile the flattened N*H*W pixel range (mode bit 11 clears)
 int g_conv_mt2_small = 0;           // 1 = two pixel tiles per stage also for the resident-weight 1x1s (mode bit 10 sets; experiment)
 int g_halo_stream_persistent = 0;   // 1 = use the persistent halo kernel also when the weights stream through a ring (tuning)
 int g_persistent = 1;  // 1 = persistent warp-specialised kernel for the non-halo path (default), 0 = one tile per CTA
@@ -907,6 +908,18 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
   else ADD_CHECK_SUP(y->pix_stride % 4 == 0 && ((uintptr_t)y->ptr % 16) == 0);
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) { g_add_last_cuda_error = (int)cudaErrorSymbolNotFound; return ADD_ERR_CUDA; }
+
+  // A stride-1 1x1 conv does not care where rows or images end: it is a GEMM over the N*H*W pixels.  Described as ONE
+  // row of N*H*W pixels, every 128-pixel tile is full except the last — with (row, 128-column) tiles a 129-wide map
+  // (the stride-8 level of the authors' 1025x2049 evaluation size) wastes half of every second tile.
+  add_tensor_t xf, yf;
+  if (g_conv_flatten_1x1 && kh == 1 && kw == 1 && stride == 1 && pad == 0 && !(bias && bias_image_stride != 0) &&
+      x->h == y->h && x->w == y->w && (long long)x->n * x->h * x->w < (1ll << 31)) {
+    xf = *x; yf = *y;
+    xf.w = yf.w = x->n * x->h * x->w;
+    xf.n = yf.n = 1; xf.h = yf.h = 1;
+    x = &xf; y = &yf;
+  }
 
   TcParams p;
   p.bias_img_stride = bias ? bias_image_stride : 0;
@@ -1101,6 +1114,7 @@ extern "C" int add_conv2d_tc_set_halo_mode(int mode) {
   g_halo_pairs = (mode & 128) ? 0 : 1;                // bit 7 set = no row pairs in the persistent halo kernel
   g_halo_quads = (mode & 512) ? 0 : 1;                // bit 9 set = no row quads (pairs only)
   g_conv_mt2_small = (mode & 1024) ? 1 : 0;           // bit 10 set = two pixel tiles per stage for the resident 1x1s
+  g_conv_flatten_1x1 = (mode & 2048) ? 0 : 1;         // bit 11 set = (row, column) tiles for the 1x1s too
   g_conv_mt2 = (mode & 64) ? 0 : 1;                   // bit 6 set = one pixel tile per weight tile everywhere
   g_halo_stream_persistent = (mode & 32) ? 1 : 0;     // bit 5 set = persistent halo kernel with streamed weights
   mode &= 15;
