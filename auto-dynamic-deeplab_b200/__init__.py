@@ -17,7 +17,7 @@ from .ADD import ADD, Cell, EDM
 from .baseline_model import Baselin_Model, AutoDeepLab, Cell_baseline, Cell_AutoDeepLab
 from .cell_level_search import MixedOp
 from .metrics import Evaluator
-from .factory import build_add, Args, synthetic_batch
+from .factory import build_add, Args, synthetic_batch, synthetic_batch_u8, normalize_u8_hwc_host
 from .pipeline import HostPipeline, ResidentPipeline
 from .parallel import shard_range, env_rank_world, all_reduce_confusion
 

@@ -447,6 +447,41 @@ widen_labels_kernel(const uint8_t* __restrict__ src, long long* __restrict__ dst
 }
 }  // namespace
 
+// ---- loader edge: uint8 HWC image -> normalised fp32 NCHW (dataloaders/custom_transforms.py:17-24 + :39) -------
+// Cityscapes images are uint8 PNGs; the reference normalises them on the host (img /= 255.0 in float32, then
+// img -= mean and img /= std, which numpy evaluates in float64 because mean / std are float64 arrays, rounding to
+// float32 after each) and ships 12 bytes per pixel to the GPU.  Here the 3 bytes travel and the same arithmetic —
+// same operation order and roundings, so bit-identical — runs on the device: 4x fewer PCIe / host-DRAM bytes.
+namespace {
+__global__ void __launch_bounds__(256)
+normalize_u8_hwc_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long hw, double m0, double m1, double m2,
+                        double s0, double s1, double s2) {
+  const int n = blockIdx.y;
+  const uint8_t* in = src + (size_t)n * hw * 3;
+  float* out = dst + (size_t)n * hw * 3;
+  for (long long p = blockIdx.x * 256ll + threadIdx.x; p < hw; p += (long long)gridDim.x * 256) {
+    const float r = __fdiv_rn((float)in[3 * p], 255.0f), g = __fdiv_rn((float)in[3 * p + 1], 255.0f), b = __fdiv_rn((float)in[3 * p + 2], 255.0f);
+    const float r1 = (float)((double)r - m0), g1 = (float)((double)g - m1), b1 = (float)((double)b - m2);
+    out[p] = (float)((double)r1 / s0);
+    out[hw + p] = (float)((double)g1 / s1);
+    out[2 * hw + p] = (float)((double)b1 / s2);
+  }
+}
+}  // namespace
+
+extern "C" int add_normalize_u8_hwc_to_nchw(const uint8_t* src, float* dst, int n, int h, int w, double mean0, double mean1,
+                                            double mean2, double std0, double std1, double std2, void* stream) {
+  ADD_CHECK_ARG(src && dst && n > 0 && h > 0 && w > 0 && std0 != 0.0 && std1 != 0.0 && std2 != 0.0);
+  ADD_CHECK_SUP(n < 65536);
+  const long long hw = (long long)h * w;
+  long long blocks = (hw + 255) / 256;
+  const long long cap = (148ll * 16 + n - 1) / n;
+  if (blocks > cap) blocks = cap;
+  normalize_u8_hwc_kernel<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, hw, mean0,
+                                                                                                        mean1, mean2, std0, std1, std2);
+  ADD_RETURN_LAUNCH();
+}
+
 extern "C" int add_widen_labels_u8(const uint8_t* src, int64_t* dst, int64_t n, void* stream) {
   ADD_CHECK_ARG(src && dst && n >= 0);
   ADD_CHECK_SUP(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0);

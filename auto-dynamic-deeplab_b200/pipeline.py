@@ -23,8 +23,14 @@ class HostPipeline:
     edm=None  → multi-exit `ADD.evaluate` (eval.py:165-193, every exit scored);
     edm given → EDM-gated early exit per image, `ADD.dynamic_evaluate` (eval.py:195-221)."""
 
-    def __init__(self, net, edm=None, threshold: float = 1.0, exit_mode: str = "reference", depth: int = 3):
+    CITYSCAPES_NORM = ((0.29866842, 0.30135223, 0.30561872), (0.23925215, 0.23859318, 0.2385942))   # cityscapes.py:53-54
+
+    def __init__(self, net, edm=None, threshold: float = 1.0, exit_mode: str = "reference", depth: int = 3,
+                 image_norm=CITYSCAPES_NORM):
+        """image_norm = (mean, std): used when a batch's images arrive as uint8 [N,H,W,3] (the PNG bytes): they cross
+        PCIe at 3 bytes per pixel and are normalised on the device exactly as the reference's host transforms do."""
         self.net, self.edm, self.threshold, self.exit_mode = net, edm, float(threshold), exit_mode
+        self.image_norm = image_norm
         # 3 slots: batch i+2 is being copied in while the trunk of batch i+1 and the exit heads of batch i compute
         self.depth = max(2 if edm is None else 3, int(depth))
         self.device = next(net.parameters()).device
@@ -36,11 +42,12 @@ class HostPipeline:
         self.d2h_bytes = 0
 
     def _ensure_slots(self, x: torch.Tensor, gt: torch.Tensor) -> None:
-        if self._slots is not None and self._slots[0]["x"].shape == x.shape:
+        shape = (x.shape[0], 3, x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else tuple(x.shape)
+        if self._slots is not None and tuple(self._slots[0]["x"].shape) == shape:
             return
         self._slots = []
         for _ in range(self.depth):
-            self._slots.append(dict(x=torch.empty(x.shape, dtype=torch.float32, device=self.device),
+            self._slots.append(dict(x=torch.empty(shape, dtype=torch.float32, device=self.device), x_u8=None,
                                     gt=torch.empty(gt.shape, dtype=torch.int64, device=self.device),
                                     gt_u8=(torch.empty(gt.shape, dtype=torch.uint8, device=self.device)
                                            if gt.dtype == torch.uint8 else None),
@@ -49,7 +56,19 @@ class HostPipeline:
     def _prefetch(self, slot: dict, x: torch.Tensor, gt: torch.Tensor) -> None:
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot["free"])        # the compute that last read this slot is done
-            slot["x"].copy_(x, non_blocking=True)
+            if x.dtype == torch.uint8:
+                # uint8 HWC images: 3 bytes per pixel over PCIe, normalised to fp32 NCHW on the device
+                if x.dim() != 4 or x.shape[3] != 3:
+                    raise ValueError(f"uint8 images must be [N,H,W,3], got {tuple(x.shape)}")
+                if slot["x_u8"] is None or slot["x_u8"].shape != x.shape:
+                    slot["x_u8"] = torch.empty(x.shape, dtype=torch.uint8, device=self.device)
+                slot["x_u8"].copy_(x, non_blocking=True)
+                (m0, m1, m2), (s0, s1, s2) = self.image_norm
+                check(lib.add_normalize_u8_hwc_to_nchw(slot["x_u8"].data_ptr(), slot["x"].data_ptr(), x.shape[0], x.shape[1],
+                                                       x.shape[2], m0, m1, m2, s0, s1, s2,
+                                                       ctypes.c_void_p(self.copy_stream.cuda_stream)), "normalize_u8")
+            else:
+                slot["x"].copy_(x, non_blocking=True)
             if gt.dtype == torch.uint8:
                 # labels travel at their native 1 byte per pixel and are widened on the device (add_widen_labels_u8)
                 if slot["gt_u8"] is None:

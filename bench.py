@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--cpu-images", type=int, default=12, help="images in the bounded CPU-baseline sample")
     ap.add_argument("--label-dtype", default="uint8", choices=["uint8", "int64"],
                     help="dtype of the HOST labels fed to the e2e loop (uint8 = Cityscapes PNG depth, widened on the device)")
+    ap.add_argument("--image-dtype", default="uint8", choices=["uint8", "fp32"],
+                    help="dtype of the HOST images fed to the e2e loop: uint8 HWC (the PNG bytes; normalised on the device "
+                         "with the reference loader's arithmetic) or the loader's normalised fp32 NCHW")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel launch table (JSON) here")
     ap.add_argument("--profile-step", action="store_true",
                     help="for `ncu --profile-from-start off`: warm up, then run ONE step between cudaProfilerStart/Stop "
@@ -303,7 +306,12 @@ def main_b200(a):
     torch.manual_seed(203)
     edm = add_b200.EDM().eval().to(dev)
     B, H, W = a.batch, a.height, a.width
-    x_host, gt_host = add_b200.synthetic_batch(B, H, W, seed=1234 + rank, pin=True)
+    if a.image_dtype == "uint8":
+        # the batch as the PNG decoder delivers it (uint8 HWC); x_host = the reference loader's normalisation of it
+        img_host, x_host, gt_host = add_b200.synthetic_batch_u8(B, H, W, seed=1234 + rank, pin=True)
+    else:
+        x_host, gt_host = add_b200.synthetic_batch(B, H, W, seed=1234 + rank, pin=True)
+        img_host = x_host
     x_dev, gt_dev = x_host.to(dev), gt_host.to(dev)
 
     # gate values for this batch → threshold between the two middle values (half the images exit early)
@@ -341,7 +349,7 @@ def main_b200(a):
 
     def run_e2e(steps):
         out = None
-        for out, _ in pipe.evaluate((x_host, gt_feed) for _ in range(steps)):
+        for out, _ in pipe.evaluate((img_host, gt_feed) for _ in range(steps)):
             pass
         return out
 
@@ -454,8 +462,8 @@ def main_b200(a):
                                                                            tensor_core_path=bool(rt.tc_available())),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_step,
                         "d2h_bytes_per_step": d2h_step + B * 4, "ms_per_step": ms_e2e / a.steps,
-                        "host_label_dtype": a.label_dtype,
-                        "api": "add_b200.HostPipeline.evaluate (pinned host batches, H2D of batch i+1 overlapped with compute of batch i)"},
+                        "host_label_dtype": a.label_dtype, "host_image_dtype": a.image_dtype,
+                        "api": "add_b200.HostPipeline.evaluate (pinned host batches over 3 slots: H2D of batch i+2 and the trunk of batch i+1 in flight while the host decides batch i's exits)"},
                 "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
         sys.stdout.flush()

@@ -202,6 +202,12 @@ int add_upsample_argmax_fwd(const add_tensor_t* x, int H, int W, const int64_t* 
                             int64_t* pred_out, int64_t* cm_out, float* entropy_out,
                             void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Loader edge: uint8 HWC images [n][h][w][3] (PIL / Cityscapes PNG layout) -> normalised fp32 NCHW [n][3][h][w], the
+ * tensor eval.py:175 copies to the device.  Same arithmetic as the reference's host transforms (Normalize then ToTensor,
+ * dataloaders/custom_transforms.py:17-24, :39: /255 in float32, -mean and /std through float64), bit-identical. */
+int add_normalize_u8_hwc_to_nchw(const uint8_t* src, float* dst, int n, int h, int w, double mean0, double mean1, double mean2,
+                                 double std0, double std1, double std2, void* stream);
+
 /* ---- label edge: uint8 labels (Cityscapes PNG depth, 255 = ignore) -> int64 [n] as the Evaluator path reads them.
  * The loader-side H2D then moves 1 byte per pixel instead of 8 (cityscapes.py:85-91 encodes ids into 0..18 / 255). */
 int add_widen_labels_u8(const uint8_t* src, int64_t* dst, int64_t n, void* stream);

@@ -669,6 +669,21 @@ def randomize_bn_(sd: SD, seed: int = 7) -> SD:
     return sd
 
 
+CITYSCAPES_MEAN = (0.29866842, 0.30135223, 0.30561872)     # dataloaders/datasets/cityscapes.py:53
+CITYSCAPES_STD = (0.23925215, 0.23859318, 0.2385942)       # dataloaders/datasets/cityscapes.py:54
+
+
+def normalize_u8_hwc(img_u8: np.ndarray, mean=CITYSCAPES_MEAN, std=CITYSCAPES_STD) -> np.ndarray:
+    """dataloaders/custom_transforms.py:17-24 (Normalize) + :39 (ToTensor's HWC -> CHW): uint8 [N,H,W,3] ->
+    float32 [N,3,H,W], with numpy's own type promotion (/= 255.0 stays float32, -= / /= with the float64 mean / std
+    tuples go through float64)."""
+    img = np.array(img_u8).astype(np.float32)
+    img /= 255.0
+    img -= mean
+    img /= std
+    return np.ascontiguousarray(img.transpose((0, 3, 1, 2)))
+
+
 def synthetic_batch(n: int, h: int, w: int, seed: int = 1234, num_class: int = 19):
     """image ~ N(0,1); labels randint(0,19) with 10 % pixels = 255 (ignore)."""
     g = torch.Generator().manual_seed(seed)

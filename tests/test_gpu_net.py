@@ -163,6 +163,28 @@ def test_host_pipeline_matches_direct_calls():
         assert torch.equal(cm_g, net.evaluate(x.to(DEV), gt.to(DEV)).cpu())
 
 
+def test_host_pipeline_uint8_images():
+    """uint8 HWC host images (3 bytes per pixel over PCIe, normalised on the device with the reference loader's arithmetic)
+    give exactly the matrices of direct calls on the host-normalised fp32 NCHW tensors."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec).to(DEV)
+    edm = util.make_edm().to(DEV)
+    g = torch.Generator().manual_seed(9)
+    imgs = [torch.randint(0, 256, (3, 33, 65, 3), generator=g, dtype=torch.uint8) for _ in range(4)]
+    gts = [util.make_input(3, 33, 65, seed=500 + i)[1] for i in range(4)]
+    xs = [add_b200.normalize_u8_hwc_host(im) for im in imgs]
+    _, _, confs = net.dynamic_evaluate(xs[0].to(DEV), gts[0].to(DEV), -1e30, edm)
+    thr = sorted(float(c) for c in confs)[1]
+    want = [net.dynamic_evaluate(x.to(DEV), gt.to(DEV), thr, edm) for x, gt in zip(xs, gts)]
+    want = [(cm.cpu().clone(), list(flags)) for cm, flags, _ in want]
+    pipe = add_b200.HostPipeline(net, edm, thr)
+    got = [(cm.clone(), list(flags)) for cm, flags in
+           pipe.evaluate((im.pin_memory(), gt.to(torch.uint8).pin_memory()) for im, gt in zip(imgs, gts))]
+    assert len(got) == len(want)
+    for (cm_g, fl_g), (cm_w, fl_w) in zip(got, want):
+        assert fl_g == fl_w and torch.equal(cm_g[0], cm_w)
+
+
 def test_resident_pipeline_matches_direct_calls():
     """ResidentPipeline (device batches cycling over three stable buffers; the trunk of batch i+1 is enqueued before
     the host reads batch i's gate values) yields exactly what blocking dynamic_evaluate calls return, in order,

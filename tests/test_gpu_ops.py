@@ -157,3 +157,22 @@ def test_accumulate_and_slice_writes():
     got = cat.nchw().cpu()
     assert util.rel_err(got[:, 40:80], want) < F32_TOL
     assert bool((got[:, :40] == 7.0).all()) and bool((got[:, 80:] == 7.0).all())
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 7), (1, 33, 65), (3, 64, 128)])
+def test_normalize_u8_hwc_is_bit_identical_to_the_reference_loader(shape):
+    """uint8 HWC -> fp32 NCHW on the device = dataloaders/custom_transforms.py:17-24 + :39 (numpy, as the oracle restates
+    it) bit for bit; the host helper used to synthesise bench batches computes the same values."""
+    import ctypes
+    from add_b200._lib import lib as _lib
+    n, h, w = shape
+    g = torch.Generator().manual_seed(3)
+    img = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8)
+    want = orc.normalize_u8_hwc(img.numpy())
+    assert np.array_equal(add_b200.normalize_u8_hwc_host(img).numpy(), want)
+    src = img.to(DEV)
+    dst = torch.empty(n, 3, h, w, dtype=torch.float32, device=DEV)
+    (m0, m1, m2), (s0, s1, s2) = orc.CITYSCAPES_MEAN, orc.CITYSCAPES_STD
+    assert _lib.add_normalize_u8_hwc_to_nchw(src.data_ptr(), dst.data_ptr(), n, h, w, m0, m1, m2, s0, s1, s2, None) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(dst.cpu().numpy(), want)
