@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product:
 only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
-``--impl reference`` legs may import it, and there only as the checker or the
-timed CPU baseline.  The product path (``auto-dynamic-deeplab_b200/``) never
+``--impl reference`` legs (plus the informational ``--impl torch_cuda`` comparator,
+which runs these same functions on cuda:0 as the stock-PyTorch baseline) may
+import it, and there only as the checker or the timed baseline.  The product path (``auto-dynamic-deeplab_b200/``) never
 imports this module and has no CPU fallback.
 
 What it is: a *functional* restatement, in plain fp32 PyTorch on the CPU, of the
