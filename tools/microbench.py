@@ -34,6 +34,11 @@ def cases():
             ("aspp_400to256_d12", "conv", (400, 256, 3, 1, 12, 12, 4, 256, 512, RELU_IN | RELU_OUT)),
             ("aspp_400to256_d12_norelu", "conv", (400, 256, 3, 1, 12, 12, 4, 256, 512, RELU_OUT)),
             ("dec_304to256_3x3", "conv", (304, 256, 3, 1, 1, 1, 4, 128, 256, RELU_IN | RELU_OUT)),
+            ("rowrate_dil3_c40", "conv", (40, 40, 3, 1, 2, 2, 8, 128, 256, 0)),
+            ("rowrate_dil3_c64", "conv", (64, 64, 3, 1, 2, 2, 8, 128, 256, 0)),
+            ("rowrate_dil3_c32", "conv", (32, 32, 3, 1, 2, 2, 8, 128, 256, 0)),
+            ("rowrate_dil5_c40", "conv", (40, 40, 5, 1, 4, 2, 8, 128, 256, 0)),
+            ("rowrate_dil5_c64", "conv", (64, 64, 5, 1, 4, 2, 8, 128, 256, 0)),
             ("bil_exit_63x127to256x512_c400", "bil", (400, 4, 63, 127, 256, 512)),
             ("bil_cellup_63x127to125x253_c400", "bil", (400, 4, 63, 127, 125, 253)),
             ("bil_dense_32x64to63x127_c160", "bil", (160, 4, 32, 64, 63, 127)),
