@@ -37,6 +37,10 @@ def cases():
             ("rowrate_dil3_c40", "conv", (40, 40, 3, 1, 2, 2, 8, 128, 256, 0)),
             ("rowrate_dil3_c64", "conv", (64, 64, 3, 1, 2, 2, 8, 128, 256, 0)),
             ("rowrate_dil3_c32", "conv", (32, 32, 3, 1, 2, 2, 8, 128, 256, 0)),
+            ("rowrate_dil3_c40_d1", "conv", (40, 40, 3, 1, 1, 1, 8, 128, 256, 0)),
+            ("rowrate_dil3_c40_d4", "conv", (40, 40, 3, 1, 4, 4, 8, 128, 256, 0)),
+            ("rowrate_dil3_c40_d8", "conv", (40, 40, 3, 1, 8, 8, 8, 128, 256, 0)),
+            ("rowrate_dil3_c64_d8", "conv", (64, 64, 3, 1, 8, 8, 8, 128, 256, 0)),
             ("rowrate_dil5_c40", "conv", (40, 40, 5, 1, 4, 2, 8, 128, 256, 0)),
             ("rowrate_dil5_c64", "conv", (64, 64, 5, 1, 4, 2, 8, 128, 256, 0)),
             ("bil_exit_63x127to256x512_c400", "bil", (400, 4, 63, 127, 256, 512)),
