@@ -30,7 +30,7 @@ __device__ __forceinline__ void warp_hist_add(unsigned int* hist, int bin, int l
 struct HeadParams {
   const float* x; int n, h, w, c, xs;      // low-res logits (fp32 NHWC)
   int H, W; float sh, sw;
-  const long long* gt; long long* pred;
+  const long long* gt; const uint8_t* gt8; long long* pred;      // labels: int64 (metrics.py:34-39) or uint8 (the PNG bytes, 255 = ignore)
   unsigned int* part_hist;                  // [n][B][bins]
   double* part_ent;                         // [n][B]
   int bins; int B; int want_ent;
@@ -89,8 +89,8 @@ upsample_argmax_kernel(const HeadParams p) {
         ent += (double)(-e * inv_logc);
       }
       if (p.pred) p.pred[(size_t)n * HW + pix] = arg;
-      if (do_hist && p.gt) {
-        long long g = p.gt[(size_t)n * HW + pix];
+      if (do_hist && (p.gt || p.gt8)) {
+        long long g = p.gt8 ? (long long)p.gt8[(size_t)n * HW + pix] : p.gt[(size_t)n * HW + pix];
         if (g >= 0 && g < p.c) bin = (int)g * p.c + arg;
       }
     }
@@ -186,8 +186,8 @@ upsample_argmax_runs_kernel(const HeadParams p) {
         }
         const size_t pix = (size_t)n * HW + (size_t)oy * p.W + ox;
         if (p.pred) p.pred[pix] = arg;
-        if (do_hist && p.gt) {
-          const long long g = __ldg(p.gt + pix);
+        if (do_hist && (p.gt || p.gt8)) {
+          const long long g = p.gt8 ? (long long)__ldg(p.gt8 + pix) : __ldg(p.gt + pix);
           if (g >= 0 && g < NC) bin = (int)g * NC + arg;
         }
       }
@@ -399,18 +399,34 @@ extern "C" int64_t add_head_workspace_bytes(int n, int H, int W, int num_class) 
   return hist + (int64_t)n * B * sizeof(double);
 }
 
+static int upsample_argmax_impl(const add_tensor_t* x, int H, int W, const int64_t* gt, const uint8_t* gt8,
+                                int64_t* pred_out, int64_t* cm_out, float* entropy_out,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+
 extern "C" int add_upsample_argmax_fwd(const add_tensor_t* x, int H, int W, const int64_t* gt,
                                        int64_t* pred_out, int64_t* cm_out, float* entropy_out,
                                        void* workspace, int64_t workspace_bytes, void* stream) {
+  return upsample_argmax_impl(x, H, W, gt, nullptr, pred_out, cm_out, entropy_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int add_upsample_argmax_u8_fwd(const add_tensor_t* x, int H, int W, const uint8_t* gt_u8,
+                                          int64_t* pred_out, int64_t* cm_out, float* entropy_out,
+                                          void* workspace, int64_t workspace_bytes, void* stream) {
+  return upsample_argmax_impl(x, H, W, nullptr, gt_u8, pred_out, cm_out, entropy_out, workspace, workspace_bytes, stream);
+}
+
+static int upsample_argmax_impl(const add_tensor_t* x, int H, int W, const int64_t* gt, const uint8_t* gt8,
+                                int64_t* pred_out, int64_t* cm_out, float* entropy_out,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
   ADD_CHECK_ARG(tensor_ok(x) && H > 0 && W > 0 && workspace);
-  ADD_CHECK_ARG(!(cm_out && !gt));
+  ADD_CHECK_ARG(!(cm_out && !gt && !gt8));
   ADD_CHECK_SUP(x->dtype == ADD_F32 && x->c <= MAX_CLASS);
   ADD_CHECK_SUP(!cm_out || x->c * x->c <= MAX_BINS);
   if (workspace_bytes < add_head_workspace_bytes(x->n, H, W, x->c)) return ADD_ERR_WORKSPACE;
   HeadParams p;
   p.x = (const float*)x->ptr; p.n = x->n; p.h = x->h; p.w = x->w; p.c = x->c; p.xs = x->pix_stride;
   p.H = H; p.W = W; p.sh = (float)x->h / (float)H; p.sw = (float)x->w / (float)W;
-  p.gt = (const long long*)gt; p.pred = (long long*)pred_out;
+  p.gt = (const long long*)gt; p.gt8 = gt8; p.pred = (long long*)pred_out;
   p.bins = x->c * x->c; p.B = head_blocks_per_image((long long)H * W, x->n);
   int64_t hist_bytes = ((int64_t)x->n * p.B * p.bins * sizeof(unsigned int) + 15) & ~15ll;
   p.part_hist = cm_out ? (unsigned int*)workspace : nullptr;

@@ -524,6 +524,6 @@ extern "C" int add_gather_images(const void* src, void* dst, const int32_t* idx_
   if (a % 16 == 0) launch_gather<uint4>(src, dst, idx_dev, count, bytes_per_image, s);
   else if (a % 8 == 0) launch_gather<uint2>(src, dst, idx_dev, count, bytes_per_image, s);
   else if (a % 4 == 0) launch_gather<uint32_t>(src, dst, idx_dev, count, bytes_per_image, s);
-  else return ADD_ERR_UNSUPPORTED;
+  else launch_gather<uint8_t>(src, dst, idx_dev, count, bytes_per_image, s);      // uint8 label slabs of odd-sized images
   ADD_RETURN_LAUNCH();
 }

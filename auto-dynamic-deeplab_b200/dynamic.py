@@ -179,7 +179,8 @@ class _EdmRunner:
     """Batched, per-image EDM-gated inference for one (input shape, precision, output mode)."""
 
     def __init__(self, net, shape, device, precision: str, edm, mode: str, exit_mode: str,
-                 bound: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None):
+                 bound: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None,
+                 label_dtype: torch.dtype = torch.int64):
         """bound = (x, target): record the plans directly on THESE device tensors (the caller promises to refill the
         same buffers for every call, as HostPipeline's slots do) — no copy into private static inputs."""
         self.generation = rt.generation()
@@ -200,8 +201,10 @@ class _EdmRunner:
         self.heads: Dict[Tuple[int, int], _Head] = {}
         self.gt_full: Optional[torch.Tensor] = None
         if mode == "evaluate":
+            # labels: the reference's int64 tensors, or uint8 (the PNG bytes: 8x less gather / histogram traffic)
+            self.label_dtype = label_dtype
             self.gt_full = (bound[1] if bound is not None else
-                            torch.empty((self.n, self.H, self.W), dtype=torch.int64, device=device))
+                            torch.empty((self.n, self.H, self.W), dtype=label_dtype, device=device))
         self.last_launches = 0
         self._side: Optional[torch.cuda.Stream] = None
         # pinned staging for the gate's host round trip (N floats down, a few index vectors up): no pageable copies
@@ -216,7 +219,7 @@ class _EdmRunner:
             out = b.raw((m, self.nc, self.H, self.W), torch.float32)
             b.upsample_logits(logits, out, self.H, self.W, "ADD.upsample_logits")
             return out
-        gt = b.raw((m, self.H, self.W), torch.int64)
+        gt = b.raw((m, self.H, self.W), self.label_dtype)
         owner.idx_gt = b.raw((m,), torch.int32, zero=True)          # ORIGINAL image ids of this plan's rows
         b.gather_images(self.gt_full, gt, owner.idx_gt, "dynamic.gather.gt")
         cm = b.raw((m, self.nc, self.nc), torch.int64)
@@ -350,16 +353,21 @@ class _EdmRunner:
 def _get_runner(net, x: torch.Tensor, edm, mode: str, exit_mode: str, target: Optional[torch.Tensor] = None,
                 bind_inputs: bool = False) -> _EdmRunner:
     prec = net.precision or rt.default_precision()
-    key = ("edm", tuple(x.shape), str(x.device), prec, id(edm), mode, exit_mode, bool(net.use_cuda_graph))
+    label_dtype = torch.int64
+    if target is not None:
+        if target.dtype not in (torch.int64, torch.uint8):
+            raise ValueError(f"labels must be int64 (metrics.py:34-39) or uint8, got {target.dtype}")
+        label_dtype = target.dtype
+    key = ("edm", tuple(x.shape), str(x.device), prec, id(edm), mode, exit_mode, bool(net.use_cuda_graph), label_dtype)
     bound = None
     if bind_inputs:
-        if not (x.dtype == torch.float32 and x.is_contiguous() and (target is None or (target.dtype == torch.int64 and target.is_contiguous()))):
-            raise ValueError("bind_inputs needs contiguous fp32 NCHW images and int64 labels")
+        if not (x.dtype == torch.float32 and x.is_contiguous() and (target is None or target.is_contiguous())):
+            raise ValueError("bind_inputs needs contiguous fp32 NCHW images and contiguous int64 / uint8 labels")
         key = key + (x.data_ptr(), 0 if target is None else target.data_ptr())
         bound = (x, target)
     r = net._plans.get(key)
     if r is None or r.generation != rt.generation():
-        r = _EdmRunner(net, tuple(x.shape), x.device, prec, edm, mode, exit_mode, bound)
+        r = _EdmRunner(net, tuple(x.shape), x.device, prec, edm, mode, exit_mode, bound, label_dtype)
         net._plans[key] = r
     return r
 

@@ -70,14 +70,17 @@ class HostPipeline:
             else:
                 slot["x"].copy_(x, non_blocking=True)
             if gt.dtype == torch.uint8:
-                # labels travel at their native 1 byte per pixel and are widened on the device (add_widen_labels_u8)
+                # labels travel at their native 1 byte per pixel; the gated path reads them as they are
+                # (add_upsample_argmax_u8_fwd), the multi-exit path widens them on the device (add_widen_labels_u8)
                 if slot["gt_u8"] is None:
                     slot["gt_u8"] = torch.empty(gt.shape, dtype=torch.uint8, device=self.device)
                 slot["gt_u8"].copy_(gt, non_blocking=True)
-                check(lib.add_widen_labels_u8(slot["gt_u8"].data_ptr(), slot["gt"].data_ptr(), gt.numel(),
-                                              ctypes.c_void_p(self.copy_stream.cuda_stream)), "widen_labels_u8")
+                if self.edm is None:
+                    check(lib.add_widen_labels_u8(slot["gt_u8"].data_ptr(), slot["gt"].data_ptr(), gt.numel(),
+                                                  ctypes.c_void_p(self.copy_stream.cuda_stream)), "widen_labels_u8")
             else:
                 slot["gt"].copy_(gt, non_blocking=True)
+            slot["labels_u8"] = gt.dtype == torch.uint8
             slot["ready"].record(self.copy_stream)
         self.h2d_bytes += x.numel() * x.element_size() + gt.numel() * gt.element_size()
 
@@ -131,7 +134,8 @@ class HostPipeline:
 
         def begin(slot):
             main.wait_event(slot["ready"])
-            return self.net.dynamic_evaluate_begin(slot["x"], slot["gt"], self.threshold, self.edm, self.exit_mode,
+            gt = slot["gt_u8"] if slot.get("labels_u8") else slot["gt"]
+            return self.net.dynamic_evaluate_begin(slot["x"], gt, self.threshold, self.edm, self.exit_mode,
                                                    bind_inputs=True)
 
         queued = [first]                                    # host batches whose H2D has been enqueued, not yet begun

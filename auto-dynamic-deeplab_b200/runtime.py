@@ -472,10 +472,12 @@ class Builder:
                         cm: Optional[torch.Tensor], ent: Optional[torch.Tensor], tag: str = "upsample_argmax") -> None:
         nbytes = lib.add_head_workspace_bytes(x.n, H, W, x.c)
         ws = self.raw((nbytes,), torch.uint8)
-        self._emit(lib.add_upsample_argmax_fwd,
+        u8 = gt is not None and gt.dtype == torch.uint8            # labels as the PNG bytes: 1 byte per pixel
+        assert gt is None or gt.dtype in (torch.uint8, torch.int64)
+        self._emit(lib.add_upsample_argmax_u8_fwd if u8 else lib.add_upsample_argmax_fwd,
                    (self._d(x), H, W, _ptr(gt), _ptr(pred), _ptr(cm), _ptr(ent), ws.data_ptr(), nbytes), tag,
                    dict(kernel="upsample_argmax", flops=8 * x.n * H * W * x.c,
-                        bytes=4 * x.n * x.h * x.w * x.c + x.n * H * W * (8 * (gt is not None) + 8 * (pred is not None))),
+                        bytes=4 * x.n * x.h * x.w * x.c + x.n * H * W * ((1 if u8 else 8) * (gt is not None) + 8 * (pred is not None))),
                    reads=(x, gt), writes=(pred, cm, ent, ws))
 
     def edm_mlp(self, pooled: torch.Tensor, n: int, ws: Sequence[torch.Tensor], out: torch.Tensor,

@@ -201,6 +201,10 @@ int64_t add_head_workspace_bytes(int n, int H, int W, int num_class);
 int add_upsample_argmax_fwd(const add_tensor_t* x, int H, int W, const int64_t* gt,
                             int64_t* pred_out, int64_t* cm_out, float* entropy_out,
                             void* workspace, int64_t workspace_bytes, void* stream);
+/* Same with uint8 labels (the Cityscapes PNG bytes; 255 = ignore, like any value >= num_class): 1 byte per pixel
+ * instead of the 8 of the int64 tensor the reference's Evaluator receives. */
+int add_upsample_argmax_u8_fwd(const add_tensor_t* x, int H, int W, const uint8_t* gt_u8, int64_t* pred_out,
+                               int64_t* cm_out, float* entropy_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Loader edge: uint8 HWC images [n][h][w][3] (PIL / Cityscapes PNG layout) -> normalised fp32 NCHW [n][3][h][w], the
  * tensor eval.py:175 copies to the device.  Same arithmetic as the reference's host transforms (Normalize then ToTensor,

@@ -163,6 +163,23 @@ def test_host_pipeline_matches_direct_calls():
         assert torch.equal(cm_g, net.evaluate(x.to(DEV), gt.to(DEV)).cpu())
 
 
+def test_dynamic_evaluate_uint8_labels_equal_int64_labels():
+    """uint8 labels (the PNG bytes, 255 = ignore) give the same per-image confusion matrices as the reference's int64
+    tensors — odd image size (33 x 65 = 2145 bytes per label slab: the byte-granular gather) and an even one."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec).to(DEV)
+    edm = util.make_edm().to(DEV)
+    for hw, seed in (((33, 65), 700), ((48, 80), 701)):
+        x, gt = util.make_input(3, *hw, seed=seed)
+        _, _, confs = net.dynamic_evaluate(x.to(DEV), gt.to(DEV), -1e30, edm)
+        thr = sorted(float(c) for c in confs)[1]
+        cm64, fl64, _ = net.dynamic_evaluate(x.to(DEV), gt.to(DEV), thr, edm)
+        cm8, fl8, _ = net.dynamic_evaluate(x.to(DEV), gt.to(torch.uint8).to(DEV), thr, edm)
+        assert list(fl64) == list(fl8) and 0 < sum(fl64) < 3
+        assert torch.equal(cm64, cm8)
+        assert int(cm8.sum()) == int((gt != 255).sum())
+
+
 def test_host_pipeline_uint8_images():
     """uint8 HWC host images (3 bytes per pixel over PCIe, normalised on the device with the reference loader's arithmetic)
     give exactly the matrices of direct calls on the host-normalised fp32 NCHW tensors."""
