@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--exit-mode", default="reference", choices=["reference", "forward"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--forward-only", action="store_true",
+                    help="informational: time ADD.evaluate (all exits, no gating) on the resident batch and exit")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="resident arm: one blocking dynamic_evaluate call per step instead of the software pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -258,7 +260,31 @@ def main_torch_cuda(a):
             one(s_ % 2, 1e30 if s_ % 2 == 0 else -1e30)
         torch.cuda.synchronize()
         res[name] = n_img / (time.perf_counter() - t0)
+    # the same network without gating, batched (ADD.forward on a.batch images -> argmax -> bincount per exit): what stock
+    # PyTorch achieves when it is allowed a full batch; compare with `bench.py --forward-only` of this repo
+    fwd = {}
+    xb, gb = add_b200.synthetic_batch(a.batch, a.height, a.width)
+    for name, dt in (("bf16", torch.bfloat16),):
+        sdd = {k: (v.to(dev).to(dt).contiguous(memory_format=torch.channels_last) if v.dim() == 4 else
+                   (v.to(dev).to(dt) if v.is_floating_point() else v.to(dev))) for k, v in sd.items()}
+        xd = xb.to(dev).to(dt).contiguous(memory_format=torch.channels_last)
+        gd = gb.to(dev)
+        m = (gd >= 0) & (gd < 19)
+
+        def fwd_step():
+            with torch.no_grad():
+                outs = orc.add_forward(sdd, arch, xd)
+                return [torch.bincount(19 * gd[m] + torch.argmax(o, 1)[m], minlength=361) for o in outs]
+        for _ in range(3):
+            fwd_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(max(a.steps, 2)):
+            fwd_step()
+        torch.cuda.synchronize()
+        fwd[name] = a.batch * max(a.steps, 2) / (time.perf_counter() - t0)
     line = {"metric": METRIC, "value": res["bf16"], "unit": UNIT, "impl": "torch_cuda", "n_gpus": 1, "steps": a.steps,
+            "forward_all_exits_batched_images_per_s": fwd,
             "warmup": max(a.warmup, 3), "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_name(a), note="stock PyTorch (cuDNN/ATen) eager on cuda:0, batch 1 per call as in eval.py:195-221, "
                            "channels_last, alternating early-exit / full-depth images"),
@@ -352,6 +378,26 @@ def main_b200(a):
         for out, _ in pipe.evaluate((img_host, gt_feed) for _ in range(steps)):
             pass
         return out
+
+    if a.forward_only:
+        # informational: ADD.evaluate (every exit, no gating: forward -> argmax -> confusion matrix per exit) on the
+        # resident batch — the counterpart of `--impl torch_cuda`'s batched forward number
+        for _ in range(3):
+            net.evaluate(x_dev, gt_dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            net.evaluate(x_dev, gt_dev)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps({"metric": "ADD 1024x2048 forward (all exits) images/sec", "value": B * a.steps / (ms / 1e3), "unit": UNIT,
+                          "impl": "b200", "mode": "forward_only", "ms_per_step": ms / a.steps, "dtype": a.precision,
+                          "config": workload_name(a)}), flush=True)
+        return 0
 
     if a.profile_step:
         for _ in range(max(a.warmup, 3)):
