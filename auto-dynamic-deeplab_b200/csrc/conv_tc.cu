@@ -262,7 +262,6 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
       if (p.b_resident) mbar_wait(bar_bres, 0);
       int s = 0; uint32_t ph = 0; int ti = 0;
       for (int uj = 0; uj < units_per_cta; ++uj, ++ti) {
-        const int u = (int)blockIdx.x + uj * (int)gridDim.x;
         const int ab = nbuf == 2 ? (ti & 1) : 0;
         const uint32_t tph = nbuf == 2 ? ((uint32_t)(ti >> 1) & 1u) : ((uint32_t)ti & 1u);
         mbar_wait(bar_tempty + 8 * ab, tph ^ 1u);
@@ -295,7 +294,6 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
       const int et = threadIdx.x - 64;
       int s = 0; uint32_t ph = 0;
       for (int uj = 0; uj < units_per_cta; ++uj) {
-        const int u = (int)blockIdx.x + uj * (int)gridDim.x;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(bar_full + 8 * s, ph);
           relu_sweep(ring_base + s * stage_bytes, MT * TC_A_BYTES, et);
@@ -312,7 +310,7 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
     pdl_wait();
     int ti = 0;
     for (int uj = 0; uj < units_per_cta; ++uj, ++ti) {
-        const int u = (int)blockIdx.x + uj * (int)gridDim.x;
+      const int u = (int)blockIdx.x + uj * (int)gridDim.x;
       const int ab = nbuf == 2 ? (ti & 1) : 0;
       const uint32_t tph = nbuf == 2 ? ((uint32_t)(ti >> 1) & 1u) : ((uint32_t)ti & 1u);
       mbar_wait_relaxed(bar_tfull + 8 * ab, tph);

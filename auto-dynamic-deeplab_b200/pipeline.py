@@ -1,9 +1,11 @@
 """Host-fed evaluation loop — what `eval.py::Evaluation.validation` / `.dynamic_inference`
 (eval.py:165-230) do around the model: for every batch from the loader copy image + label to the
-device, run the network, argmax, add to the confusion matrix.  Here the loop is double-buffered:
-the H2D copy of batch i+1 runs on a side stream while batch i computes, and only the per-image
-confusion matrices (N x 19 x 19 int64) come back over PCIe.  PyTorch supplies pinned memory,
-streams and events; all compute is libadd_b200."""
+device, run the network, argmax, add to the confusion matrix.  Here the loop runs over three slots:
+the H2D copy of batch i+2 (copy stream) and the trunk of batch i+1 are in flight while the host
+decides batch i's exits, and only the per-image confusion matrices (N x 19 x 19 int64) come back
+over PCIe.  Images may arrive as the loader's fp32 NCHW tensors or as uint8 HWC (normalised on the
+device), labels as int64 or uint8.  PyTorch supplies pinned memory, streams and events; all
+compute is libadd_b200."""
 from __future__ import annotations
 
 from typing import Iterable, Iterator, List, Optional, Tuple
