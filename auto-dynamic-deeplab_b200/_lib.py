@@ -66,6 +66,7 @@ _SIGS = {
     "add_scale_fwd": (c_int, [TP, TP, c_float, c_int, c_uint32, c_void_p]),
     "add_bilinear_fwd": (c_int, [TP, TP, c_uint32, c_void_p]),
     "add_gather_images": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    "add_gather_images_view": (c_int, [TP, TP, c_void_p, c_void_p]),
     "add_global_avgpool_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "add_global_avgpool_fwd": (c_int, [TP, c_void_p, c_uint32, c_void_p, c_int64, c_void_p]),
     "add_edm_mlp_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 6 + [c_void_p, c_void_p]),

@@ -515,6 +515,40 @@ void launch_gather(const void* src, void* dst, const int32_t* idx, int count, in
 }
 }  // namespace
 
+// channel-slice variant: dst[j][p][0..c) = src[idx[j]][p][0..c) for NHWC views (possibly slices of wider buffers) —
+// gathers only the live channels (the 48-channel low-level slot of the decoder's 304-channel concat buffer)
+namespace {
+__global__ void __launch_bounds__(256)
+gather_view_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ idx, long long pixels,
+                   int vec_per_pix, long long src_img_vec, long long dst_img_vec, int src_pix_vec, int dst_pix_vec) {
+  const int j = blockIdx.y;
+  const uint4* s = src + (size_t)idx[j] * src_img_vec;
+  uint4* d = dst + (size_t)j * dst_img_vec;
+  const long long total = pixels * vec_per_pix;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long p = i / vec_per_pix;
+    const int v = (int)(i - p * vec_per_pix);
+    d[p * dst_pix_vec + v] = __ldg(s + p * src_pix_vec + v);
+  }
+}
+}  // namespace
+
+extern "C" int add_gather_images_view(const add_tensor_t* src, const add_tensor_t* dst, const int32_t* idx_dev, void* stream) {
+  ADD_CHECK_ARG(tensor_ok(src) && tensor_ok(dst) && idx_dev);
+  ADD_CHECK_ARG(src->h == dst->h && src->w == dst->w && src->c == dst->c && src->dtype == dst->dtype);
+  const size_t e = dtype_size(src->dtype);
+  ADD_CHECK_SUP((src->c * e) % 16 == 0 && (src->pix_stride * e) % 16 == 0 && (dst->pix_stride * e) % 16 == 0 &&
+                ((uintptr_t)src->ptr % 16) == 0 && ((uintptr_t)dst->ptr % 16) == 0 && dst->n < 65536);
+  const long long pixels = (long long)src->h * src->w;
+  const int vpp = (int)(src->c * e / 16);
+  long long bx = (pixels * vpp + 255) / 256;
+  if (bx > 148 * 4) bx = 148 * 4;
+  gather_view_kernel<<<dim3((unsigned)bx, (unsigned)dst->n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const uint4*)src->ptr, (uint4*)dst->ptr, idx_dev, pixels, vpp, pixels * (long long)(src->pix_stride * e / 16),
+      pixels * (long long)(dst->pix_stride * e / 16), (int)(src->pix_stride * e / 16), (int)(dst->pix_stride * e / 16));
+  ADD_RETURN_LAUNCH();
+}
+
 extern "C" int add_gather_images(const void* src, void* dst, const int32_t* idx_dev, int count,
                                  int64_t bytes_per_image, void* stream) {
   ADD_CHECK_ARG(src && dst && idx_dev && count > 0 && bytes_per_image > 0);

@@ -56,12 +56,22 @@ def _alloc_state_like(b: Builder, st: dict, m: int, need_two: bool) -> dict:
     return new
 
 
+def _low_slot(cat: View) -> View:
+    """The low-level slice of the decoder's concat buffer (decoder.py:26: cat(x[256], low_level[48]))."""
+    from .decoder import ASPP_C, LOW_LEVEL_C
+    return cat.slice(ASPP_C, LOW_LEVEL_C)
+
+
 def _emit_state_gather(b: Builder, src: dict, dst: dict, idx: torch.Tensor) -> None:
     done = set()
     for (name, s), (_, d) in zip(_state_items(src), _state_items(dst)):
         if id(d.buf) in done:
             continue
         done.add(id(d.buf))
+        if name == "low_cat":
+            # only the low-level slot of the decoder's concat buffer is live here (the ASPP part is written later)
+            b.gather_view(_low_slot(s), _low_slot(d), idx, "dynamic.gather.low_cat")
+            continue
         b.gather_images(s.buf, d.buf, idx, "dynamic.gather." + name)
 
 
@@ -146,7 +156,7 @@ class _Head:
         low_src = seg.state["low_cat"]
         low = View(b.raw((m,) + tuple(low_src.buf.shape[1:]), low_src.buf.dtype))
         b.gather_images(y_src.buf, y.buf, self.idx, "dynamic.gather.exit_feature")
-        b.gather_images(low_src.buf, low.buf, self.idx, "dynamic.gather.low_cat")
+        b.gather_view(_low_slot(low_src), _low_slot(low), self.idx, "dynamic.gather.low_cat")
         # conv_aspp_iter == k: every earlier exit was skipped (ADD.py:422)
         logits = net._emit_exit_lowres(b, y, dict(low_cat=low), i, runner.early_aspp_size, k, True, True)
         self.out = runner.emit_head_output(b, logits, m, self)

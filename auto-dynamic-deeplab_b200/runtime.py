@@ -432,6 +432,14 @@ class Builder:
         self._emit(lib.add_gather_images, (src.data_ptr(), dst.data_ptr(), idx.data_ptr(), dst.shape[0], per), tag,
                    dict(kernel="gather_images", flops=0, bytes=2 * per * dst.shape[0]), reads=(src, idx), writes=(dst,))
 
+    def gather_view(self, src: View, dst: View, idx: torch.Tensor, tag: str = "gather_view") -> None:
+        """dst image j = src image idx[j], only the views' channels (both may be slices of wider buffers)."""
+        assert (src.h, src.w, src.c, src.dtype) == (dst.h, dst.w, dst.c, dst.dtype) and idx.dtype == torch.int32
+        self.keep.append(idx)
+        e = src.buf.element_size()
+        self._emit(lib.add_gather_images_view, (self._d(src), self._d(dst), idx.data_ptr()), tag,
+                   dict(kernel="gather_images", flops=0, bytes=2 * dst.n * dst.h * dst.w * dst.c * e), reads=(src, idx), writes=(dst,))
+
     def gap(self, x: View, out: torch.Tensor, flags: int = 0, tag: str = "gap") -> None:
         nbytes = lib.add_global_avgpool_workspace_bytes(x.n, x.h, x.w, x.c)
         ws = self.raw((max(int(nbytes), 16),), torch.uint8)

@@ -169,6 +169,9 @@ int add_bilinear_set_mode(int mode);
  * slabs dst[j] = src[idx[j]], j < count; idx lives on the device so the launch is graph-replayable. */
 int add_gather_images(const void* src, void* dst, const int32_t* idx_dev, int count,
                       int64_t bytes_per_image, void* stream);
+/* Same for NHWC views: dst image j = src image idx[j] restricted to the views' channel range (dst->n images are
+ * written; src and dst may be channel slices of wider buffers with different pixel strides). */
+int add_gather_images_view(const add_tensor_t* src, const add_tensor_t* dst, const int32_t* idx_dev, void* stream);
 
 /* ---- global average pool (aspp_train.py:49, ADD.py:522): out[n][c] fp32 = mean_hw relu?(x).
  * Two deterministic stages (per-split partial sums in the workspace, fixed-order final sum). */
