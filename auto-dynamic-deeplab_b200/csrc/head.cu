@@ -228,10 +228,21 @@ head_finalize_kernel(const unsigned int* __restrict__ part_hist, const double* _
   if (cm_out) {
     for (int i0 = 0; i0 < bins; i0 += 32 * 4) {
       long long s[4] = {0, 0, 0, 0};
-      for (int b = warp; b < B; b += HD_WARPS) {
-        const unsigned int* row = part_hist + ((size_t)n * B + b) * bins;
+      // four partial rows per trip: 16 independent loads in flight per thread (the merge is a chain of L2 round trips —
+      // one row per trip made this kernel 40 us for 2 x 148 rows of 361 counters; integer sums, any order is exact)
+      for (int b = warp; b < B; b += 4 * HD_WARPS) {
+        unsigned int v[4][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + lane; if (i < bins) s[u] += __ldg(row + i); }
+        for (int r = 0; r < 4; ++r) {
+          const int br = b + r * HD_WARPS;
+          const unsigned int* row = part_hist + ((size_t)n * B + (br < B ? br : b)) * bins;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + lane; v[r][u] = (br < B && i < bins) ? __ldg(row + i) : 0u; }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) s[u] += v[r][u];
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + lane; if (i < bins) red[warp][i] = s[u]; }
