@@ -80,7 +80,10 @@ bilinear_kernel(const TI* __restrict__ x, TO* __restrict__ y, int H, int W, int 
 // are a contiguous range found by walking from an under-estimate); every output is the same expression as in
 // bilinear_pixel.  Results are bit-identical to the generic kernel's, borders (clamped sources) included.
 __device__ __forceinline__ int bilinear_first_out(int cell, float scale, int in_size, int out_size) {
-  // smallest output index whose source index i0 is >= cell
+  // smallest output index whose source index i0 is >= cell.  Cell 0 also owns the clamped outputs (source coordinate
+  // < 0 -> index 0), so it starts at output 0 whatever the scale (the estimate below is only an under-estimate for
+  // cell >= 1: with scale factors above ~6 it would skip cell 0's first outputs)
+  if (cell <= 0) return 0;
   int e = (int)floorf((static_cast<float>(cell) + 0.5f) / scale - 0.5f) - 1;
   e = e < 0 ? 0 : e;
   while (e < out_size) {

@@ -87,7 +87,7 @@ def test_bilinear_matches_numpy_oracle(hw_in, hw_out):
 
 @pytest.mark.parametrize("hw_in,hw_out", [((2, 2), (8, 8)), ((5, 9), (20, 36)), ((16, 33), (32, 66)), ((63, 127), (256, 512)),
                                           ((63, 127), (125, 253)), ((32, 64), (63, 127)), ((1, 5), (4, 20)), ((3, 3), (5, 6)),
-                                          ((7, 1), (29, 3))])
+                                          ((7, 1), (29, 3)), ((2, 3), (41, 50)), ((8, 16), (64, 128)), ((4, 8), (63, 127))])
 @pytest.mark.parametrize("flags", [0, 1, 3], ids=["plain", "relu_in", "relu_in_out"])
 def test_bilinear_upscale_kernel_equals_generic_kernel(hw_in, hw_out, flags):
     """bf16 upscales by >= 1.5x take the source-cell kernel: bit-identical to the generic per-pixel kernel (same
