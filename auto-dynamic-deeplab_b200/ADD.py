@@ -385,7 +385,7 @@ class ADD(AddModule):
         plan = self._get_plan(x, "forward")
         plan.set_input(x)
         plan.main.run()
-        return list(plan.outputs)
+        return plan.fresh_logits()
 
     def evaluate(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """Fused eval.py:178-185: forward → per-exit argmax → per-exit confusion matrix, without
@@ -404,7 +404,7 @@ class ADD(AddModule):
         plan = self._get_plan(x, "get_feature")
         plan.set_input(x)
         plan.main.run()
-        return plan.outputs[0], plan.feature.nchw()
+        return plan.fresh_logits()[0], plan.fresh_feature()
 
     def dynamic_inference(self, x: torch.Tensor, threshold=1.0, confidence='edm', edm=False):
         """ADD.py:379-488 (batch-1 semantics).  Returns (y, earlier_exit, seconds, confidence_value)."""
@@ -467,7 +467,8 @@ class _NetPlan:
         dtype = rt.act_dtype(precision)
         b = Builder(device, dtype, record=True)
         self.x_static = b.raw(shape, torch.float32)
-        self.outputs: List[torch.Tensor] = []
+        self.lowres: List[View] = []       # fp32 decoder-resolution logits per exit (plan buffers)
+        self.out_shape = (n, net._num_classes, H, W)
         self.cm = None
         self.feature = None
         nc = net._num_classes
@@ -488,27 +489,47 @@ class _NetPlan:
                 if net.network_arch[i] != net.network_arch[-1]:
                     it += 1
                 if kind == "forward":
-                    out = b.raw((n, nc, H, W), torch.float32)
-                    b.upsample_logits(logits, out, H, W, "ADD.upsample_logits")
-                    self.outputs.append(out)
+                    self.lowres.append(logits)
                 else:
                     b.upsample_argmax(logits, H, W, self.gt_static, None, self.cm[e], None, "ADD.upsample_argmax_cm")
                 e += 1
         elif kind == "get_feature":
             aspp_size = net._aspp_size((H, W), net.network_arch[-1])        # ADD.py:329-330
-            i = net.C_index[0]
+            i = min(net.C_index)        # the reference takes the first exit in ASCENDING layer order (ADD.py:366)
             net._emit_trunk(b, self.x_static, 0, i, st)
             self.feature = net._feature(st, i)
-            logits = net._emit_exit_lowres(b, self.feature, st, i, aspp_size, 0)
-            out = b.raw((n, nc, H, W), torch.float32)
-            b.upsample_logits(logits, out, H, W, "ADD.upsample_logits")
-            self.outputs.append(out)
+            self.lowres.append(net._emit_exit_lowres(b, self.feature, st, i, aspp_size, 0))
         else:
             raise ValueError(kind)
         self.builder = b
         self.main = Plan(b)
         if net.use_cuda_graph:
             self.main.capture()
+
+    # The reference returns FRESH tensors from forward / get_feature (`o1 = model(a); o2 = model(b)` must not alias).
+    # The recorded plan ends at the decoder-resolution logits; the final x8 bilinear (decoder.py:28) is launched eagerly
+    # after the replay into newly allocated NCHW fp32 tensors — same kernel count as recording it, no copy.
+    def fresh_logits(self) -> List[torch.Tensor]:
+        dev = self.x_static.device
+        s = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        n, nc, H, W = self.out_shape
+        outs = []
+        for lg in self.lowres:
+            out = torch.empty(self.out_shape, dtype=torch.float32, device=dev)
+            d = lg.desc()
+            check(lib.add_upsample_logits_nchw(ctypes.byref(d), out.data_ptr(), H, W, s), "ADD.upsample_logits")
+            outs.append(out)
+        return outs
+
+    def fresh_feature(self) -> torch.Tensor:
+        """The raw exit feature as a fresh NCHW fp32 tensor (ADD.py:366-377 returns `x` itself)."""
+        f = self.feature
+        dev = self.x_static.device
+        out = torch.empty((f.n, f.c, f.h, f.w), dtype=torch.float32, device=dev)
+        d = f.desc()
+        check(lib.add_nhwc_to_nchw(ctypes.byref(d), out.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+              "ADD.feature_nchw")
+        return out
 
     def set_input(self, x: torch.Tensor, target: Optional[torch.Tensor] = None) -> None:
         self.x_static.copy_(x)        # API-edge copy into the plan's static input buffer

@@ -72,8 +72,8 @@ _SIGS = {
     "add_edm_mlp_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 6 + [c_void_p, c_void_p]),
     "add_upsample_logits_nchw": (c_int, [TP, c_void_p, c_int, c_int, c_void_p]),
     "add_head_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
-    "add_upsample_argmax_fwd": (c_int, [TP, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
-    "add_upsample_argmax_u8_fwd": (c_int, [TP, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "add_upsample_argmax_fwd": (c_int, [TP, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "add_upsample_argmax_u8_fwd": (c_int, [TP, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "add_normalize_u8_hwc_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [ctypes.c_double] * 6 + [c_void_p]),
     "add_widen_labels_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "add_confusion_workspace_bytes": (c_int64, [c_int64, c_int]),

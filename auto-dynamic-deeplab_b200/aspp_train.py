@@ -37,8 +37,9 @@ class ASPP_train(AddModule):
         self.cw_out = ConvWeights(self.conv1.weight, self.bn1)
         d = self._depth
         # the 1x1 over the concatenation, split: rows of the four spatial branches / rows of the image-pool branch
-        self.cw_out_main = ConvWeights.from_folded(self.cw_out.w[:, :, :4 * d, :].contiguous(), self.cw_out.bias)
-        self.w_out_pool = self.cw_out.w[0, 0, 4 * d:, :].contiguous()            # [depth][out] fp32
+        dev = self.cw_out.w.device
+        self.cw_out_main = ConvWeights.from_folded(self.cw_out.w_h[:, :, :4 * d, :].contiguous(), self.cw_out.bias_h, dev)
+        self.w_out_pool = rt.host_to(self.cw_out.w_h[0, 0, 4 * d:, :], dev)       # [depth][out] fp32
 
     def out_shape(self, n, c, h, w):
         return n, self._out, h, w

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <mutex>
 #include "../../include/add_b200.h"
 
 #define ADD_CHECK_ARG(cond) do { if (!(cond)) return ADD_ERR_BAD_ARG; } while (0)
@@ -16,6 +17,17 @@ extern int g_add_pdl;      // api.cu: 1 = launch the tcgen05 kernels with progra
     g_add_last_cuda_error = (int)e_; return ADD_ERR_CUDA; } while (0)
 
 typedef __nv_bfloat16 bf16;
+
+// cudaFuncSetAttribute (dynamic shared memory size, carve-out) is a PER-DEVICE setting: a process that drives several
+// GPUs (the reference's nn.DataParallel) must apply it on each device it launches on, not once per process.
+struct PerDeviceOnce { std::mutex mu; bool done[64] = {}; };
+template <class F> static inline void once_per_device(PerDeviceOnce& o, F fn) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) { fn(); return; }
+  std::lock_guard<std::mutex> g(o.mu);
+  if (!o.done[dev]) { fn(); o.done[dev] = true; }
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

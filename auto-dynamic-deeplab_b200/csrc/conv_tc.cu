@@ -30,6 +30,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 1];   // full[s], empty[s], relu[s], accum
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
+  // a per-image bias (ASPP pool branch) is ACTIVATION data written by the previous kernel: wait for it first
+  if (p.bias_img_stride != 0) pdl_wait();
   stage_bias(bias_s, p, threadIdx.x, TC_THREADS, (int)(blockIdx.x / (unsigned)(p.tiles_x * p.tiles_y)));
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles: 1024-B aligned
@@ -305,9 +307,10 @@ conv2d_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
   } else {
     // ===== epilogue: warps 6..9 (TMEM lane quadrants 2,3,0,1) =====
     int cur_n = ((int)blockIdx.x * MT) / tiles_per_img;
+    if (p.bias_img_stride != 0) pdl_wait();   // per-image bias = activation data of the previous kernel
     stage_bias(bias_s, p, threadIdx.x - 192, 128, cur_n);
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    pdl_wait();
+    if (p.bias_img_stride == 0) pdl_wait();
     int ti = 0;
     for (int uj = 0; uj < units_per_cta; ++uj, ++ti) {
       const int u = (int)blockIdx.x + uj * (int)gridDim.x;
@@ -413,6 +416,8 @@ conv2d_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   __shared__ __align__(8) uint64_t bars[6 + 2 * TC_MAX_STAGES + 1];   // halo full/empty/relu [2], b_full[s], b_empty[s], accum
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[TC_MAX_NPAD];
+  // a per-image bias (ASPP pool branch) is ACTIVATION data written by the previous kernel: wait for it first
+  if (p.bias_img_stride != 0) pdl_wait();
   stage_bias(bias_s, p, threadIdx.x, TCH_THREADS, (int)(blockIdx.x / (unsigned)(p.tiles_x * p.tiles_y)));
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -816,9 +821,10 @@ conv2d_tc_halo_persistent_kernel(const __grid_constant__ CUtensorMap map_x, cons
     // ===== epilogue: warps 7..10 =====
     int cur_n = 0;
     { int tx0, r00; halo_unit_rows((int)blockIdx.x < n_units ? (int)blockIdx.x : 0, upc, p.tiles_x, p.dil, MT, cur_n, tx0, r00); }
+    if (p.bias_img_stride != 0) pdl_wait();   // per-image bias = activation data of the previous kernel
     stage_bias(bias_s, p, threadIdx.x - 224, 128, cur_n);
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    pdl_wait();                               // += y reads and y writes must follow the previous kernel
+    if (p.bias_img_stride == 0) pdl_wait();                               // += y reads and y writes must follow the previous kernel
     int ti = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ti) {
       const int ab = nbuf == 2 ? (ti & 1) : 0;
@@ -983,8 +989,8 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return ADD_ERR_UNSUPPORTED;
   }
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
+  static PerDeviceOnce attr_once;
+  once_per_device(attr_once, [] {
     cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // + static < 227 KB
     cudaFuncSetAttribute(conv2d_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   });
@@ -1009,8 +1015,8 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
     if (st >= 2) {
       p.stages = st;
       const size_t psmem = fixed + (size_t)st * sbytes;
-      static std::once_flag ponce;
-      std::call_once(ponce, [] {
+      static PerDeviceOnce ponce;
+      once_per_device(ponce, [] {
         cudaFuncSetAttribute(conv2d_tc_persistent_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(conv2d_tc_persistent_kernel<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         cudaFuncSetAttribute(conv2d_tc_persistent_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1088,8 +1094,8 @@ extern "C" int add_conv2d_tc_fwd(const add_tensor_t* x, const add_tensor_t* y, c
       psmem = (size_t)q.halo_bufs * hbytes + (size_t)(sb > 0 ? sb : 0) * p.b_bytes + 1024;
     }
     if (ok && (q.b_resident || q.mt >= 2 || g_halo_stream_persistent)) {
-      static std::once_flag hponce;
-      std::call_once(hponce, [] {
+      static PerDeviceOnce hponce;
+      once_per_device(hponce, [] {
         cudaFuncSetAttribute(conv2d_tc_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
         cudaFuncSetAttribute(conv2d_tc_halo_persistent_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       });

@@ -220,7 +220,7 @@ upsample_argmax_runs_kernel(const HeadParams p) {
 __global__ void __launch_bounds__(HD_THREADS)
 head_finalize_kernel(const unsigned int* __restrict__ part_hist, const double* __restrict__ part_ent,
                      int B, int bins, long long* __restrict__ cm_out, float* __restrict__ ent_out,
-                     double inv_hw) {
+                     double inv_hw, const int* __restrict__ cm_row) {
   // warp w sums the per-block histograms b = w, w+8, ... (coalesced rows, independent loads), then the eight
   // per-warp sums are added in fixed order: integer arithmetic, deterministic.
   __shared__ long long red[HD_WARPS][MAX_BINS];
@@ -252,7 +252,7 @@ head_finalize_kernel(const unsigned int* __restrict__ part_hist, const double* _
       long long s = 0;
 #pragma unroll
       for (int wv = 0; wv < HD_WARPS; ++wv) s += red[wv][i];
-      cm_out[(size_t)n * bins + i] = s;
+      cm_out[(size_t)(cm_row ? cm_row[n] : n) * bins + i] = s;   // cm_row: scatter to the image's ORIGINAL batch row
     }
   }
   if (ent_out && threadIdx.x == 0) {
@@ -288,30 +288,31 @@ upsample_logits_nchw_kernel(const float* __restrict__ x, int n_img, int h, int w
 // ---- Evaluator._generate_matrix: int64 gt/pred -> int64 [nc*nc] -------------------------------
 __global__ void __launch_bounds__(HD_THREADS)
 confusion_kernel(const long long* __restrict__ gt, const long long* __restrict__ pred, long long n_pix,
-                 int nc, unsigned int* __restrict__ part) {
+                 int nc, unsigned int* __restrict__ part, int vec_ok) {
   __shared__ unsigned int hist[HD_WARPS][MAX_BINS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < HD_WARPS * MAX_BINS; i += HD_THREADS) (&hist[0][0])[i] = 0u;
   __syncthreads();
-  const long long per = ((n_pix + gridDim.x - 1) / gridDim.x + 1) & ~1ll;   // even → 16 B aligned pairs
+  const long long per = ((n_pix + gridDim.x - 1) / gridDim.x + 1) & ~1ll;   // even -> 16 B aligned pairs
   const long long start = blockIdx.x * per, end = (start + per < n_pix) ? start + per : n_pix;
-  // two pixels per lane per iteration through 16-byte loads
+  // two pixels per lane per iteration: 16-byte loads when both bases are 16-byte aligned (vec_ok), else two 8-byte
+  // loads each (a per-image slice of an odd-sized map, e.g. target[i] of 1025x2049 labels, starts 8 bytes off)
   for (long long base = start + warp * 64; base < end; base += HD_THREADS * 2) {
     long long pix = base + lane * 2;
     int bin0 = -1, bin1 = -1;
-    if (pix + 1 < end) {
+    long long g0 = -1, q0 = 0, g1 = -1, q1 = 0;
+    if (vec_ok && pix + 1 < end) {
       longlong2 g = __ldcs(reinterpret_cast<const longlong2*>(gt + pix));
       longlong2 q = __ldcs(reinterpret_cast<const longlong2*>(pred + pix));
-      if (g.x >= 0 && g.x < nc) bin0 = (int)(g.x * nc + q.x);
-      if (g.y >= 0 && g.y < nc) bin1 = (int)(g.y * nc + q.y);
-    } else if (pix < end) {
-      long long g = gt[pix], q = pred[pix];
-      if (g >= 0 && g < nc) bin0 = (int)(g * nc + q);
+      g0 = g.x; q0 = q.x; g1 = g.y; q1 = q.y;
+    } else {
+      if (pix < end) { g0 = __ldcs(gt + pix); q0 = __ldcs(pred + pix); }
+      if (pix + 1 < end) { g1 = __ldcs(gt + pix + 1); q1 = __ldcs(pred + pix + 1); }
     }
-    // a prediction outside [0,nc) would index past the matrix: drop it like bincount(minlength)
-    // cannot — the reference would grow the vector and fail the reshape; we clamp to "ignore".
-    if (bin0 >= nc * nc) bin0 = -1;
-    if (bin1 >= nc * nc) bin1 = -1;
+    // a prediction outside [0,nc) has no cell in the matrix (the reference's bincount raises on a negative label and
+    // fails its reshape on a too large one, metrics.py:37-38): such pixels are dropped, never aliased into a valid bin
+    if (g0 >= 0 && g0 < nc && q0 >= 0 && q0 < nc) bin0 = (int)(g0 * nc + q0);
+    if (g1 >= 0 && g1 < nc && q1 >= 0 && q1 < nc) bin1 = (int)(g1 * nc + q1);
     warp_hist_add(hist[warp], bin0, lane);
     warp_hist_add(hist[warp], bin1, lane);
   }
@@ -411,23 +412,23 @@ extern "C" int64_t add_head_workspace_bytes(int n, int H, int W, int num_class) 
 }
 
 static int upsample_argmax_impl(const add_tensor_t* x, int H, int W, const int64_t* gt, const uint8_t* gt8,
-                                int64_t* pred_out, int64_t* cm_out, float* entropy_out,
+                                int64_t* pred_out, int64_t* cm_out, const int32_t* cm_row_index, float* entropy_out,
                                 void* workspace, int64_t workspace_bytes, void* stream);
 
 extern "C" int add_upsample_argmax_fwd(const add_tensor_t* x, int H, int W, const int64_t* gt,
-                                       int64_t* pred_out, int64_t* cm_out, float* entropy_out,
+                                       int64_t* pred_out, int64_t* cm_out, const int32_t* cm_row_index, float* entropy_out,
                                        void* workspace, int64_t workspace_bytes, void* stream) {
-  return upsample_argmax_impl(x, H, W, gt, nullptr, pred_out, cm_out, entropy_out, workspace, workspace_bytes, stream);
+  return upsample_argmax_impl(x, H, W, gt, nullptr, pred_out, cm_out, cm_row_index, entropy_out, workspace, workspace_bytes, stream);
 }
 
 extern "C" int add_upsample_argmax_u8_fwd(const add_tensor_t* x, int H, int W, const uint8_t* gt_u8,
-                                          int64_t* pred_out, int64_t* cm_out, float* entropy_out,
+                                          int64_t* pred_out, int64_t* cm_out, const int32_t* cm_row_index, float* entropy_out,
                                           void* workspace, int64_t workspace_bytes, void* stream) {
-  return upsample_argmax_impl(x, H, W, nullptr, gt_u8, pred_out, cm_out, entropy_out, workspace, workspace_bytes, stream);
+  return upsample_argmax_impl(x, H, W, nullptr, gt_u8, pred_out, cm_out, cm_row_index, entropy_out, workspace, workspace_bytes, stream);
 }
 
 static int upsample_argmax_impl(const add_tensor_t* x, int H, int W, const int64_t* gt, const uint8_t* gt8,
-                                int64_t* pred_out, int64_t* cm_out, float* entropy_out,
+                                int64_t* pred_out, int64_t* cm_out, const int32_t* cm_row_index, float* entropy_out,
                                 void* workspace, int64_t workspace_bytes, void* stream) {
   ADD_CHECK_ARG(tensor_ok(x) && H > 0 && W > 0 && workspace);
   ADD_CHECK_ARG(!(cm_out && !gt && !gt8));
@@ -453,7 +454,7 @@ static int upsample_argmax_impl(const add_tensor_t* x, int H, int W, const int64
   }
   if (cm_out || entropy_out)
     head_finalize_kernel<<<x->n, HD_THREADS, 0, s>>>(p.part_hist, p.part_ent, p.B, p.bins,
-                                                      (long long*)cm_out, entropy_out, 1.0 / ((double)H * W));
+                                                      (long long*)cm_out, entropy_out, 1.0 / ((double)H * W), cm_row_index);
   ADD_RETURN_LAUNCH();
 }
 
@@ -467,12 +468,13 @@ extern "C" int add_confusion_matrix(const int64_t* gt, const int64_t* pred, int6
   ADD_CHECK_ARG(cm_out && workspace && n_pixels >= 0 && num_class > 0);
   ADD_CHECK_ARG(n_pixels == 0 || (gt && pred));
   ADD_CHECK_SUP(num_class * num_class <= MAX_BINS);
-  ADD_CHECK_SUP(((uintptr_t)gt % 16 == 0) && ((uintptr_t)pred % 16 == 0));
+  ADD_CHECK_SUP(((uintptr_t)gt % 8 == 0) && ((uintptr_t)pred % 8 == 0));
+  const int vec_ok = (((uintptr_t)gt % 16 == 0) && ((uintptr_t)pred % 16 == 0)) ? 1 : 0;
   if (workspace_bytes < add_confusion_workspace_bytes(n_pixels, num_class)) return ADD_ERR_WORKSPACE;
   int B = confusion_blocks(n_pixels);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   confusion_kernel<<<B, HD_THREADS, 0, s>>>((const long long*)gt, (const long long*)pred, n_pixels, num_class,
-                                            (unsigned int*)workspace);
+                                            (unsigned int*)workspace, vec_ok);
   confusion_finalize_kernel<<<1, HD_THREADS, 0, s>>>((const unsigned int*)workspace, B, num_class * num_class,
                                                      (long long*)cm_out);
   ADD_RETURN_LAUNCH();

@@ -417,8 +417,8 @@ sepconv_half_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, con
 template <int K, int MAXT, int MINB>
 int launch_sepconv_tc_persistent(const CUtensorMap& map_x, const CUtensorMap& map_w, const SpParams& p, int grid, int threads,
                                  size_t smem, cudaStream_t s) {
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static PerDeviceOnce once;
+  once_per_device(once, [] {
     cudaFuncSetAttribute(sepconv_half_tc_persistent_kernel<K, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(sepconv_half_tc_persistent_kernel<K, MAXT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   });
@@ -433,8 +433,8 @@ int g_sepconv_mode = 1;    // 1 = persistent pipeline where it fits (default), 0
 
 template <int K>
 int launch_sepconv_tc(const CUtensorMap& map_x, const CUtensorMap& map_w, const ScParams& p, long long grid, size_t smem, cudaStream_t s) {
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static PerDeviceOnce once;
+  once_per_device(once, [] {
     cudaFuncSetAttribute(sepconv_half_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(sepconv_half_tc_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   });

@@ -249,8 +249,8 @@ extern "C" int add_stem_conv3x3s2_nchw_fwd(const float* x_nchw, int n, int h, in
       return ADD_ERR_UNSUPPORTED;
   }
   const size_t smem = TC_A_BYTES + ST_COUT * 128 + 9 * ST_IN_PITCH * sizeof(float) + 1024;
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static PerDeviceOnce once;
+  once_per_device(once, [] {
     cudaFuncSetAttribute(stem_conv3x3s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(stem_conv3x3s2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   });

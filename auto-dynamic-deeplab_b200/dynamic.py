@@ -210,7 +210,9 @@ class _EdmRunner:
         self.segments: Dict[Tuple[int, int], _Segment] = {}
         self.heads: Dict[Tuple[int, int], _Head] = {}
         self.gt_full: Optional[torch.Tensor] = None
+        self.cm_full: Optional[torch.Tensor] = None
         if mode == "evaluate":
+            self.cm_full = torch.zeros((self.n, self.nc, self.nc), dtype=torch.int64, device=device)
             # labels: the reference's int64 tensors, or uint8 (the PNG bytes: 8x less gather / histogram traffic)
             self.label_dtype = label_dtype
             self.gt_full = (bound[1] if bound is not None else
@@ -232,18 +234,22 @@ class _EdmRunner:
         gt = b.raw((m, self.H, self.W), self.label_dtype)
         owner.idx_gt = b.raw((m,), torch.int32, zero=True)          # ORIGINAL image ids of this plan's rows
         b.gather_images(self.gt_full, gt, owner.idx_gt, "dynamic.gather.gt")
-        cm = b.raw((m, self.nc, self.nc), torch.int64)
-        b.upsample_argmax(logits, self.H, self.W, gt, None, cm, None, "ADD.upsample_argmax_cm")
-        return cm
+        # every plan scatters its rows' matrices straight into the [N, nc, nc] result of the original batch
+        # (cm_row_index of add_upsample_argmax_fwd): no stacking of per-plan outputs afterwards
+        b.upsample_argmax(logits, self.H, self.W, gt, None, self.cm_full, None, "ADD.upsample_argmax_cm",
+                          cm_rows=owner.idx_gt)
+        return self.cm_full
 
     def segment(self, k: int, m: int, prev: Optional[_Segment]) -> _Segment:
-        key = (k, m, prev.m if prev is not None else 0)
+        # a plan is recorded against the buffers of ONE specific source segment: key it by that segment's identity
+        # (with >= 3 gated exits several segments share (k, m) and differ only in their lineage)
+        key = (k, m, id(prev) if prev is not None else 0)
         if key not in self.segments:
             self.segments[key] = _Segment(self, k, m, prev)
         return self.segments[key]
 
     def head(self, k: int, m: int, seg: _Segment) -> _Head:
-        key = (k, m, seg.m)
+        key = (k, m, id(seg))
         if key not in self.heads:
             self.heads[key] = _Head(self, k, m, seg)
         return self.heads[key]
@@ -265,7 +271,7 @@ class _EdmRunner:
 
     # The gate is a host decision (the reference's implicit sync, ADD.py:421): after the trunk graph the host reads N
     # floats, picks the plans for the exiting / continuing images and launches them — ~0.15 ms per step during which
-    # the GPU is idle (tools/bubble_test.py).  begin() enqueues everything up to the first gate and returns; finish()
+    # the GPU is idle (tools/gate_bubble.py).  begin() enqueues everything up to the first gate and returns; finish()
     # waits for that gate's values and enqueues the rest.  A caller that owns several runners (HostPipeline's slots)
     # calls begin() of batch i+1 BEFORE finish() of batch i, so the GPU works on the next trunk while the host decides.
     def begin(self, x: torch.Tensor, threshold: float, target: Optional[torch.Tensor] = None):
@@ -312,7 +318,7 @@ class _EdmRunner:
             launches += seg.n_launches
             if k == len(self.exits):
                 for j, img in enumerate(active):
-                    outs[img] = seg.out[j:j + 1] if self.mode == "logits" else seg.out[j]
+                    outs[img] = seg.out[j:j + 1] if self.mode == "logits" else self.cm_full[img]
                 break
             # host decision = the reference's implicit sync (ADD.py:421): N floats come down through pinned memory
             m_act = len(active)
@@ -346,7 +352,7 @@ class _EdmRunner:
                 self.last_plans.append(head.main)
                 launches += head.n_launches
                 for jj, j in enumerate(ex):
-                    outs[active[j]] = head.out[jj:jj + 1] if self.mode == "logits" else head.out[jj]
+                    outs[active[j]] = head.out[jj:jj + 1] if self.mode == "logits" else self.cm_full[active[j]]
                     flags[active[j]] = 1
             if not co:
                 break
@@ -479,11 +485,13 @@ def begin_dynamic_evaluate(net, x: torch.Tensor, target: torch.Tensor, threshold
 
 
 def finish_dynamic_evaluate(net, handle):
-    """Second half: wait for the gate values, enqueue the exit heads / remaining trunk.  Returns (cm, flags, confs)."""
+    """Second half: wait for the gate values, enqueue the exit heads / remaining trunk.  Returns (cm, flags, confs);
+    cm [N,nc,nc] int64 ALIASES the runner's result buffer (every plan scatters its images' matrices into it): it is
+    overwritten by the next batch begun on the same input buffers."""
     r, state = handle
     outs, flags, confs = r.finish(state)
     net.last_dynamic_launches = r.last_launches
-    return torch.stack(outs), flags, confs
+    return r.cm_full, flags, confs
 
 
 def run_dynamic_evaluate(net, x: torch.Tensor, target: torch.Tensor, threshold, edm, exit_mode: str = "reference",
@@ -495,4 +503,6 @@ def run_dynamic_evaluate(net, x: torch.Tensor, target: torch.Tensor, threshold, 
     r = _get_runner(net, x, edm, "evaluate", exit_mode, target, bind_inputs)
     outs, flags, confs = r.run(x, float(threshold), target)
     net.last_dynamic_launches = r.last_launches
-    return torch.stack(outs), flags, confs
+    # the blocking call hands out a private copy (one 8*N*nc*nc-byte device memcpy); the begin / finish pair used by
+    # the pipelines returns the runner's own result buffer, which the next batch on the same inputs overwrites
+    return r.cm_full.clone(), flags, confs

@@ -183,8 +183,8 @@ class SepConv(AddModule):
         self.k, self.C = kernel_size, C_out
 
     def _prepare(self):
-        def dw(conv):  # [C,1,k,k] -> [k][k][C]
-            return conv.weight.detach().float()[:, 0].permute(1, 2, 0).contiguous()
+        def dw(conv):  # [C,1,k,k] -> [k][k][C], permuted on the host
+            return rt.host_to(conv.weight.detach().cpu().float()[:, 0].permute(1, 2, 0), conv.weight.device)
         self.dw1, self.dw2 = dw(self.op[1]), dw(self.op[5])
         self.pw1 = ConvWeights(self.op[2].weight, self.op[3])
         self.pw2 = ConvWeights(self.op[6].weight, self.op[7])
@@ -197,8 +197,8 @@ class SepConv(AddModule):
         b.release(mid)
 
     def _forward_train(self, x):
-        def dw(conv):  # [C,1,k,k] -> [k][k][C]
-            return conv.weight.detach().float()[:, 0].permute(1, 2, 0).contiguous()
+        def dw(conv):  # [C,1,k,k] -> [k][k][C], permuted on the host
+            return rt.host_to(conv.weight.detach().cpu().float()[:, 0].permute(1, 2, 0), conv.weight.device)
         b, xv = self._train_io(x)
         t1 = b.alloc(xv.n, xv.h, xv.w, self.C)
         b.sepconv_half(xv, t1, dw(self.op[1]), ConvWeights(self.op[2].weight), self.k, RELU_IN, "SepConv.half1.train")
@@ -300,7 +300,6 @@ class _FactorizedReduceBase(AddModule):
 
     def _prepare(self):
         half = self.C_out // 2
-        scale, shift = rt.bn_scale_shift(self.bn)
 
         class _Half:  # a BN view restricted to one half of the channels
             def __init__(s, lo, hi, bn):
@@ -317,10 +316,11 @@ class _FactorizedReduceBase(AddModule):
         self.cw_merged = None
         if self.STEP == 2:
             cin = self.cw1.cin
-            w = torch.zeros(2, 2, cin, self.C_out, device=self.cw1.w.device, dtype=torch.float32)
-            w[0, 0, :, :half] = self.cw1.w[0, 0]
-            w[1, 1, :, half:] = self.cw2.w[0, 0]
-            self.cw_merged = ConvWeights.from_folded(w, torch.cat([self.cw1.bias, self.cw2.bias]).contiguous())
+            w = torch.zeros(2, 2, cin, self.C_out, dtype=torch.float32)
+            w[0, 0, :, :half] = self.cw1.w_h[0, 0]
+            w[1, 1, :, half:] = self.cw2.w_h[0, 0]
+            self.cw_merged = ConvWeights.from_folded(w, torch.cat([self.cw1.bias_h, self.cw2.bias_h]).contiguous(),
+                                                     self.cw1.w.device)
 
     def out_shape(self, n, c, h, w):
         s = self.STEP

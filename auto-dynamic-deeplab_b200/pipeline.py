@@ -40,14 +40,27 @@ class HostPipeline:
             raise RuntimeError("HostPipeline needs the model on a CUDA device (add_b200 has no CPU fallback)")
         self.copy_stream = torch.cuda.Stream(self.device)
         self._slots: Optional[List[dict]] = None
+        self._slot_sets: dict = {}
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    @staticmethod
+    def _batch_key(batch) -> tuple:
+        x, gt = batch
+        return (tuple(x.shape), x.dtype, tuple(gt.shape), gt.dtype)
+
     def _ensure_slots(self, x: torch.Tensor, gt: torch.Tensor) -> None:
+        """Slots (device buffers + the plans recorded on them) are per batch SHAPE: a loader's last, smaller batch
+        (500 Cityscapes val images in batches of 8 leave 4) gets its own slot set instead of being broadcast into —
+        and counted as — a full one."""
         shape = (x.shape[0], 3, x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else tuple(x.shape)
-        if self._slots is not None and tuple(self._slots[0]["x"].shape) == shape:
+        if gt.shape[0] != shape[0] or tuple(gt.shape[1:]) != tuple(shape[2:]):
+            raise ValueError(f"labels {tuple(gt.shape)} do not match images {shape}")
+        key = (shape, tuple(gt.shape), gt.dtype)
+        if key in self._slot_sets:
+            self._slots = self._slot_sets[key]
             return
-        self._slots = []
+        self._slots = self._slot_sets[key] = []
         for _ in range(self.depth):
             self._slots.append(dict(x=torch.empty(shape, dtype=torch.float32, device=self.device), x_u8=None,
                                     gt=torch.empty(gt.shape, dtype=torch.int64, device=self.device),
@@ -56,6 +69,9 @@ class HostPipeline:
                                     ready=torch.cuda.Event(), free=torch.cuda.Event(), out=None))
 
     def _prefetch(self, slot: dict, x: torch.Tensor, gt: torch.Tensor) -> None:
+        want = (x.shape[0], 3, x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else tuple(x.shape)
+        if tuple(slot["x"].shape) != want or tuple(slot["gt"].shape) != tuple(gt.shape):
+            raise RuntimeError(f"HostPipeline slot {tuple(slot['x'].shape)} fed a batch of shape {want}")   # never broadcast
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot["free"])        # the compute that last read this slot is done
             if x.dtype == torch.uint8:
@@ -87,9 +103,16 @@ class HostPipeline:
         self.h2d_bytes += x.numel() * x.element_size() + gt.numel() * gt.element_size()
 
     def evaluate(self, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]]) -> Iterator[Tuple[torch.Tensor, Optional[list]]]:
-        if self.edm is not None:
-            yield from self._evaluate_gated(batches)
-            return
+        """Runs of equal-shaped batches are pipelined; a shape change (the loader's final partial batch) drains the
+        pipeline and continues on that shape's own slots."""
+        import itertools
+        for _, run in itertools.groupby(batches, key=self._batch_key):
+            if self.edm is not None:
+                yield from self._evaluate_gated(run)
+            else:
+                yield from self._evaluate_all_exits(run)
+
+    def _evaluate_all_exits(self, batches):
         main = torch.cuda.current_stream(self.device)
         it = iter(batches)
         nxt = next(it, None)

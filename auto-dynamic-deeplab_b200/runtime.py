@@ -94,44 +94,56 @@ class View:
 class ConvWeights:
     """A conv (+ folded eval-mode BN) ready for the kernels: fp32 [kh][kw][Cin][Cout] with the BN
     scale folded in, fp32 bias (w' = w·γ/σ, b' = β − μ·γ/σ), and, lazily, the
-    bf16 UMMA-packed image for the tcgen05 path."""
+    bf16 UMMA-packed image for the tcgen05 path.
+
+    The fold runs ON THE HOST (one-off preparation of a few MB of parameters): the parameters are copied down once,
+    folded / permuted / padded in CPU fp32, and the finished images go up with plain memcpys — so no ATen device kernel
+    is ever launched on behalf of this library and every kernel a profiler sees on the device is one of ours.
+    `w_h` / `bias_h` are the host masters (derived weights — channel slices, merged FactorizedReduce taps, packed UMMA
+    images — are built from them), `w` / `bias` the device copies the kernels read."""
 
     def __init__(self, weight: torch.Tensor, bn=None, bias: Optional[torch.Tensor] = None,
                  cin_pad: Optional[int] = None):
-        w = weight.detach().float()
+        dev = weight.device
+        w = weight.detach().cpu().float()
         co, ci, kh, kw = w.shape
         if bn is not None:
             scale, shift = bn_scale_shift(bn)
             w = w * scale.view(-1, 1, 1, 1)
-            b = shift if bias is None else shift + bias.detach().float() * scale
+            b = shift if bias is None else shift + bias.detach().cpu().float() * scale
         else:
-            b = bias.detach().float() if bias is not None else None
+            b = bias.detach().cpu().float() if bias is not None else None
         w = w.permute(2, 3, 1, 0).contiguous()  # [kh][kw][Cin][Cout]
         if cin_pad is not None and cin_pad > ci:
-            wp = torch.zeros(kh, kw, cin_pad, co, device=w.device, dtype=w.dtype)
+            wp = torch.zeros(kh, kw, cin_pad, co, dtype=w.dtype)
             wp[:, :, :ci] = w
-            w, ci = wp, cin_pad
-        self.w = w.contiguous()
-        self.bias = b.contiguous() if b is not None else None
-        self.cin, self.cout, self.kh, self.kw = ci, co, kh, kw
+            w = wp
+        self._finish(w, b, dev)
+
+    def _finish(self, w_host: torch.Tensor, bias_host: Optional[torch.Tensor], dev) -> None:
+        self.w_h = w_host.contiguous()
+        self.bias_h = bias_host.contiguous() if bias_host is not None else None
+        self.w = self.w_h.to(dev)
+        self.bias = self.bias_h.to(dev) if self.bias_h is not None else None
+        self.kh, self.kw, self.cin, self.cout = self.w_h.shape
         self._packed: Optional[torch.Tensor] = None
 
     @classmethod
-    def from_folded(cls, w_hwio: torch.Tensor, bias: Optional[torch.Tensor]) -> "ConvWeights":
-        """From already folded fp32 [kh][kw][Cin][Cout] weights (e.g. an input-channel slice of another conv)."""
+    def from_folded(cls, w_hwio: torch.Tensor, bias: Optional[torch.Tensor], device=None) -> "ConvWeights":
+        """From already folded HOST fp32 [kh][kw][Cin][Cout] weights (e.g. an input-channel slice of another conv's
+        `w_h`); `device` = where the kernels will read them."""
+        assert w_hwio.device.type == "cpu" and (bias is None or bias.device.type == "cpu"), "from_folded takes host masters"
         self = cls.__new__(cls)
-        self.w = w_hwio.contiguous()
-        self.bias = bias
-        self.kh, self.kw, self.cin, self.cout = self.w.shape
-        self._packed = None
+        self._finish(w_hwio, bias, device if device is not None else w_hwio.device)
         return self
 
     def cout_slice(self, c0: int, g: int) -> "ConvWeights":
         """The conv restricted to output channels [c0, c0 + g) (cached)."""
         cache = self.__dict__.setdefault("_cout_slices", {})
         if (c0, g) not in cache:
-            cache[(c0, g)] = ConvWeights.from_folded(self.w[..., c0:c0 + g].contiguous(),
-                                                     None if self.bias is None else self.bias[c0:c0 + g].contiguous())
+            cache[(c0, g)] = ConvWeights.from_folded(self.w_h[..., c0:c0 + g].contiguous(),
+                                                     None if self.bias_h is None else self.bias_h[c0:c0 + g].contiguous(),
+                                                     self.w.device)
         return cache[(c0, g)]
 
     def packed_tc(self) -> torch.Tensor:
@@ -140,8 +152,7 @@ class ConvWeights:
             if nbytes < 0:
                 check(int(nbytes), "conv2d_tc_packed_bytes")
             host = torch.empty(nbytes, dtype=torch.uint8)
-            w_host = self.w.cpu().contiguous()
-            check(lib.add_conv2d_tc_pack(w_host.data_ptr(), self.cin, self.cout, self.kh, self.kw,
+            check(lib.add_conv2d_tc_pack(self.w_h.data_ptr(), self.cin, self.cout, self.kh, self.kw,
                                          host.data_ptr()), "conv2d_tc_pack")
             self._packed = host.to(self.w.device)
         return self._packed
@@ -149,7 +160,7 @@ class ConvWeights:
 
 def pack_stem_tc(cw: "ConvWeights") -> torch.Tensor:
     """bf16 [64][64] UMMA image of a folded 3->64 3x3 conv for add_stem_conv3x3s2_nchw_fwd (device tensor)."""
-    w_oihw = cw.w[:, :, :3, :].permute(3, 2, 0, 1).contiguous().cpu()        # [co][ci][ky][kx]
+    w_oihw = cw.w_h[:, :, :3, :].permute(3, 2, 0, 1).contiguous()        # [co][ci][ky][kx]
     assert tuple(w_oihw.shape) == (64, 3, 3, 3)
     host = torch.empty(int(lib.add_stem_tc_packed_bytes()), dtype=torch.uint8)
     check(lib.add_stem_tc_pack(w_oihw.data_ptr(), host.data_ptr()), "stem_tc_pack")
@@ -157,14 +168,19 @@ def pack_stem_tc(cw: "ConvWeights") -> torch.Tensor:
 
 
 def bn_scale_shift(bn) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Eval-mode BatchNorm as y = x*scale + shift (fp32)."""
-    var = bn.running_var.detach().float()
-    mean = bn.running_mean.detach().float()
+    """Eval-mode BatchNorm as y = x*scale + shift (HOST fp32 tensors)."""
+    var = bn.running_var.detach().cpu().float()
+    mean = bn.running_mean.detach().cpu().float()
     inv = torch.rsqrt(var + bn.eps)
-    gamma = bn.weight.detach().float() if bn.weight is not None else torch.ones_like(var)
-    beta = bn.bias.detach().float() if bn.bias is not None else torch.zeros_like(var)
+    gamma = bn.weight.detach().cpu().float() if bn.weight is not None else torch.ones_like(var)
+    beta = bn.bias.detach().cpu().float() if bn.bias is not None else torch.zeros_like(var)
     scale = gamma * inv
     return scale, beta - mean * scale
+
+
+def host_to(t: torch.Tensor, dev) -> torch.Tensor:
+    """A parameter prepared on the host (permuted / sliced, fp32 contiguous) -> device copy (a memcpy, no kernel)."""
+    return t.contiguous().to(dev)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -477,16 +493,19 @@ class Builder:
                    reads=(x,), writes=(dst,))
 
     def upsample_argmax(self, x: View, H: int, W: int, gt: Optional[torch.Tensor], pred: Optional[torch.Tensor],
-                        cm: Optional[torch.Tensor], ent: Optional[torch.Tensor], tag: str = "upsample_argmax") -> None:
+                        cm: Optional[torch.Tensor], ent: Optional[torch.Tensor], tag: str = "upsample_argmax",
+                        cm_rows: Optional[torch.Tensor] = None) -> None:
+        """cm_rows: device int32 [n] — image j's confusion matrix goes to row cm_rows[j] of `cm` (scatter into the
+        result of the original, uncompacted batch) instead of row j."""
         nbytes = lib.add_head_workspace_bytes(x.n, H, W, x.c)
         ws = self.raw((nbytes,), torch.uint8)
         u8 = gt is not None and gt.dtype == torch.uint8            # labels as the PNG bytes: 1 byte per pixel
         assert gt is None or gt.dtype in (torch.uint8, torch.int64)
         self._emit(lib.add_upsample_argmax_u8_fwd if u8 else lib.add_upsample_argmax_fwd,
-                   (self._d(x), H, W, _ptr(gt), _ptr(pred), _ptr(cm), _ptr(ent), ws.data_ptr(), nbytes), tag,
+                   (self._d(x), H, W, _ptr(gt), _ptr(pred), _ptr(cm), _ptr(cm_rows), _ptr(ent), ws.data_ptr(), nbytes), tag,
                    dict(kernel="upsample_argmax", flops=8 * x.n * H * W * x.c,
                         bytes=4 * x.n * x.h * x.w * x.c + x.n * H * W * ((1 if u8 else 8) * (gt is not None) + 8 * (pred is not None))),
-                   reads=(x, gt), writes=(pred, cm, ent, ws))
+                   reads=(x, gt, cm_rows), writes=(pred, cm, ent, ws))
 
     def edm_mlp(self, pooled: torch.Tensor, n: int, ws: Sequence[torch.Tensor], out: torch.Tensor,
                 tag: str = "edm_mlp") -> None:

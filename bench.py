@@ -140,46 +140,89 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port of the reference's CPU path, all host threads
+# CPU baseline / reference arm: the reference's own CPU path on all host threads.
+# Nothing here imports add_b200 (the product): the reference arm's process must not map libadd_b200.so.
+#   kind "reference": the UNMODIFIED reference modules staged under the git-ignored baseline/_ref/
+#                     (oracle/stage_reference.py) — modeling.ADD.ADD.dynamic_inference + utils.metrics.Evaluator;
+#   kind "port":      oracle/add_oracle.py (the cited restatement) when nothing was staged.
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_setup(a):
-    import torch
-    import add_b200  # only for the deterministic weight construction (same state_dict as the GPU arm)
-    from oracle import add_oracle as orc
-    torch.set_num_threads(os.cpu_count() or 1)
-    net = add_b200.build_add("searched-dense", 2, 20, seed=1)
-    sd = {k: v.detach() for k, v in net.state_dict().items()}
-    torch.manual_seed(203)
-    edm_sd = {k: v.detach() for k, v in add_b200.EDM().state_dict().items()}
-    na, ci, low = add_b200.NETWORKS["searched-dense"][2]
-    arch = orc.Arch(na, ci, low_level_layer=low)
-    return orc, sd, edm_sd, arch
+SEARCHED_DENSE_C2 = ([1, 2, 2, 2, 3, 2, 2, 1, 1, 1, 1, 2], [5], 0)      # eval.py:42-57 (network_arch, C_index, low_level_layer)
 
 
-def cpu_reference_image(orc, sd, edm_sd, arch, x1, gt1, threshold):
-    """One image through the reference's dynamic_inference + argmax + confusion matrix on the CPU."""
+def cpu_synthetic_batch(n, h, w, seed=1234):
+    """The SURVEY §8d synthetic batch (same generator calls as add_b200.synthetic_batch), built with torch only."""
     import torch
-    with torch.no_grad():
-        y, ee, conf = orc.add_dynamic_inference(sd, arch, x1, threshold, 'edm', edm_sd)
-        pred = torch.argmax(y, 1)
-    return orc.generate_matrix(gt1.numpy(), pred.numpy()), ee
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 3, h, w, generator=g)
+    gt = torch.randint(0, 19, (n, h, w), generator=g, dtype=torch.int64)
+    gt[torch.rand(n, h, w, generator=g) < 0.1] = 255
+    return x, gt
+
+
+class CpuReference:
+    """One image at a time through dynamic_inference + argmax + confusion matrix, like eval.py:195-221."""
+
+    def __init__(self):
+        import torch
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.torch = torch
+        ref = ROOT / "baseline" / "_ref"
+        na, ci, low = SEARCHED_DENSE_C2
+        if (ref / "modeling" / "ADD.py").exists() and (ref / "utils" / "metrics.py").exists():
+            import numpy as np
+            from types import SimpleNamespace
+            sys.path.insert(0, str(ref))
+            from modeling.ADD import ADD as RefADD, EDM as RefEDM       # noqa: E402  (the staged, unmodified reference)
+            from utils.metrics import Evaluator as RefEvaluator          # noqa: E402
+            # ADD.py:380,436 call torch.cuda.synchronize() unconditionally; this arm runs on CPU tensors, so the call is
+            # made a no-op (it would fail without a GPU and create an idle CUDA context with one)
+            torch.cuda.synchronize = lambda *a, **k: None
+            cell = np.load(ref / "searched_arch" / "autodeeplab" / "genotype.npy")
+            torch.manual_seed(1)                                         # eval.py:276,302
+            self.model = RefADD(na, ci, cell, 19, SimpleNamespace(F=20, B=5, sync_bn=False), low).eval()
+            torch.manual_seed(203)
+            self.edm = RefEDM().eval()
+            self.evaluator = RefEvaluator(19)
+            self.kind = "reference"
+            self.what = "unmodified reference (baseline/_ref): modeling.ADD.ADD.dynamic_inference + argmax + utils.metrics.Evaluator.add_batch"
+        else:
+            from oracle import add_oracle as orc
+            self.orc = orc
+            self.arch = orc.Arch(na, ci, low_level_layer=low)
+            self.sd = orc.init_state_dict(self.arch, 1)
+            self.edm_sd = orc.init_edm_state_dict(203)
+            self.kind = "port"
+            self.what = "oracle/add_oracle.py port of ADD.dynamic_inference + argmax + confusion matrix"
+
+    def image(self, x1, gt1, threshold):
+        torch = self.torch
+        with torch.no_grad():
+            if self.kind == "reference":
+                y, ee, _, _ = self.model.dynamic_inference(x1, threshold, 'edm', self.edm)
+                self.evaluator.add_batch(gt1, torch.argmax(y, 1))
+                return ee
+            y, ee, _ = self.orc.add_dynamic_inference(self.sd, self.arch, x1, threshold, 'edm', self.edm_sd)
+            self.orc.generate_matrix(gt1.numpy(), torch.argmax(y, 1).numpy())
+            return ee
+
+    def warm(self):
+        xs, gs = cpu_synthetic_batch(1, 128, 256, seed=5)
+        self.image(xs, gs, 1e30)                                         # thread-pool / allocator warm-up (small)
 
 
 def run_cpu_sample(a, n_images: int, exits: list) -> dict:
     """Time `n_images` images, image j forced to exit early iff exits[j] (same 50 % mix as the GPU arm)."""
-    import add_b200
-    orc, sd, edm_sd, arch = cpu_reference_setup(a)
-    x, gt = add_b200.synthetic_batch(max(n_images, 1), a.height, a.width)
-    xs, gs = add_b200.synthetic_batch(1, 128, 256, seed=5)
-    cpu_reference_image(orc, sd, edm_sd, arch, xs, gs, 1e30)       # thread-pool / allocator warm-up (small)
+    ref = CpuReference()
+    x, gt = cpu_synthetic_batch(max(min(n_images, 2), 1), a.height, a.width)
+    ref.warm()
     t0 = time.perf_counter()
     for j in range(n_images):
         thr = 1e30 if exits[j % len(exits)] else -1e30
-        cpu_reference_image(orc, sd, edm_sd, arch, x[j:j + 1], gt[j:j + 1], thr)
+        ref.image(x[j % x.shape[0]:j % x.shape[0] + 1], gt[j % x.shape[0]:j % x.shape[0] + 1], thr)
     dt = time.perf_counter() - t0
-    return {"value": n_images / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": f"{n_images} image(s) {a.height}x{a.width} fp32, oracle/add_oracle.py add_dynamic_inference + argmax + "
-                      f"confusion matrix, early-exit pattern {[int(e) for e in exits[:n_images]]}, {dt:.1f} s",
+    return {"value": n_images / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": ref.kind,
+            "sample": f"{n_images} image(s) {a.height}x{a.width} fp32, {ref.what}, "
+                      f"early-exit pattern {[int(exits[j % len(exits)]) for j in range(n_images)]}, {dt:.1f} s",
             "seconds": dt}
 
 
@@ -187,31 +230,40 @@ def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import add_b200
-    orc, sd, edm_sd, arch = cpu_reference_setup(a)
-    x, gt = add_b200.synthetic_batch(2, a.height, a.width)
-    xs, gs = add_b200.synthetic_batch(1, 128, 256, seed=5)
-    cpu_reference_image(orc, sd, edm_sd, arch, xs, gs, 1e30)
-    # one step = ONE image (bounded sample of the 8-image batch); even steps exit early, odd steps do not
+    ref = CpuReference()
+    x, gt = cpu_synthetic_batch(2, a.height, a.width)
+    ref.warm()
+    # one step = the SAME batch as the b200 arm: a.batch images, one dynamic_inference call each (the reference's gate
+    # is batch-1, ADD.py:421), half of them forced to exit early (the b200 arm's median threshold gives the same mix)
     times = []
     for s in range(a.warmup + a.steps):
         t0 = time.perf_counter()
-        cpu_reference_image(orc, sd, edm_sd, arch, x[s % 2:s % 2 + 1], gt[s % 2:s % 2 + 1], 1e30 if s % 2 == 0 else -1e30)
+        for j in range(a.batch):
+            ref.image(x[j % 2:j % 2 + 1], gt[j % 2:j % 2 + 1], 1e30 if j % 2 == 0 else -1e30)
         if s >= a.warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    val = len(times) / total
+    val = a.batch * len(times) / total
     cores = os.cpu_count() or 1
-    sample = (f"1 image {a.height}x{a.width} per step (bounded sample of the {a.batch}-image batch), alternating "
-              "early-exit / full-depth, oracle port of ADD.dynamic_inference + argmax + confusion matrix, fp32")
+    sample = (f"{a.batch} images {a.height}x{a.width} per step (the b200 arm's batch), one batch-1 dynamic_inference call per "
+              f"image, alternating early-exit / full-depth, {ref.what}, fp32, {cores} host threads")
     line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_name(a),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
     return 0
+
+
+def cpu_reference_setup(a):
+    """torch_cuda comparator only: oracle + weights built without the product."""
+    import torch
+    from oracle import add_oracle as orc
+    na, ci, low = SEARCHED_DENSE_C2
+    arch = orc.Arch(na, ci, low_level_layer=low)
+    return orc, orc.init_state_dict(arch, 1), orc.init_edm_state_dict(203), arch
 
 
 def main_torch_cuda(a):
@@ -224,13 +276,12 @@ def main_torch_cuda(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import add_b200
     orc, sd, edm_sd, arch = cpu_reference_setup(a)
     dev = torch.device("cuda:0")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
-    x, gt = add_b200.synthetic_batch(2, a.height, a.width)
+    x, gt = cpu_synthetic_batch(2, a.height, a.width)
     res = {}
     for name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
         def cast(v):
@@ -263,7 +314,7 @@ def main_torch_cuda(a):
     # the same network without gating, batched (ADD.forward on a.batch images -> argmax -> bincount per exit): what stock
     # PyTorch achieves when it is allowed a full batch; compare with `bench.py --forward-only` of this repo
     fwd = {}
-    xb, gb = add_b200.synthetic_batch(a.batch, a.height, a.width)
+    xb, gb = cpu_synthetic_batch(a.batch, a.height, a.width)
     for name, dt in (("bf16", torch.bfloat16),):
         sdd = {k: (v.to(dev).to(dt).contiguous(memory_format=torch.channels_last) if v.dim() == 4 else
                    (v.to(dev).to(dt) if v.is_floating_point() else v.to(dev))) for k, v in sd.items()}
@@ -353,7 +404,7 @@ def main_b200(a):
 
     # resident arm: the batch lives in HBM in three buffers that are cycled through add_b200.ResidentPipeline — the
     # trunk of step i+1 is enqueued before the host reads step i's gate values, so the gate's host round trip
-    # (~0.15 ms per step, tools/bubble_test.py) does not leave the GPU idle.  --no-pipeline: one blocking call per step.
+    # (~0.15 ms per step, tools/gate_bubble.py) does not leave the GPU idle.  --no-pipeline: one blocking call per step.
     res_bufs = [(x_dev, gt_dev)] if a.no_pipeline else [(x_dev.clone(), gt_dev.clone()) for _ in range(3)]
     rpipe = add_b200.ResidentPipeline(net, edm, thr, a.exit_mode)
 

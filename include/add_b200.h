@@ -197,17 +197,19 @@ int add_edm_mlp_fwd(const float* pooled, int n, const float* w0, const float* b0
 int add_upsample_logits_nchw(const add_tensor_t* x, float* dst, int H, int W, void* stream);
 /* (b) upsample → argmax (eval.py:183) → optional int64 prediction map and/or confusion matrix
  *     (utils/metrics.py:34-39).  gt: int64 [n,H,W] or NULL; pred_out: int64 [n,H,W] or NULL;
- *     cm_out: int64 [n][num_class*num_class] per-image matrices or NULL;
+ *     cm_out: int64 [n][num_class*num_class] per-image matrices or NULL; cm_row_index: device int32 [n] or NULL —
+ *     when given, image j's matrix is written to row cm_row_index[j] of cm_out (the early-exit runner's compacted
+ *     batches scatter their results straight into the [N][nc*nc] result of the original batch);
  *     entropy_out: float [n] per-image normalized Shannon entropy (operations.py:161-170) or NULL.
  *     workspace: add_head_workspace_bytes() bytes.                                              */
 int64_t add_head_workspace_bytes(int n, int H, int W, int num_class);
 int add_upsample_argmax_fwd(const add_tensor_t* x, int H, int W, const int64_t* gt,
-                            int64_t* pred_out, int64_t* cm_out, float* entropy_out,
+                            int64_t* pred_out, int64_t* cm_out, const int32_t* cm_row_index, float* entropy_out,
                             void* workspace, int64_t workspace_bytes, void* stream);
 /* Same with uint8 labels (the Cityscapes PNG bytes; 255 = ignore, like any value >= num_class): 1 byte per pixel
  * instead of the 8 of the int64 tensor the reference's Evaluator receives. */
 int add_upsample_argmax_u8_fwd(const add_tensor_t* x, int H, int W, const uint8_t* gt_u8, int64_t* pred_out,
-                               int64_t* cm_out, float* entropy_out, void* workspace, int64_t workspace_bytes, void* stream);
+                               int64_t* cm_out, const int32_t* cm_row_index, float* entropy_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Loader edge: uint8 HWC images [n][h][w][3] (PIL / Cityscapes PNG layout) -> normalised fp32 NCHW [n][3][h][w], the
  * tensor eval.py:175 copies to the device.  Same arithmetic as the reference's host transforms (Normalize then ToTensor,

@@ -650,6 +650,114 @@ def sync_batchnorm_train(shards: Sequence[torch.Tensor], weight: Optional[torch.
     return outs, rm, rv, mean, inv_std
 
 
+def init_state_dict(arch: Arch, seed: int = 1) -> SD:
+    """A random-init, reference-format ``state_dict`` built WITHOUT any model class: the parameter names and shapes
+    of ``ADD.__init__`` (ADD.py:119-274; Cell :14-67; operations.py:18-119; aspp_train.py:8-32; decoder.py:8-21) and
+    the init rule of ``ADD._init_weight`` (ADD.py:491-500: kaiming-normal conv weights, BN gamma 1 / beta 0, running
+    stats (0, 1); the classifier bias keeps nn.Conv2d's default uniform init).  Key set and shapes equal the
+    reference's (checked in tests/test_oracle_golden.py); the VALUES are seeded here and are not the reference's RNG
+    stream — used where only the workload matters (bench.py's reference arm) and no product module may be imported."""
+    g = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    fm = {0: 1, 1: 2, 2: 4, 3: 8}
+    F_, B, na = arch.F, arch.B, list(arch.network_arch)
+    FB = F_ * B
+
+    def conv(key, co, ci, k):
+        fan_in = ci * k * k
+        sd[key] = torch.randn(co, ci, k, k, generator=g) * math.sqrt(2.0 / fan_in)      # kaiming_normal_, fan_in, relu gain
+
+    def bn(p, c):
+        sd[p + '.weight'] = torch.ones(c)
+        sd[p + '.bias'] = torch.zeros(c)
+        sd[p + '.running_mean'] = torch.zeros(c)
+        sd[p + '.running_var'] = torch.ones(c)
+        sd[p + '.num_batches_tracked'] = torch.zeros((), dtype=torch.int64)
+
+    def rcb(p, ci, co, k=1):                     # ReLUConvBN, operations.py:18-29
+        conv(p + '.op.1.weight', co, ci, k)
+        bn(p + '.op.2', co)
+
+    def fr(p, ci, co):                           # (Double)FactorizedReduce, operations.py:86-119
+        conv(p + '.conv_1.weight', co // 2, ci, 1)
+        conv(p + '.conv_2.weight', co // 2, ci, 1)
+        bn(p + '.bn', co)
+
+    # decoder (decoder.py:8-21) — registered first in ADD.__init__ (ADD.py:150)
+    conv('decoder._conv.1.weight', 256, 304, 3); bn('decoder._conv.2', 256)
+    conv('decoder._conv.4.weight', 256, 256, 3); bn('decoder._conv.5', 256)
+    conv('decoder._conv.7.weight', arch.num_classes, 256, 1)
+    bound = 1.0 / math.sqrt(256)
+    sd['decoder._conv.7.bias'] = (torch.rand(arch.num_classes, generator=g) * 2 - 1) * bound
+    # stems (ADD.py:154-169)
+    conv('stem0.0.weight', 64, 3, 3); bn('stem0.1', 64)
+    conv('stem1.0.weight', 64, 64, 3); bn('stem1.1', 64)
+    conv('stem2.1.weight', 128, 64, 3); bn('stem2.2', 128)
+    n = len(na)
+    for i in range(n):                           # ADD.py:171-240
+        p = f'cells.{i}'
+        C = F_ * fm[na[i]]
+        downup, dense_in, dense_out = _cell_kind(arch, i)
+        prev_C = 128 if i == 0 else FB * fm[na[i - 1]]
+        if downup == -1:
+            fr(p + '.preprocess', prev_C, C)
+        else:
+            rcb(p + '.preprocess', prev_C, C)
+        for k_, row in enumerate(np.asarray(arch.cell_arch)):
+            name = PRIMITIVES[int(row[1])]
+            q = f'{p}._ops.{k_}'
+            if name.startswith('sep_conv'):
+                k = int(name[-1])
+                conv(q + '.op.1.weight', C, 1, k); conv(q + '.op.2.weight', C, C, 1); bn(q + '.op.3', C)
+                conv(q + '.op.5.weight', C, 1, k); conv(q + '.op.6.weight', C, C, 1); bn(q + '.op.7', C)
+            elif name.startswith('dil_conv'):
+                k = int(name[-1])
+                conv(q + '.op.1.weight', C, C, k); bn(q + '.op.2', C)
+        if dense_in:
+            chans = [F_ * fm[s] for s in na[:i - 1]]
+            for j, c in enumerate(chans):
+                rcb(f'{p}.pre_preprocess.{j}', c, C)
+            rcb(p + '.pre_preprocess_1x1', len(chans) * C, C)
+        else:
+            pp_C = 64 if i == 0 else (128 if i == 1 else FB * fm[na[i - 2]])
+            rcb(p + '.pre_preprocess', pp_C, C)
+        if dense_out:
+            rcb(p + '.dense_process', C * B, C)
+    conv('low_level_conv.1.weight', 48, FB * 2 ** na[arch.low_level_layer], 1); bn('low_level_conv.2', 48)
+    cin = FB * fm[na[-1]]                        # aspp_train.py:8-32
+    conv('aspp.aspp1.weight', 256, cin, 1)
+    for k_ in (2, 3, 4):
+        conv(f'aspp.aspp{k_}.weight', 256, cin, 3)
+    conv('aspp.aspp5.weight', 256, cin, 1)
+    conv('aspp.conv1.weight', 256, 1280, 1)
+    bn('aspp.bn1', 256)
+    for k_ in range(1, 6):
+        bn(f'aspp.aspp{k_}_bn', 256)
+    it = 0
+    for c in arch.C_index:                       # ADD.py:265-273
+        d = na[c] - na[-1]
+        if d in (-1, -2):
+            fr(f'conv_aspp.{it}', FB * 2 ** na[c], FB * 2 ** na[-1]); it += 1
+        elif d > 0:
+            rcb(f'conv_aspp.{it}', FB * 2 ** na[c], FB * 2 ** na[-1]); it += 1
+    return sd
+
+
+def init_edm_state_dict(seed: int = 203) -> SD:
+    """EDM parameters (ADD.py:502-513): conv [128,400,3,3] without bias, Linear 128-64-32-1 — nn default
+    (kaiming-uniform a=sqrt(5)) init ranges, seeded here (values are not the reference's RNG stream)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def uni(shape, fan_in):
+        b = 1.0 / math.sqrt(fan_in)
+        return (torch.rand(*shape, generator=g) * 2 - 1) * b
+    sd = {'conv.weight': uni((128, 400, 3, 3), 400 * 9)}
+    for idx, (o, i) in zip((0, 2, 4), ((64, 128), (32, 64), (1, 32))):
+        sd[f'edm.{idx}.weight'] = uni((o, i), i)
+        sd[f'edm.{idx}.bias'] = uni((o,), i)
+    return sd
+
+
 def randomize_bn_(sd: SD, seed: int = 7) -> SD:
     """Give every BN non-trivial affine params and running stats so BN folding is exercised."""
     g = torch.Generator().manual_seed(seed)

@@ -2,7 +2,7 @@
 """How much of a bench step is the gate's host round trip?  Times (a) the normal step (`dynamic_evaluate`: trunk graph
 -> D2H of N gate values -> host decision -> head / remaining-trunk graphs) and (b) the SAME graphs replayed back to
 back with the indices left as the last step wrote them (no host decision in between).  (a) - (b) = GPU idle time per
-step caused by the gate.  Usage: python tools/bubble_test.py [steps]"""
+step caused by the gate.  Usage: python tools/gate_bubble.py [steps]"""
 import sys
 import time
 from pathlib import Path
