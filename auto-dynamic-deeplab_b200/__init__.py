@@ -19,6 +19,8 @@ from .cell_level_search import MixedOp
 from .metrics import Evaluator
 from .factory import build_add, Args, synthetic_batch, synthetic_batch_u8, normalize_u8_hwc_host
 from .pipeline import HostPipeline, ResidentPipeline
+from .io_edges import (encode_segmap, decode_segmap, full_image_eval_preprocess, load_checkpoint, pad_labels,
+                       get_cityscapes_labels, cityscapes_label_lut)
 from .parallel import shard_range, env_rank_world, all_reduce_confusion
 
 __version__ = "0.1.0"

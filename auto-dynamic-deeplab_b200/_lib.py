@@ -75,6 +75,9 @@ _SIGS = {
     "add_upsample_argmax_fwd": (c_int, [TP, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "add_upsample_argmax_u8_fwd": (c_int, [TP, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "add_normalize_u8_hwc_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [ctypes.c_double] * 6 + [c_void_p]),
+    "add_encode_pad_labels_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "add_normalize_pad_u8_hwc_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int] + [ctypes.c_double] * 6 + [c_void_p]),
+    "add_decode_segmap": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "add_widen_labels_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "add_confusion_workspace_bytes": (c_int64, [c_int64, c_int]),
     "add_confusion_matrix": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),

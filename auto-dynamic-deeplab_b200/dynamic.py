@@ -212,7 +212,8 @@ class _EdmRunner:
         self.gt_full: Optional[torch.Tensor] = None
         self.cm_full: Optional[torch.Tensor] = None
         if mode == "evaluate":
-            self.cm_full = torch.zeros((self.n, self.nc, self.nc), dtype=torch.int64, device=device)
+            self.cm_store = torch.zeros((self.n + 1, self.nc, self.nc), dtype=torch.int64, device=device)   # row N: spare
+            self.cm_full = self.cm_store[:self.n]
             # labels: the reference's int64 tensors, or uint8 (the PNG bytes: 8x less gather / histogram traffic)
             self.label_dtype = label_dtype
             self.gt_full = (bound[1] if bound is not None else
@@ -221,7 +222,7 @@ class _EdmRunner:
         self._side: Optional[torch.cuda.Stream] = None
         # pinned staging for the gate's host round trip (N floats down, a few index vectors up): no pageable copies
         self._conf_pin = torch.empty(self.n, dtype=torch.float32).pin_memory()
-        self._idx_pin = torch.empty((16, self.n), dtype=torch.int32).pin_memory()
+        self._idx_pin = torch.empty((16, 2 * self.n), dtype=torch.int32).pin_memory()
         self._idx_np = self._idx_pin.numpy()
         self._idx_slot = 0
 
@@ -232,12 +233,16 @@ class _EdmRunner:
             b.upsample_logits(logits, out, self.H, self.W, "ADD.upsample_logits")
             return out
         gt = b.raw((m, self.H, self.W), self.label_dtype)
-        owner.idx_gt = b.raw((m,), torch.int32, zero=True)          # ORIGINAL image ids of this plan's rows
-        b.gather_images(self.gt_full, gt, owner.idx_gt, "dynamic.gather.gt")
-        # every plan scatters its rows' matrices straight into the [N, nc, nc] result of the original batch
-        # (cm_row_index of add_upsample_argmax_fwd): no stacking of per-plan outputs afterwards
-        b.upsample_argmax(logits, self.H, self.W, gt, None, self.cm_full, None, "ADD.upsample_argmax_cm",
-                          cm_rows=owner.idx_gt)
+        # ORIGINAL image ids of this plan's rows, twice: [0, m) drives the label gather, [m, 2m) the scatter of the
+        # confusion matrices into the [N, nc, nc] result of the original batch (cm_row_index of
+        # add_upsample_argmax_fwd: no stacking of per-plan outputs afterwards).  Until the host uploads real ids (the
+        # warm-up run of Plan.capture) the gather reads image 0 and the scatter goes to the spare row N of cm_store,
+        # so recording a plan never disturbs results that other plans have already written for this batch.
+        owner.idx_gt = torch.tensor([0] * m + [self.n] * m, dtype=torch.int32).to(self.device)    # host-built: a memcpy
+        b.keep.append(owner.idx_gt)
+        b.gather_images(self.gt_full, gt, owner.idx_gt[:m], "dynamic.gather.gt")
+        b.upsample_argmax(logits, self.H, self.W, gt, None, self.cm_store, None, "ADD.upsample_argmax_cm",
+                          cm_rows=owner.idx_gt[m:])
         return self.cm_full
 
     def segment(self, k: int, m: int, prev: Optional[_Segment]) -> _Segment:
@@ -312,7 +317,7 @@ class _EdmRunner:
                 seg.gather.run()
                 self.last_plans.append(seg.gather)
             if k == len(self.exits) and self.mode == "evaluate":
-                self._put_idx(seg.idx_gt, active)
+                self._put_idx(seg.idx_gt, list(active) * 2)
             seg.main.run()
             self.last_plans.append(seg.main)
             launches += seg.n_launches
@@ -336,7 +341,7 @@ class _EdmRunner:
                 head = self.head(k, len(ex), seg)
                 self._put_idx(head.idx, ex)
                 if self.mode == "evaluate":
-                    self._put_idx(head.idx_gt, [active[j] for j in ex])
+                    self._put_idx(head.idx_gt, [active[j] for j in ex] * 2)
                 if co and _OVERLAP_HEADS:
                     # the early-exit head (throughput-bound: ASPP on the up-sampled map) and the remaining trunk
                     # (latency-bound small kernels) only READ this segment's state: replay them side by side

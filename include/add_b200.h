@@ -211,6 +211,23 @@ int add_upsample_argmax_fwd(const add_tensor_t* x, int H, int W, const int64_t* 
 int add_upsample_argmax_u8_fwd(const add_tensor_t* x, int H, int W, const uint8_t* gt_u8, int64_t* pred_out,
                                int64_t* cm_out, const int32_t* cm_row_index, float* entropy_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- loader / dump edges ------------------------------------------------------------------ */
+/* Cityscapes label ids -> train ids (dataloaders/datasets/cityscapes.py:85-91: void ids -> 255, valid ids -> 0..18) as a
+ * 256-entry device table, fused with the bottom / right pad of the evaluation transform (custom_transforms.py:344,
+ * ConstantPad2d(..., 255)): dst[n][Hp][Wp] = lut[src[n][h][w]] inside the image, `fill` outside.  lut256_dev NULL =
+ * identity (pad only). */
+int add_encode_pad_labels_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int Hp, int Wp,
+                             const uint8_t* lut256_dev, int fill, void* stream);
+/* full_image_eval_preprocess (custom_transforms.py:322-347): uint8 HWC [n][h][w][3] -> ToTensor + Normalize (the
+ * arithmetic of add_normalize_u8_hwc_to_nchw, bit-identical) -> zero pad to [n][3][Hp][Wp] fp32 (ZeroPad2d AFTER the
+ * normalisation, so the padding is exactly 0). */
+int add_normalize_pad_u8_hwc_to_nchw(const uint8_t* src, float* dst, int n, int h, int w, int Hp, int Wp, double mean0,
+                                     double mean1, double mean2, double std0, double std1, double std2, void* stream);
+/* decode_segmap (dataloaders/utils.py:14-51): class map (int64 if labels_are_int64 else uint8) -> uint8 RGB [n_pixels][3]
+ * through a 256 x 3 device table (rows >= 19: the label value itself in all three channels, like the reference). */
+int add_decode_segmap(const void* labels, int labels_are_int64, uint8_t* rgb, int64_t n_pixels, const uint8_t* lut768_dev,
+                      void* stream);
+
 /* Loader edge: uint8 HWC images [n][h][w][3] (PIL / Cityscapes PNG layout) -> normalised fp32 NCHW [n][3][h][w], the
  * tensor eval.py:175 copies to the device.  Same arithmetic as the reference's host transforms (Normalize then ToTensor,
  * dataloaders/custom_transforms.py:17-24, :39: /255 in float32, -mean and /std through float64), bit-identical. */

@@ -778,6 +778,38 @@ def randomize_bn_(sd: SD, seed: int = 7) -> SD:
     return sd
 
 
+def calibrate_bn_(sd: SD, arch: Arch, size: Tuple[int, int] = (129, 257), n: int = 8, seed: int = 77,
+                  affine_seed: Optional[int] = 23, var_floor: float = 1e-2) -> SD:
+    """BN-CALIBRATED weights: one TRAINING-mode forward (batch statistics, momentum 1.0) over a seeded
+    synthetic batch writes every BatchNorm's running mean / variance, exactly as the first step of train.py would
+    (train.py:227 under model.train()); afterwards the eval-mode activations are O(1) at every depth instead of growing
+    to 1e8 with identity statistics, so tolerances on the logits are meaningful.  `affine_seed`:
+    also give gamma / beta non-trivial values first (so the BN fold is exercised).  `var_floor`: the image-pool
+    branch's BN (aspp5_bn, aspp_train.py:49-53) sees only N values per channel in one step — on a calibration batch of a
+    few images its variance can come out at 1e-5..1e-10, an inv_std of ~300 that a running average over thousands of
+    training steps never has; running variances are floored at `var_floor` (0 disables).  In place; returns sd."""
+    if affine_seed is not None:
+        g = torch.Generator().manual_seed(affine_seed)
+        for k in sorted(sd.keys()):
+            base = k.rsplit('.', 1)[0]
+            if base + '.running_mean' in sd:
+                if k.endswith('.weight'):
+                    sd[k] = torch.rand(sd[k].shape, generator=g) * 0.5 + 0.75
+                elif k.endswith('.bias'):
+                    sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+    for k in sd:
+        if k.endswith('running_mean') or k.endswith('running_var'):
+            sd[k] = sd[k].clone()
+    x, _ = synthetic_batch(n, size[0], size[1], seed)
+    with torch.no_grad(), bn_training(momentum=1.0):
+        add_forward(sd, arch, x)
+    if var_floor > 0:
+        for k in sd:
+            if k.endswith('running_var'):
+                sd[k].clamp_(min=var_floor)
+    return sd
+
+
 CITYSCAPES_MEAN = (0.29866842, 0.30135223, 0.30561872)     # dataloaders/datasets/cityscapes.py:53
 CITYSCAPES_STD = (0.23925215, 0.23859318, 0.2385942)       # dataloaders/datasets/cityscapes.py:54
 
@@ -801,3 +833,53 @@ def synthetic_batch(n: int, h: int, w: int, seed: int = 1234, num_class: int = 1
     ign = torch.rand(n, h, w, generator=g) < 0.1
     gt[ign] = 255
     return x, gt
+
+
+# --------------------------------------------------------------------------------------
+# loader / dump edges
+# --------------------------------------------------------------------------------------
+CITYSCAPES_VOID = [0, 1, 2, 3, 4, 5, 6, 9, 10, 14, 15, 16, 18, 29, 30, -1]                           # cityscapes.py:44
+CITYSCAPES_VALID = [7, 8, 11, 12, 13, 17, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 31, 32, 33]      # cityscapes.py:45
+
+
+def encode_segmap(mask: np.ndarray, ignore_index: int = 255) -> np.ndarray:
+    """dataloaders/datasets/cityscapes.py:85-91 — the in-place cascade, restated literally (on a copy)."""
+    mask = mask.copy()
+    class_map = dict(zip(CITYSCAPES_VALID, range(len(CITYSCAPES_VALID))))
+    for voidc in CITYSCAPES_VOID:
+        mask[mask == voidc] = ignore_index
+    for validc in CITYSCAPES_VALID:
+        mask[mask == validc] = class_map[validc]
+    return mask
+
+
+def full_image_eval_preprocess(img_u8: np.ndarray, mask_u8: np.ndarray, crop_size, mean=CITYSCAPES_MEAN, std=CITYSCAPES_STD):
+    """dataloaders/custom_transforms.py:322-347: ToTensor (/255, CHW) -> Normalize -> ZeroPad2d / ConstantPad2d(255) to
+    at least crop_size (bottom / right).  img_u8 [H,W,3], mask_u8 [H,W] -> (fp32 [3,Hp,Wp], int64 [Hp,Wp])."""
+    t = torch.from_numpy(img_u8).permute(2, 0, 1).contiguous().to(torch.float32).div(255)          # transforms.ToTensor
+    m_, s_ = torch.as_tensor(mean, dtype=torch.float32), torch.as_tensor(std, dtype=torch.float32)
+    t = (t - m_.view(-1, 1, 1)) / s_.view(-1, 1, 1)                                                  # transforms.Normalize
+    mask = torch.from_numpy(mask_u8.astype(np.int64))
+    h, w = t.shape[1], t.shape[2]
+    pad_tb, pad_lr = max(0, crop_size[0] - h), max(0, crop_size[1] - w)
+    t = F.pad(t, (0, pad_lr, 0, pad_tb), value=0.0)
+    mask = F.pad(mask, (0, pad_lr, 0, pad_tb), value=255)
+    return t, mask
+
+
+CITYSCAPES_COLOURS = np.array([[128, 64, 128], [244, 35, 232], [70, 70, 70], [102, 102, 156], [190, 153, 153], [153, 153, 153],
+                               [250, 170, 30], [220, 220, 0], [107, 142, 35], [152, 251, 152], [0, 130, 180], [220, 20, 60],
+                               [255, 0, 0], [0, 0, 142], [0, 0, 70], [0, 60, 100], [0, 80, 100], [0, 0, 230], [119, 11, 32]])
+
+
+def decode_segmap(label_mask: np.ndarray) -> np.ndarray:
+    """dataloaders/utils.py:14-51 (dataset='cityscapes'): float64 [H,W,3] in units of 1/255; labels outside [0,19) keep
+    their own value in the three channels."""
+    r, g, b = label_mask.copy(), label_mask.copy(), label_mask.copy()
+    for ll in range(19):
+        r[label_mask == ll] = CITYSCAPES_COLOURS[ll, 0]
+        g[label_mask == ll] = CITYSCAPES_COLOURS[ll, 1]
+        b[label_mask == ll] = CITYSCAPES_COLOURS[ll, 2]
+    rgb = np.zeros((label_mask.shape[0], label_mask.shape[1], 3))
+    rgb[:, :, 0], rgb[:, :, 1], rgb[:, :, 2] = r / 255.0, g / 255.0, b / 255.0
+    return rgb

@@ -254,7 +254,81 @@ def gen_mixed_op():
     print("mixed_op.npz", len(g), "arrays")
 
 
+def gen_gates():
+    """`dynamic_inference(confidence='entropy' | 'max')` (ADD.py:440-488), the unmodified reference.  The reference
+    returns the feature map `x` there instead of the logits (:488); what the exit head produced is recorded through a
+    forward hook on `ref.decoder` (observation only).  Stored per gate and per decision: the earlier_exit flag, the
+    confidence value, the logits of the LAST decoder call (= the exit that was taken) and |x|-sum of the returned map."""
+    g = {}
+    spec = util.NET_CASES["searched-dense-C2"]
+    ours = util.make_net(spec)
+    na, ci, low = util.net_arch(spec)
+    ref = RefADD(na, ci, util.cell_arch(), 19, SimpleNamespace(F=spec["F"], B=5, sync_bn=False), low)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ref.eval()
+    seen = []
+    ref.decoder.register_forward_hook(lambda m, i, o: seen.append(o.detach().clone()))
+    for (h, w) in spec["sizes"]:
+        x, _ = util.make_input(1, h, w)
+        tag = f"searched-dense-C2/{h}x{w}"
+        # entropy of the first exit's logits decides; thresholds on either side of it
+        with torch.no_grad():
+            seen.clear()
+            _, _, _, e0 = ref.dynamic_inference(x, threshold=-1.0, confidence='entropy')      # never exits: e0 = exit-1 entropy
+        g[f"{tag}/entropy/value"] = np.float64(e0)
+        cases = [("entropy", "exit", float(e0) + 0.05), ("entropy", "noexit", float(e0) - 0.05),
+                 ("max", "exit", 0.05), ("max", "noexit", 1.0)]
+        for conf, label, thr in cases:
+            seen.clear()
+            with torch.no_grad():
+                xret, ee, _, cv = ref.dynamic_inference(x, threshold=thr, confidence=conf)
+            assert ee == (1 if label == "exit" else 0), (conf, label, thr, ee, cv)
+            k = f"{tag}/{conf}/{label}"
+            g[k + "/threshold"] = np.float64(thr)
+            g[k + "/conf"] = np.float64(float(cv))
+            g[k + "/y"] = f32(seen[-1])
+            g[k + "/n_heads"] = np.int64(len(seen))
+            g[k + "/x_abs_sum"] = np.float64(xret.double().abs().sum().item())
+    g["searched-dense-C2/wsum"] = np.float64(util.weight_checksum(ours.state_dict()))
+    np.savez_compressed(OUT / "gates.npz", **g)
+    print("gates.npz", len(g), "entries", os.path.getsize(OUT / "gates.npz") / 1e6, "MB")
+
+
+def gen_io_edges():
+    """Loader / dump edges, the unmodified reference: CityscapesSegmentation.encode_segmap (cityscapes.py:85-91; the
+    class is constructed with its file glob stubbed — the dataset is not here), full_image_eval_preprocess
+    (custom_transforms.py:322-347) on PIL inputs, decode_segmap (dataloaders/utils.py:14-51; matplotlib, which that
+    module imports for its optional plot, is absent here and stubbed)."""
+    import types
+    from PIL import Image
+    sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
+    sys.modules.setdefault("matplotlib.pyplot", types.ModuleType("matplotlib.pyplot"))
+    from dataloaders.datasets.cityscapes import CityscapesSegmentation
+    from dataloaders import custom_transforms as tr
+    from dataloaders.utils import decode_segmap as ref_decode
+    CityscapesSegmentation.recursive_glob = lambda self, rootdir='.', suffix='': ['stub.png']
+    ds = CityscapesSegmentation(None, root='/tmp', split='val')
+    g = {}
+    g["encode/all_ids"] = ds.encode_segmap(np.arange(256, dtype=np.uint8).reshape(16, 16).copy())
+    for name, spec in util.IO_CASES.items():
+        img, ids = util.make_io_case(name)
+        enc = ds.encode_segmap(ids.copy())
+        g[f"{name}/encoded"] = enc
+        out = tr.full_image_eval_preprocess(spec["crop"], ds.mean, ds.std)({'image': Image.fromarray(img), 'label': Image.fromarray(enc)})
+        g[f"{name}/image"] = f32(out['image'])
+        g[f"{name}/label"] = out['label'].numpy().astype(np.int64)
+        g[f"{name}/decoded"] = ref_decode(enc.astype(np.int64), 'cityscapes')
+    np.savez_compressed(OUT / "io_edges.npz", **g)
+    print("io_edges.npz", len(g), "arrays")
+
+
 if __name__ == "__main__":
+    if "--only-io" in sys.argv:
+        gen_io_edges()
+        sys.exit(0)
+    if "--only-gates" in sys.argv:
+        gen_gates()
+        sys.exit(0)
     if "--only-syncbn" in sys.argv:
         gen_syncbn()
         gen_train_ops()
@@ -266,3 +340,5 @@ if __name__ == "__main__":
     gen_syncbn()
     gen_train_ops()
     gen_mixed_op()
+    gen_gates()
+    gen_io_edges()

@@ -99,6 +99,28 @@ def test_entropy_gate_runs_and_matches_oracle():
     assert util.rel_err(y, y_ref) < 1e-3
 
 
+GATES = np.load(util.ROOT / "tests/golden/gates.npz")
+
+
+@pytest.mark.parametrize("conf", ["entropy", "max"])
+@pytest.mark.parametrize("label", ["exit", "noexit"])
+def test_entropy_and_max_gates_match_reference(conf, label):
+    """dynamic_inference(confidence='entropy' | 'max') (ADD.py:440-488) against fixtures made by the unmodified
+    reference: same decision, same confidence value, and the logits of the exit taken (the reference returns the
+    feature map there, :488; we return the logits — INTEGRATION.md lists the deviation)."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec).to(DEV)
+    for (h, w) in spec["sizes"]:
+        x, _ = util.make_input(1, h, w)
+        k = f"searched-dense-C2/{h}x{w}/{conf}/{label}"
+        y, ee, secs, cv = net.dynamic_inference(x.to(DEV), threshold=float(GATES[k + "/threshold"]), confidence=conf)
+        assert ee == (1 if label == "exit" else 0)
+        assert float(cv) == pytest.approx(float(GATES[k + "/conf"]), rel=1e-3, abs=1e-5)
+        ref = torch.from_numpy(GATES[k + "/y"])
+        assert util.rel_err(y, ref) < 1e-3
+        assert _agree(y.cpu(), ref) >= 0.999
+
+
 def test_batched_edm_gating_matches_per_image():
     """Per-image gating of a batch (compaction) == the batch-1 reference control flow per image."""
     spec = util.NET_CASES["searched-dense-C2"]
@@ -250,3 +272,48 @@ def test_sibling_models(cname, precision, tol, agree_min):
         ref = torch.from_numpy(sibs[f"{cname}/forward/{e}"])
         assert util.rel_err(o, ref) < tol
         assert _agree(o.cpu(), ref) >= agree_min
+
+
+def test_three_gated_exits_plan_cache_lineage():
+    """A network with THREE EDM-gated exits and a batch of 6: with >= 3 gates several compacted segments share
+    (exit index, image count) and differ only in which earlier segment they continue — the recorded plans are keyed by
+    that lineage.  Calls with different exit patterns, back to back on the same runner, must each equal the batch-1
+    control flow (ADD.py:394-438) per image, and the oracle."""
+    na, ci = [1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2], [3, 6, 9]       # every gated exit at level 2: 400-channel features (EDM, ADD.py:508)
+    torch.manual_seed(1)
+    net = add_b200.ADD(na, ci, add_b200.AUTODEEPLAB_CELL.copy(), 19, add_b200.Args(20, 5), 0)
+    net = util._randomized(net, 21).to(DEV)
+    edm = util.make_edm().to(DEV)
+    n = 6
+    x, gt = util.make_input(n, 33, 65, seed=77)
+    xd, gtd = x.to(DEV), gt.to(DEV)
+    # gate values of every image at every gate: run with thresholds that never exit, image by image, and record the trail
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    edm_sd = {k: v.detach().cpu() for k, v in edm.state_dict().items()}
+    arch = orc.Arch(na, ci, util.cell_arch(), 19, 20, 5, 0)
+    firsts = []
+    for i in range(n):
+        _, _, _, cv = net.dynamic_inference(xd[i:i + 1], threshold=1e30, confidence='edm', edm=edm)   # exits at gate 1
+        firsts.append(float(cv))
+    srt = sorted(firsts)
+    patterns_seen = set()
+    for thr in (0.5 * (srt[1] + srt[2]), 0.5 * (srt[3] + srt[4]), srt[0] - 1.0, 0.5 * (srt[2] + srt[3]), 0.5 * (srt[1] + srt[2])):
+        ref = [net.dynamic_inference(xd[i:i + 1], threshold=thr, confidence='edm', edm=edm) for i in range(n)]
+        ref = [(r[0].clone(), r[1], float(r[3])) for r in ref]
+        ys, flags, confs = net.dynamic_inference_batch(xd, thr, 'edm', edm)
+        assert flags == [r[1] for r in ref]
+        for i in range(n):
+            assert util.rel_err(ys[i], ref[i][0]) < 1e-6, (thr, i)
+            assert float(confs[i]) == pytest.approx(ref[i][2], rel=1e-5, abs=1e-6)
+        cms, flags2, _ = net.dynamic_evaluate(xd, gtd, thr, edm)
+        assert flags2 == flags
+        for i in range(n):
+            want = orc.generate_matrix(gt[i].numpy(), ref[i][0].argmax(1).cpu().numpy())
+            assert np.array_equal(cms[i].cpu().numpy(), want), (thr, i)
+        patterns_seen.add(tuple(flags))
+    assert len(patterns_seen) >= 3
+    # one image against the oracle (reference control flow with three gates)
+    with torch.no_grad():
+        y_ref, ee_ref, cv_ref = orc.add_dynamic_inference(sd, arch, x[0:1], 0.5 * (srt[2] + srt[3]), 'edm', edm_sd)
+    y, ee, _, cv = net.dynamic_inference(xd[0:1], threshold=0.5 * (srt[2] + srt[3]), confidence='edm', edm=edm)
+    assert ee == ee_ref and util.rel_err(y, y_ref) < 1e-3

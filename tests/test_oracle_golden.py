@@ -139,3 +139,43 @@ def test_sibling_models_match_reference(cname):
             outs = [orc.autodeeplab_forward(sd, orc.Arch(na, [], low_level_layer=low), x)]
     for e, o in enumerate(outs):
         assert util.rel_err(o, torch.from_numpy(SIBS[f"{cname}/forward/{e}"])) < TOL
+
+
+GATES = np.load(util.ROOT / "tests/golden/gates.npz")
+GATE_CASES = [(h, w, conf, label) for (h, w) in util.NET_CASES["searched-dense-C2"]["sizes"]
+              for conf in ("entropy", "max") for label in ("exit", "noexit")]
+
+
+@pytest.mark.parametrize("h,w,conf,label", GATE_CASES)
+def test_entropy_and_max_gates_match_reference(h, w, conf, label):
+    """ADD.py:440-488 — the 'entropy' and 'max' gates of dynamic_inference, against fixtures produced by the
+    unmodified reference (the logits of the exit it took were observed through a hook on its decoder; the reference
+    itself returns the feature map `x`, :488 — the oracle returns those logits, a documented deviation)."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec)
+    assert util.weight_checksum(net.state_dict()) == pytest.approx(float(GATES["searched-dense-C2/wsum"]), rel=1e-12)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    x, _ = util.make_input(1, h, w)
+    k = f"searched-dense-C2/{h}x{w}/{conf}/{label}"
+    with torch.no_grad():
+        y, ee, cv = orc.add_dynamic_inference(sd, util.oracle_arch(spec), x, float(GATES[k + "/threshold"]), conf)
+    assert ee == (1 if label == "exit" else 0)
+    assert float(cv) == pytest.approx(float(GATES[k + "/conf"]), rel=1e-4, abs=1e-6)
+    assert util.rel_err(y, torch.from_numpy(GATES[k + "/y"])) < TOL
+
+
+IO = np.load(util.ROOT / "tests/golden/io_edges.npz")
+
+
+def test_io_edges_oracle_matches_reference():
+    """Loader / dump edges: encode_segmap, full_image_eval_preprocess and decode_segmap restated in
+    the oracle against fixtures produced by the unmodified reference classes / functions."""
+    assert np.array_equal(orc.encode_segmap(np.arange(256, dtype=np.uint8).reshape(16, 16)), IO["encode/all_ids"])
+    for name, spec in util.IO_CASES.items():
+        img, ids = util.make_io_case(name)
+        enc = orc.encode_segmap(ids)
+        assert np.array_equal(enc, IO[f"{name}/encoded"])
+        t, m = orc.full_image_eval_preprocess(img, enc, spec["crop"])
+        assert t.shape == IO[f"{name}/image"].shape and np.array_equal(t.numpy(), IO[f"{name}/image"])    # bit-identical
+        assert np.array_equal(m.numpy(), IO[f"{name}/label"])
+        assert np.array_equal(orc.decode_segmap(enc.astype(np.int64)), IO[f"{name}/decoded"])

@@ -240,3 +240,21 @@ def make_mixed_op_case(name):
     x = torch.randn(*spec["x"], generator=g)
     w = torch.softmax(torch.randn(8, generator=g), dim=0)
     return m, x, w
+
+
+# ---- loader / dump edges ----------------------------------------------------------------------
+IO_CASES = {
+    "pad_both": dict(h=37, w=64, crop=(40, 70), seed=51),
+    "no_pad": dict(h=45, w=80, crop=(40, 70), seed=52),
+    "pad_rows": dict(h=33, w=70, crop=(41, 70), seed=53),
+}
+
+
+def make_io_case(name):
+    """(uint8 image [H,W,3], uint8 label-id map [H,W] covering every id 0..255 at least once when it fits)."""
+    spec = IO_CASES[name]
+    g = torch.Generator().manual_seed(spec["seed"])
+    img = torch.randint(0, 256, (spec["h"], spec["w"], 3), generator=g, dtype=torch.int64).to(torch.uint8)
+    ids = torch.randint(0, 40, (spec["h"], spec["w"]), generator=g, dtype=torch.int64)
+    ids.view(-1)[:256] = torch.arange(256)
+    return img.numpy(), ids.to(torch.uint8).numpy()
