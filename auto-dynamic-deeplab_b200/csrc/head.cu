@@ -140,12 +140,29 @@ upsample_argmax_runs_kernel(const HeadParams p) {
   const long long HW = (long long)p.H * p.W;
   const float* xn = p.x + (size_t)n * p.h * p.w * p.xs;
   const float inv_logc = 1.f / logf((float)NC);
+  constexpr int NCV = (NC + 3) / 4;
+  const bool vec4 = (p.xs % 4 == 0) && (p.xs >= 4 * NCV) && (((uintptr_t)p.x & 15) == 0);
+  const bool want_gt = do_hist && (p.gt || p.gt8);
   double ent = 0.0;
   for (long long base = start + warp * 32; base < end; base += HD_THREADS) {      // uniform trip count per warp
     const long long run = base + lane;
     const bool live = run < end;
     const int oy = live ? (int)(run / runs_per_row) : 0;
     const int ox_first = live ? ((int)(run % runs_per_row) * 8 - 4) : 0;
+    const size_t row_pix = (size_t)n * HW + (size_t)oy * p.W;
+    // the run's 8 labels first, all loads in flight together: inside the pixel loop each one was a dependent global
+    // round trip in front of that pixel's histogram update (ncu r4: the kernel sat at 0.07 of HBM with ~half its issue
+    // slots idle, stalled on these loads — not on the 19-class interpolation)
+    // (labels outside [0, NC) -> 255 = no sample; the 8 of them packed into one 64-bit register)
+    unsigned long long g8 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ox = ox_first + j;
+      long long g = -1;
+      if (want_gt && live && ox >= 0 && ox < p.W)
+        g = p.gt8 ? (long long)__ldg(p.gt8 + row_pix + ox) : __ldg(p.gt + row_pix + ox);
+      g8 |= (unsigned long long)((g >= 0 && g < NC) ? (unsigned)g : 255u) << (8 * j);
+    }
     int y0, y1; float hl0, hl1;
     bilinear_src(oy, p.sh, p.h, y0, y1, hl0, hl1);
     const float* row0 = xn + (size_t)y0 * p.w * p.xs;
@@ -162,34 +179,47 @@ upsample_argmax_runs_kernel(const HeadParams p) {
         if (x0 != cx0 || x1 != cx1) {
           const float* a0 = row0 + (size_t)x0 * p.xs; const float* a1 = row0 + (size_t)x1 * p.xs;
           const float* b0 = row1 + (size_t)x0 * p.xs; const float* b1 = row1 + (size_t)x1 * p.xs;
+          if (vec4) {      // 16-byte loads: a pixel's NC logits + padding are NCV = ceil(NC / 4) float4 (pix_stride >= 4 * NCV)
 #pragma unroll
-          for (int c = 0; c < NC; ++c) { v00[c] = __ldg(a0 + c); v01[c] = __ldg(a1 + c); v10[c] = __ldg(b0 + c); v11[c] = __ldg(b1 + c); }
+            for (int c4 = 0; c4 < NCV; ++c4) {
+              const float4 t0 = __ldg(reinterpret_cast<const float4*>(a0) + c4), t1 = __ldg(reinterpret_cast<const float4*>(a1) + c4);
+              const float4 t2 = __ldg(reinterpret_cast<const float4*>(b0) + c4), t3 = __ldg(reinterpret_cast<const float4*>(b1) + c4);
+              const float e0[4] = {t0.x, t0.y, t0.z, t0.w}, e1[4] = {t1.x, t1.y, t1.z, t1.w};
+              const float e2[4] = {t2.x, t2.y, t2.z, t2.w}, e3[4] = {t3.x, t3.y, t3.z, t3.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (4 * c4 + u < NC) { v00[4 * c4 + u] = e0[u]; v01[4 * c4 + u] = e1[u]; v10[4 * c4 + u] = e2[u]; v11[4 * c4 + u] = e3[u]; }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { v00[c] = __ldg(a0 + c); v01[c] = __ldg(a1 + c); v10[c] = __ldg(b0 + c); v11[c] = __ldg(b1 + c); }
+          }
           cx0 = x0; cx1 = x1;
         }
-        float v[NC];
-        float best = -INFINITY; int arg = 0;
+        int arg = 0;
+        {
+          float v[NC];
+          float best = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const float val = hl0 * (wl0 * v00[c] + wl1 * v01[c]) + hl1 * (wl0 * v10[c] + wl1 * v11[c]);
-          v[c] = val;
-          if (val > best) { best = val; arg = c; }    // first maximum wins, like torch.argmax
-        }
-        if (WANT_ENT) {
-          float s = 0.f;
+          for (int c = 0; c < NC; ++c) {
+            const float val = hl0 * (wl0 * v00[c] + wl1 * v01[c]) + hl1 * (wl0 * v10[c] + wl1 * v11[c]);
+            v[c] = val;
+            if (val > best) { best = val; arg = c; }    // first maximum wins, like torch.argmax
+          }
+          if (WANT_ENT) {
+            float s = 0.f;
 #pragma unroll
-          for (int c = 0; c < NC; ++c) s += expf(v[c] - best);
-          const float logs = logf(s);
-          float e = 0.f;
+            for (int c = 0; c < NC; ++c) s += expf(v[c] - best);
+            const float logs = logf(s);
+            float e = 0.f;
 #pragma unroll
-          for (int c = 0; c < NC; ++c) { const float lp = v[c] - best - logs; e += expf(lp) * lp; }
-          ent += (double)(-e * inv_logc);
+            for (int c = 0; c < NC; ++c) { const float lp = v[c] - best - logs; e += expf(lp) * lp; }
+            ent += (double)(-e * inv_logc);
+          }
         }
-        const size_t pix = (size_t)n * HW + (size_t)oy * p.W + ox;
-        if (p.pred) p.pred[pix] = arg;
-        if (do_hist && (p.gt || p.gt8)) {
-          const long long g = p.gt8 ? (long long)__ldg(p.gt8 + pix) : __ldg(p.gt + pix);
-          if (g >= 0 && g < NC) bin = (int)g * NC + arg;
-        }
+        if (p.pred) p.pred[row_pix + ox] = arg;
+        const int lab = (int)((g8 >> (8 * j)) & 0xffull);
+        if (lab < NC) bin = lab * NC + arg;
       }
       if (do_hist) warp_hist_add(hist[warp], bin, lane);
     }
@@ -295,26 +325,38 @@ confusion_kernel(const long long* __restrict__ gt, const long long* __restrict__
   __syncthreads();
   const long long per = ((n_pix + gridDim.x - 1) / gridDim.x + 1) & ~1ll;   // even -> 16 B aligned pairs
   const long long start = blockIdx.x * per, end = (start + per < n_pix) ? start + per : n_pix;
-  // two pixels per lane per iteration: 16-byte loads when both bases are 16-byte aligned (vec_ok), else two 8-byte
-  // loads each (a per-image slice of an odd-sized map, e.g. target[i] of 1025x2049 labels, starts 8 bytes off)
-  for (long long base = start + warp * 64; base < end; base += HD_THREADS * 2) {
-    long long pix = base + lane * 2;
-    int bin0 = -1, bin1 = -1;
-    long long g0 = -1, q0 = 0, g1 = -1, q1 = 0;
-    if (vec_ok && pix + 1 < end) {
-      longlong2 g = __ldcs(reinterpret_cast<const longlong2*>(gt + pix));
-      longlong2 q = __ldcs(reinterpret_cast<const longlong2*>(pred + pix));
-      g0 = g.x; q0 = q.x; g1 = g.y; q1 = q.y;
-    } else {
-      if (pix < end) { g0 = __ldcs(gt + pix); q0 = __ldcs(pred + pix); }
-      if (pix + 1 < end) { g1 = __ldcs(gt + pix + 1); q1 = __ldcs(pred + pix + 1); }
+  // Two pixels per lane and step, 16-byte loads when both bases are 16-byte aligned (vec_ok), else two 8-byte loads
+  // each (a per-image slice of an odd-sized map, e.g. target[i] of 1025x2049 labels, starts 8 bytes off).  UNR steps'
+  // loads are issued before the first histogram update, so a warp keeps 4 KB in flight instead of 1 KB (r4: with one
+  // step per round trip the kernel ran at 0.17 of HBM, stalled on these loads).
+  constexpr int UNR = 4;
+  for (long long base = start + warp * 64; base < end; base += (long long)HD_THREADS * 2 * UNR) {
+    long long g[UNR][2], q[UNR][2];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long pix = base + (long long)u * HD_THREADS * 2 + lane * 2;
+      g[u][0] = g[u][1] = -1; q[u][0] = q[u][1] = 0;
+      if (vec_ok && pix + 1 < end) {
+        const longlong2 gv = __ldcs(reinterpret_cast<const longlong2*>(gt + pix));
+        const longlong2 qv = __ldcs(reinterpret_cast<const longlong2*>(pred + pix));
+        g[u][0] = gv.x; g[u][1] = gv.y; q[u][0] = qv.x; q[u][1] = qv.y;
+      } else {
+        if (pix < end) { g[u][0] = __ldcs(gt + pix); q[u][0] = __ldcs(pred + pix); }
+        if (pix + 1 < end) { g[u][1] = __ldcs(gt + pix + 1); q[u][1] = __ldcs(pred + pix + 1); }
+      }
     }
     // a prediction outside [0,nc) has no cell in the matrix (the reference's bincount raises on a negative label and
     // fails its reshape on a too large one, metrics.py:37-38): such pixels are dropped, never aliased into a valid bin
-    if (g0 >= 0 && g0 < nc && q0 >= 0 && q0 < nc) bin0 = (int)(g0 * nc + q0);
-    if (g1 >= 0 && g1 < nc && q1 >= 0 && q1 < nc) bin1 = (int)(g1 * nc + q1);
-    warp_hist_add(hist[warp], bin0, lane);
-    warp_hist_add(hist[warp], bin1, lane);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (base + (long long)u * HD_THREADS * 2 >= end) break;            // warp-uniform: no lane of this step is in range
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int bin = -1;
+        if (g[u][e] >= 0 && g[u][e] < nc && q[u][e] >= 0 && q[u][e] < nc) bin = (int)(g[u][e] * nc + q[u][e]);
+        warp_hist_add(hist[warp], bin, lane);
+      }
+    }
   }
   __syncthreads();
   int bins = nc * nc;

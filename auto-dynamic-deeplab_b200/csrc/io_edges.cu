@@ -2,7 +2,7 @@
 //   * Cityscapes label ids -> train ids (dataloaders/datasets/cityscapes.py:85-91) as a 256-entry LUT, fused with the
 //     pad-to-crop-size of the evaluation transform (custom_transforms.py:322-347: labels padded with 255);
 //   * uint8 HWC image -> normalised fp32 NCHW, padded with zeros AFTER normalisation (same transform: ZeroPad2d follows
-//     ToTensor + Normalize), bit-identical arithmetic to add_normalize_u8_hwc_to_nchw;
+//     torchvision's ToTensor + Normalize: float32 arithmetic, bit-identical);
 //   * class map -> colour image (dataloaders/utils.py:14-51 decode_segmap) as a 256-entry RGB LUT.
 // One thread handles 16 output bytes (labels) / 4 output pixels (images); rows are independent, grids are sized in
 // multiples of the SM count.
@@ -50,11 +50,14 @@ normalize_pad_u8_hwc_kernel(const uint8_t* __restrict__ src, float* __restrict__
     float o0 = 0.f, o1 = 0.f, o2 = 0.f;                       // ZeroPad2d after Normalize: the padding is exactly 0
     if (y < h && x < w) {
       const uint8_t* px = in + ((size_t)y * w + x) * 3;
-      // ToTensor: /255 in float32; Normalize: (x - mean) / std — the reference's numpy path evaluates both in float64
-      // (mean / std are float64) and rounds to float32 after each (custom_transforms.py:17-24,39)
+      // full_image_eval_preprocess uses torchvision's transforms (custom_transforms.py:331-336): ToTensor = /255 in
+      // float32, Normalize = tensor.sub_(mean).div_(std) with mean / std converted to float32 tensors — all float32,
+      // each operation rounded to nearest (unlike the numpy Normalize class of the training transforms, which goes
+      // through float64: that one is add_normalize_u8_hwc_to_nchw)
       const float r = __fdiv_rn((float)px[0], 255.0f), g = __fdiv_rn((float)px[1], 255.0f), b = __fdiv_rn((float)px[2], 255.0f);
-      const float r1 = (float)((double)r - m0), g1 = (float)((double)g - m1), b1 = (float)((double)b - m2);
-      o0 = (float)((double)r1 / s0); o1 = (float)((double)g1 / s1); o2 = (float)((double)b1 / s2);
+      o0 = __fdiv_rn(__fsub_rn(r, (float)m0), (float)s0);
+      o1 = __fdiv_rn(__fsub_rn(g, (float)m1), (float)s1);
+      o2 = __fdiv_rn(__fsub_rn(b, (float)m2), (float)s2);
     }
     out[p] = o0; out[per + p] = o1; out[2 * per + p] = o2;
   }

@@ -193,9 +193,12 @@ __host__ __device__ inline int gap_splits(int HW, int n) {
 template <typename TI, int V>
 __global__ void __launch_bounds__(GAP_THREADS)
 gap_partial_kernel(const TI* __restrict__ x, float* __restrict__ part, int HW, int C, int xs, uint32_t flags) {
-  extern __shared__ float gap_red[];                 // [lanes][C]
-  const int cv = C / V;
-  const int lanes = GAP_THREADS / cv;                // pixel lanes (>= 1: host checks cv <= 256)
+  extern __shared__ float gap_red[];                 // [lanes][Cg]
+  // blockIdx.z = channel group of up to GAP_THREADS * V channels (wide inputs: the ASPP image pool at Cin = 3200)
+  const int c0 = blockIdx.z * (GAP_THREADS * V);
+  const int Cg = min(C - c0, GAP_THREADS * V);
+  const int cv = Cg / V;
+  const int lanes = GAP_THREADS / cv;                // pixel lanes (>= 1)
   const int n = blockIdx.y, S = gridDim.x;
   const int per = (HW + S - 1) / S;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
@@ -205,7 +208,7 @@ gap_partial_kernel(const TI* __restrict__ x, float* __restrict__ part, int HW, i
 #pragma unroll
   for (int i = 0; i < V; ++i) acc[i] = 0.f;
   if (l < lanes) {
-    const TI* xn = x + (size_t)n * HW * xs + v * V;
+    const TI* xn = x + (size_t)n * HW * xs + c0 + v * V;
     int p = p0 + l;
     for (; p + 3 * lanes < p1; p += 4 * lanes) {
       float t[4][V];
@@ -223,13 +226,13 @@ gap_partial_kernel(const TI* __restrict__ x, float* __restrict__ part, int HW, i
       for (int i = 0; i < V; ++i) acc[i] += relu ? fmaxf(t[i], 0.f) : t[i];
     }
 #pragma unroll
-    for (int i = 0; i < V; ++i) gap_red[l * C + v * V + i] = acc[i];
+    for (int i = 0; i < V; ++i) gap_red[l * Cg + v * V + i] = acc[i];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += GAP_THREADS) {
+  for (int c = threadIdx.x; c < Cg; c += GAP_THREADS) {
     float tot = gap_red[c];
-    for (int r = 1; r < lanes; ++r) tot += gap_red[r * C + c];
-    part[((size_t)n * S + blockIdx.x) * C + c] = tot;
+    for (int r = 1; r < lanes; ++r) tot += gap_red[r * Cg + c];
+    part[((size_t)n * S + blockIdx.x) * C + c0 + c] = tot;
   }
 }
 
@@ -350,12 +353,13 @@ extern "C" int add_global_avgpool_fwd(const add_tensor_t* x, float* out, uint32_
                                       int64_t workspace_bytes, void* stream) {
   ADD_CHECK_ARG(tensor_ok(x) && out && workspace);
   const bool v8 = x->dtype == ADD_BF16 && x->c % 8 == 0 && x->pix_stride % 8 == 0 && ((uintptr_t)x->ptr % 16) == 0;
-  ADD_CHECK_SUP(tensor_vec4_ok(x) && x->c / (v8 ? 8 : 4) <= GAP_THREADS);
+  ADD_CHECK_SUP(tensor_vec4_ok(x));
   if (workspace_bytes < add_global_avgpool_workspace_bytes(x->n, x->h, x->w, x->c)) return ADD_ERR_WORKSPACE;
   const int HW = x->h * x->w, S = gap_splits(HW, x->n);
-  const int cv = x->c / (v8 ? 8 : 4);
-  dim3 grid(S, x->n);
-  size_t smem = (size_t)(GAP_THREADS / cv) * x->c * sizeof(float);
+  const int V = v8 ? 8 : 4;
+  dim3 grid(S, x->n, ceil_div(x->c, GAP_THREADS * V));          // z: channel groups of GAP_THREADS * V channels
+  ADD_CHECK_SUP(grid.z < 65536);
+  size_t smem = (size_t)GAP_THREADS * V * sizeof(float);       // lanes * Cg <= GAP_THREADS * V
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (v8)
     gap_partial_kernel<bf16, 8><<<grid, GAP_THREADS, smem, s>>>((const bf16*)x->ptr, (float*)workspace, HW, x->c, x->pix_stride, flags);

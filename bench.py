@@ -57,6 +57,12 @@ def parse():
     ap.add_argument("--image-dtype", default="uint8", choices=["uint8", "fp32"],
                     help="dtype of the HOST images fed to the e2e loop: uint8 HWC (the PNG bytes; normalised on the device "
                          "with the reference loader's arithmetic) or the loader's normalised fp32 NCHW")
+    ap.add_argument("--per-rank-threshold", action="store_true",
+                    help="multi-GPU: every rank gates at ITS OWN batch median (always 50 %% early exits per rank, the round-1 "
+                         "behaviour).  Default: ONE global threshold — rank 0's batch median, broadcast before the timed "
+                         "region — as a deployment would use, so exit counts (and step times) differ per rank")
+    ap.add_argument("--no-fp32-feed", action="store_true",
+                    help="skip the second e2e measurement that feeds the reference loader's fp32 NCHW images + int64 labels")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel launch table (JSON) here")
     ap.add_argument("--profile-step", action="store_true",
                     help="for `ncu --profile-from-start off`: warm up, then run ONE step between cudaProfilerStart/Stop "
@@ -395,6 +401,12 @@ def main_b200(a):
     _, _, confs = net.dynamic_evaluate(x_dev, gt_dev, -1e30, edm, a.exit_mode)
     vals = sorted(float(c) for c in confs)
     thr = 0.5 * (vals[B // 2 - 1] + vals[B // 2]) if B > 1 else vals[0] + 1.0
+    if world > 1 and not a.per_rank_threshold:
+        # ONE threshold for the whole job (rank 0's batch median), fixed before the timed region: the ranks' batches
+        # differ (seed 1234 + rank), so their early-exit counts differ and the job runs at the pace of the slowest rank
+        t = torch.tensor([thr], device=dev, dtype=torch.float64)
+        dist.broadcast(t, 0)
+        thr = float(t.item())
     cm0, flags0, _ = net.dynamic_evaluate(x_dev, gt_dev, thr, edm, a.exit_mode)
     cm0 = cm0.clone()
     launches_per_step = net.last_dynamic_launches + 0
@@ -421,14 +433,40 @@ def main_b200(a):
     # e2e: the public host-fed loop (add_b200.HostPipeline = eval.py's `for batch in loader` loop): every step's
     # images + labels come from pinned HOST memory (H2D inside the timed region, double-buffered on a copy
     # stream so batch i+1's copy overlaps batch i's compute) and its confusion matrices go back to the host.
-    pipe = add_b200.HostPipeline(net, edm, thr, a.exit_mode)
-    gt_feed = gt_host.to(torch.uint8).pin_memory() if a.label_dtype == "uint8" else gt_host   # 255 (ignore) fits uint8
+    # Two feeds: (1) the batch as the PNG decoder delivers it — uint8 HWC images + uint8 labels, normalised on the
+    # device (the default `e2e`); (2) the tensors the reference's loader hands to eval.py:175 — normalised fp32 NCHW
+    # images + int64 labels, 5x the bytes (`e2e_fp32_feed`).
+    def make_e2e(image_dtype, label_dtype):
+        pipe_ = add_b200.HostPipeline(net, edm, thr, a.exit_mode)
+        img_ = img_host if image_dtype == "uint8" else x_host
+        gt_ = gt_host.to(torch.uint8).pin_memory() if label_dtype == "uint8" else gt_host   # 255 (ignore) fits uint8
 
-    def run_e2e(steps):
-        out = None
-        for out, _ in pipe.evaluate((img_host, gt_feed) for _ in range(steps)):
-            pass
-        return out
+        def run(steps):
+            out = None
+            for out, _ in pipe_.evaluate((img_, gt_) for _ in range(steps)):
+                pass
+            return out
+        return pipe_, run
+
+    def time_e2e(image_dtype, label_dtype):
+        pipe_, run = make_e2e(image_dtype, label_dtype)
+        run(pipe_.depth + 1)                                     # warm-up: every slot's plans recorded and captured, pinned result buffers
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h2d0, d2h0 = pipe_.h2d_bytes, pipe_.d2h_bytes
+        e0.record()
+        cm_host = run(a.steps)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t_ = torch.tensor([ms], device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            ms = float(t_.item())
+        assert torch.equal(cm_host[0], cm0.cpu()), "e2e result differs from the resident-input result"
+        return dict(value=world * B * a.steps / (ms / 1e3), unit=UNIT, h2d_bytes_per_step=(pipe_.h2d_bytes - h2d0) // a.steps,
+                    d2h_bytes_per_step=(pipe_.d2h_bytes - d2h0) // a.steps + B * 4, ms_per_step=ms / a.steps,
+                    host_label_dtype=label_dtype, host_image_dtype=image_dtype)
 
     if a.forward_only:
         # informational: ADD.evaluate (every exit, no gating: forward -> argmax -> confusion matrix per exit) on the
@@ -476,74 +514,95 @@ def main_b200(a):
         if sampler:
             sampler.mark()
         clocks = sampler.stop() if sampler else None
-        ms = e0.elapsed_time(e1)
+        ms = ms_local = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         assert torch.equal(last, cm0), "pipelined resident result differs from the single-call result"
-        return ms, clocks
+        return ms, ms_local, clocks
 
-    ms_res, clocks = timed(run_resident, a.steps, max(a.warmup, 3), sample_clocks=True)
-    run_e2e(pipe.depth + 1)                                      # warm-up: every slot's plans recorded and captured, pinned result buffers
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h2d0, d2h0 = pipe.h2d_bytes, pipe.d2h_bytes
-    e0.record()
-    cm_host = run_e2e(a.steps)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    ms_res, ms_res_local, clocks = timed(run_resident, a.steps, max(a.warmup, 3), sample_clocks=True)
+    if a.image_dtype == "fp32":
+        e2e_main = time_e2e("fp32", a.label_dtype)
+        e2e_fp32 = None
+    else:
+        e2e_main = time_e2e("uint8", a.label_dtype)
+        e2e_fp32 = None if a.no_fp32_feed else time_e2e("fp32", "int64")
+    # per-rank view of the resident arm: this rank's own step time and early-exit count (imbalance under one threshold)
+    rank_ms, rank_exits = [ms_res_local / a.steps], [int(sum(flags0))]
     if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    h2d_step, d2h_step = (pipe.h2d_bytes - h2d0) // a.steps, (pipe.d2h_bytes - d2h0) // a.steps
-    assert torch.equal(cm_host[0], cm0.cpu()), "e2e result differs from the resident-input result"
+        g_ms = [None] * world
+        dist.all_gather_object(g_ms, (ms_res_local / a.steps, int(sum(flags0))))
+        rank_ms, rank_exits = [v[0] for v in g_ms], [v[1] for v in g_ms]
     value = world * B * a.steps / (ms_res / 1e3)
-    e2e = world * B * a.steps / (ms_e2e / 1e3)
 
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel: per-launch CUDA-event times over one full step ----
+        # ---- roofline: per-launch CUDA-event times over one full step (the plans the timed step replays), grouped into
+        # kernel INSTANCES — launches of one kernel with the same tag and the same algorithmic work (= same shapes).
+        # One instance per bound class is reported: the dominant tensor-bound instance (arithmetic intensity above the
+        # bf16 ridge, FLOPs / time against the measured sustained bf16 peak) and the dominant HBM-bound instance
+        # (algorithmic bytes / time against the measured copy bandwidth); the top-level keys are those of whichever
+        # of the two takes more of the step.  `whole_step`: total algorithmic FLOPs / ms_per_step against the peak.
         runner = next(v for k, v in net._plans.items() if k[0] == "edm" and k[5] == "evaluate")
         rows = []
         for plan in runner.last_plans:                 # exactly the plans the timed step replays
             rows += plan.profile()
-        agg = {}
-        for r in rows:
-            d = agg.setdefault(r["kernel"], dict(ms=0.0, flops=0, bytes=0, launches=0))
-            d["ms"] += r["ms"]; d["flops"] += r["flops"]; d["bytes"] += r["bytes"]; d["launches"] += 1
-        total_ms = sum(d["ms"] for d in agg.values())
-        top = max(agg, key=lambda k: agg[k]["ms"])
-        t = agg[top]
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
             peaks = json.loads(pk.read_text())
         hbm_peak, tc_peak = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
-        src = "MEASURED_PEAKS.json" if pk.exists() else "fallback (B200_PROFILING.md)"
-        ai = t["flops"] / max(t["bytes"], 1)
-        if top.startswith("conv2d") and ai > 100:
-            ach = t["flops"] / (t["ms"] / 1e3) / 1e12
-            roof = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak}
-        else:
-            ach = t["bytes"] / (t["ms"] / 1e3) / 1e9
-            roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
-        traffic, traffic_src = None, None
+        src = "MEASURED_PEAKS.json (hbm_gbs, bf16_tflops_sustained: kernels timed inside a long step)" if pk.exists() else "fallback (B200_PROFILING.md)"
+        ridge = tc_peak * 1e12 / (hbm_peak * 1e9)
+        agg, inst = {}, {}
+        for r in rows:
+            d = agg.setdefault(r["kernel"], dict(ms=0.0, flops=0, bytes=0, launches=0))
+            d["ms"] += r["ms"]; d["flops"] += r["flops"]; d["bytes"] += r["bytes"]; d["launches"] += 1
+            key = f'{r["tag"]}|{r["flops"]}|{r["bytes"]}'
+            d = inst.setdefault(key, dict(kernel=r["kernel"], tag=r["tag"], ms=0.0, flops=r["flops"], bytes=r["bytes"], launches=0))
+            d["ms"] += r["ms"]; d["launches"] += 1
+        total_ms = sum(d["ms"] for d in agg.values())
+        traffic_tab = {}
         tj = ROOT / "profiles" / "traffic.json"
-        if tj.exists():                       # measured DRAM bytes per launch of this kernel family (ncu, committed)
-            tk = json.loads(tj.read_text()).get("kernels", {}).get(top)
-            if tk:
-                traffic, traffic_src = tk["traffic_per_launch"], "profiles/traffic.json (ncu dram__bytes_read+write per launch)"
-        roof.update({"kernel": top, "traffic": traffic, "traffic_source": traffic_src,
-                     "algorithmic_per_launch": (t["flops"] if roof["bound"] == "tensor" else t["bytes"]) / t["launches"],
-                     "peak_source": src, "launches": t["launches"],
-                     "avg_launch_ms": t["ms"] / t["launches"], "share_of_step": t["ms"] / total_ms,
-                     "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
-                                     "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
-                                     "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in
-                                 sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}})
+        if tj.exists():                       # measured DRAM bytes per launch per instance (ncu launch list, committed)
+            traffic_tab = json.loads(tj.read_text()).get("instances", {})
+
+        def entry(key, d, bound):
+            per_ms = d["ms"] / d["launches"]
+            if bound == "tensor":
+                ach, peak, unit, alg = d["flops"] / (per_ms / 1e3) / 1e12, tc_peak, "TFLOP/s", d["flops"]
+            else:
+                ach, peak, unit, alg = d["bytes"] / (per_ms / 1e3) / 1e9, hbm_peak, "GB/s", d["bytes"]
+            tr = traffic_tab.get(key)
+            return {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                    "traffic": tr["traffic_per_launch"] if tr else None,
+                    "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write per launch of this instance)" if tr else None,
+                    "kernel": d["kernel"], "instance": d["tag"], "algorithmic_per_launch": alg,
+                    "algorithmic_flops_per_launch": d["flops"], "algorithmic_bytes_per_launch": d["bytes"],
+                    "launches": d["launches"], "avg_launch_ms": per_ms, "share_of_step": d["ms"] / total_ms}
+        tens = {k: d for k, d in inst.items() if d["bytes"] > 0 and d["flops"] / d["bytes"] > ridge}
+        mems = {k: d for k, d in inst.items() if d["bytes"] > 0 and d["flops"] / d["bytes"] <= ridge}
+        classes = {}
+        if tens:
+            k = max(tens, key=lambda k: tens[k]["ms"]); classes["tensor"] = entry(k, tens[k], "tensor")
+        if mems:
+            k = max(mems, key=lambda k: mems[k]["ms"]); classes["hbm"] = entry(k, mems[k], "hbm")
+        roof = dict(max(classes.values(), key=lambda c: c["share_of_step"]))
+        step_flops = sum(r["flops"] for r in rows)
+        step_bytes = sum(r["bytes"] for r in rows)
+        roof.update({"peak_source": src, "classes": classes,
+                     "whole_step": {"algorithmic_flops": step_flops, "algorithmic_bytes": step_bytes,
+                                    "tflops": step_flops / (ms_res / a.steps / 1e3) / 1e12,
+                                    "frac_of_bf16_sustained": step_flops / (ms_res / a.steps / 1e3) / 1e12 / tc_peak,
+                                    "gbs": step_bytes / (ms_res / a.steps / 1e3) / 1e9,
+                                    "frac_of_hbm": step_bytes / (ms_res / a.steps / 1e3) / 1e9 / hbm_peak,
+                                    "note": "every launch of the step: op-granularity algorithmic work (SURVEY 8d) / measured ms_per_step"},
+                     "families": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                      "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
+                                      "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in
+                                  sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}})
         if a.profile_out:
             Path(a.profile_out).write_text(json.dumps(rows, indent=0))
         cpu = None
@@ -557,10 +616,12 @@ def main_b200(a):
                                                                            resident_pipeline=(None if a.no_pipeline else
                                                                                               "3 resident input buffers cycled; trunk of step i+1 enqueued before the host reads step i's gate values"),
                                                                            tensor_core_path=bool(rt.tc_available())),
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_step,
-                        "d2h_bytes_per_step": d2h_step + B * 4, "ms_per_step": ms_e2e / a.steps,
-                        "host_label_dtype": a.label_dtype, "host_image_dtype": a.image_dtype,
+                "e2e": {**e2e_main,
                         "api": "add_b200.HostPipeline.evaluate (pinned host batches over 3 slots: H2D of batch i+2 and the trunk of batch i+1 in flight while the host decides batch i's exits)"},
+                "e2e_fp32_feed": e2e_fp32,
+                "ranks": {"threshold": "per-rank batch median" if (a.per_rank_threshold or world == 1) else "global (rank 0's batch median, broadcast)",
+                          "ms_per_step": rank_ms, "early_exits_of_batch": rank_exits,
+                          "slowest_rank_penalty": max(rank_ms) / (sum(rank_ms) / len(rank_ms))},
                 "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
         sys.stdout.flush()

@@ -218,9 +218,10 @@ int add_upsample_argmax_u8_fwd(const add_tensor_t* x, int H, int W, const uint8_
  * identity (pad only). */
 int add_encode_pad_labels_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int Hp, int Wp,
                              const uint8_t* lut256_dev, int fill, void* stream);
-/* full_image_eval_preprocess (custom_transforms.py:322-347): uint8 HWC [n][h][w][3] -> ToTensor + Normalize (the
- * arithmetic of add_normalize_u8_hwc_to_nchw, bit-identical) -> zero pad to [n][3][Hp][Wp] fp32 (ZeroPad2d AFTER the
- * normalisation, so the padding is exactly 0). */
+/* full_image_eval_preprocess (custom_transforms.py:322-347): uint8 HWC [n][h][w][3] -> torchvision ToTensor + Normalize
+ * (all float32: /255, - mean, / std, each rounded to nearest; bit-identical) -> zero pad to [n][3][Hp][Wp] fp32 (ZeroPad2d
+ * AFTER the normalisation, so the padding is exactly 0).  (add_normalize_u8_hwc_to_nchw is the numpy Normalize class of
+ * the training transforms, which evaluates - mean and / std in float64.) */
 int add_normalize_pad_u8_hwc_to_nchw(const uint8_t* src, float* dst, int n, int h, int w, int Hp, int Wp, double mean0,
                                      double mean1, double mean2, double std0, double std1, double std2, void* stream);
 /* decode_segmap (dataloaders/utils.py:14-51): class map (int64 if labels_are_int64 else uint8) -> uint8 RGB [n_pixels][3]
@@ -249,6 +250,51 @@ int add_confusion_matrix(const int64_t* gt, const int64_t* pred, int64_t n_pixel
 int64_t add_confidence_workspace_bytes(int n, int H, int W);
 int add_confidence_nchw(const float* logits, int n, int num_class, int H, int W, float threshold,
                         float* out2, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- training step: backward kernels (train.py:216-247) — fp32 NHWC, deterministic ------------------ */
+/* dx *= (x > 0): the ReLU in front of every conv (operations.py:21,33,47) */
+int add_relu_mask_bwd(const add_tensor_t* x, const add_tensor_t* dx, void* stream);
+/* conv weight gradient, layout [kh][kw][Cin][Cout] like add_conv2d_fwd's weights; flags: ADD_RELU_IN (the conv read relu(x)),
+ * ADD_ACCUMULATE (dw += ...).  workspace: add_conv2d_wgrad_workspace_bytes(). */
+int64_t add_conv2d_wgrad_workspace_bytes(int n, int ho, int wo, int cin, int cout, int kh, int kw);
+int add_conv2d_wgrad(const add_tensor_t* x, const add_tensor_t* dy, float* dw, int kh, int kw, int stride, int pad, int dil,
+                     uint32_t flags, void* workspace, int64_t workspace_bytes, void* stream);
+/* conv input gradient for any stride (stride-1 convs use add_conv2d_fwd with flipped weights instead); flags: ADD_ACCUMULATE */
+int add_conv2d_dgrad(const add_tensor_t* dy, const float* w, const add_tensor_t* dx, int kh, int kw, int stride, int pad,
+                     int dil, uint32_t flags, void* stream);
+/* depthwise weight gradient [k][k][C] (operations.py:52,56) */
+int64_t add_depthwise_wgrad_workspace_bytes(int n, int h, int w, int c, int k);
+int add_depthwise_wgrad(const add_tensor_t* x, const add_tensor_t* dy, float* dw, int k, uint32_t flags, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+/* training-mode BatchNorm backward (F.batch_norm / SynchronizedBatchNorm2d, sync_batchnorm/batchnorm.py:59-75,113-125):
+ * reduce -> sums double[2][C] = [sum dy', sum dy' * xhat] (dy' masked by y > 0 with ADD_RELU_OUT); the caller all-reduces
+ * `sums` over the ranks for the synchronised layer; apply -> dx = gamma * inv_std * (dy' - sum1/M - xhat * sum2/M * var_term).
+ * d gamma = sum2, d beta = sum1 (this rank's, before the all-reduce). */
+int64_t add_bn_bwd_workspace_bytes(int n, int h, int w, int c);
+int add_bn_bwd_reduce(const add_tensor_t* dy, const add_tensor_t* x, const float* mean, const float* inv_std, const float* gamma,
+                      const float* beta, uint32_t flags, double* sums, void* workspace, int64_t workspace_bytes, void* stream);
+int add_bn_bwd_apply(const add_tensor_t* dy, const add_tensor_t* x, const float* mean, const float* inv_std, const float* gamma,
+                     const float* beta, const double* sums, double inv_count, const float* var_term, uint32_t flags,
+                     const add_tensor_t* dx, void* stream);
+/* adjoint of add_bilinear_fwd (F.interpolate bilinear, align_corners=False): per-axis tables built once per (in, out) size */
+int add_bilinear_bwd_tables(int in_size, int out_size, int32_t* i0, int32_t* i1, float* l0, float* l1, int32_t* lo, int32_t* hi,
+                            void* stream);
+int add_bilinear_bwd(const add_tensor_t* dy, const add_tensor_t* dx, const int32_t* yi0, const int32_t* yi1, const float* yl0,
+                     const float* yl1, const int32_t* ylo, const int32_t* yhi, const int32_t* xi0, const int32_t* xi1,
+                     const float* xl0, const float* xl1, const int32_t* xlo, const int32_t* xhi, uint32_t flags, void* stream);
+/* 3x3 pool backward (operations.py:9-10): mode 0 avg (count_include_pad=False), 1 max (first maximum) */
+int add_pool3x3_bwd(const add_tensor_t* x, const add_tensor_t* dy, const add_tensor_t* dx, int mode, int stride, uint32_t flags,
+                    void* stream);
+/* nn.CrossEntropyLoss(weight, ignore_index) on NCHW fp32 logits (utils/loss.py:16-25; train.py:229-233): loss_wsum[0] = mean
+ * loss, [1] = weight sum of the valid pixels; dlogits (or NULL) = grad_scale * d loss / d logits */
+int64_t add_ce_loss_workspace_bytes(int n, int h, int w);
+int add_ce_loss_fwd_bwd(const float* logits, const int64_t* target, int n, int num_class, int h, int w, int64_t ignore_index,
+                        const float* class_weight, float grad_scale, float* loss_wsum, float* dlogits, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+/* torch.optim.SGD(momentum, weight_decay, nesterov) (train.py:126-127) over a device table of
+ * {float* param, const float* grad, float* momentum_buf, int64 numel} entries, one launch */
+int add_sgd_nesterov(const void* table_dev, int n_tensors, int64_t max_numel, float lr, float momentum, float weight_decay,
+                     int nesterov, int first_step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -298,8 +298,10 @@ def test_three_gated_exits_plan_cache_lineage():
     srt = sorted(firsts)
     patterns_seen = set()
     for thr in (0.5 * (srt[1] + srt[2]), 0.5 * (srt[3] + srt[4]), srt[0] - 1.0, 0.5 * (srt[2] + srt[3]), 0.5 * (srt[1] + srt[2])):
-        ref = [net.dynamic_inference(xd[i:i + 1], threshold=thr, confidence='edm', edm=edm) for i in range(n)]
-        ref = [(r[0].clone(), r[1], float(r[3])) for r in ref]
+        ref = []
+        for i in range(n):                       # clone at once: the logits alias plan buffers the next call overwrites
+            y1, e1, _, c1 = net.dynamic_inference(xd[i:i + 1], threshold=thr, confidence='edm', edm=edm)
+            ref.append((y1.clone(), e1, float(c1)))
         ys, flags, confs = net.dynamic_inference_batch(xd, thr, 'edm', edm)
         assert flags == [r[1] for r in ref]
         for i in range(n):
@@ -311,7 +313,11 @@ def test_three_gated_exits_plan_cache_lineage():
             want = orc.generate_matrix(gt[i].numpy(), ref[i][0].argmax(1).cpu().numpy())
             assert np.array_equal(cms[i].cpu().numpy(), want), (thr, i)
         patterns_seen.add(tuple(flags))
-    assert len(patterns_seen) >= 3
+    # the exit flag is binary (an image that passes gate 1 usually leaves at gate 2 or 3), so the diversity of the runs is
+    # read off the plans that were recorded: segments / heads at several gates and image counts
+    runner = next(v for k, v in net._plans.items() if k[0] == "edm" and k[5] == "logits" and k[1][0] == n)
+    assert len({k[0] for k in runner.segments}) >= 3 and len(runner.segments) >= 4, sorted(k[:2] for k in runner.segments)
+    assert len({k[0] for k in runner.heads}) >= 2, sorted(k[:2] for k in runner.heads)
     # one image against the oracle (reference control flow with three gates)
     with torch.no_grad():
         y_ref, ee_ref, cv_ref = orc.add_dynamic_inference(sd, arch, x[0:1], 0.5 * (srt[2] + srt[3]), 'edm', edm_sd)
