@@ -86,14 +86,15 @@ _SIGS = {
     "add_depthwise_wgrad": (c_int, [TP, TP, c_void_p, c_int, c_uint32, c_void_p, c_int64, c_void_p]),
     "add_bn_bwd_workspace_bytes": (c_int64, [c_int] * 4),
     "add_bn_bwd_reduce": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_int64, c_void_p]),
-    "add_bn_bwd_apply": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double, c_void_p, c_uint32, TP, c_void_p]),
+    "add_bn_bwd_apply": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double, c_void_p, c_void_p, c_uint32, TP, c_void_p]),
     "add_bilinear_bwd_tables": (c_int, [c_int, c_int] + [c_void_p] * 6 + [c_void_p]),
     "add_bilinear_bwd": (c_int, [TP, TP] + [c_void_p] * 12 + [c_uint32, c_void_p]),
     "add_pool3x3_bwd": (c_int, [TP, TP, TP, c_int, c_int, c_uint32, c_void_p]),
     "add_ce_loss_workspace_bytes": (c_int64, [c_int] * 3),
-    "add_ce_loss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_float, c_void_p, c_void_p,
-                                    c_void_p, c_int64, c_void_p]),
-    "add_sgd_nesterov": (c_int, [c_void_p, c_int, c_int64, c_float, c_float, c_float, c_int, c_int, c_void_p]),
+    "add_ce_loss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p,
+                                    c_float, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "add_sgd_nesterov": (c_int, [c_void_p, c_int, c_int64, c_float, c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
+    "add_peer_allreduce": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_uint32, c_void_p, c_int64, c_void_p, c_void_p]),
     "add_widen_labels_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "add_confusion_workspace_bytes": (c_int64, [c_int64, c_int]),
     "add_confusion_matrix": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),

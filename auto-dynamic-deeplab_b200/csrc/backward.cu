@@ -276,8 +276,9 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int blocks, int C, double
 __global__ void __launch_bounds__(BW_THREADS)
 bn_bwd_apply_kernel(const float* __restrict__ dy, int dys, const float* __restrict__ x, int xs, const float* __restrict__ mean,
                     const float* __restrict__ inv_std, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    const double* __restrict__ sums, double inv_count, const float* __restrict__ var_term,
-                    long long P, int C, int relu_out, float* __restrict__ dx, int dxs) {
+                    const double* __restrict__ sums, double inv_count, const float* __restrict__ count_dev,
+                    const float* __restrict__ var_term, long long P, int C, int relu_out, float* __restrict__ dx, int dxs) {
+  if (count_dev) inv_count = 1.0 / (double)__ldg(count_dev);
   const int c4n = C / 4;
   const long long total = P * c4n;
   for (long long i = blockIdx.x * (long long)BW_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * BW_THREADS) {
@@ -393,7 +394,8 @@ pool3x3_bwd_kernel(const float* __restrict__ x, int xs, const float* __restrict_
 // dlogits[p][c] = scale * w[t_p] * (softmax_c - [c == t_p]) / wsum, 0 at ignored pixels.
 __global__ void __launch_bounds__(BW_THREADS)
 ce_partial_kernel(const float* __restrict__ logits, const long long* __restrict__ target, int N, int C, long long HW,
-                  long long ignore_index, const float* __restrict__ cw, double* __restrict__ part /* [blocks][2] */) {
+                  long long sn, long long sc, long long sp, long long ignore_index, const float* __restrict__ cw,
+                  double* __restrict__ part /* [blocks][2] */) {
   __shared__ double red[2][BW_THREADS / 32];
   double num = 0.0, den = 0.0;
   const long long total = (long long)N * HW;
@@ -401,14 +403,14 @@ ce_partial_kernel(const float* __restrict__ logits, const long long* __restrict_
     const long long t = target[i];
     if (t == ignore_index || t < 0 || t >= C) continue;
     const int n = (int)(i / HW); const long long pix = i - (long long)n * HW;
-    const float* z = logits + (size_t)n * C * HW + pix;
+    const float* z = logits + (size_t)n * sn + (size_t)pix * sp;
     float mx = -INFINITY;
-    for (int c = 0; c < C; ++c) mx = fmaxf(mx, __ldg(z + (size_t)c * HW));
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, __ldg(z + (size_t)c * sc));
     float s = 0.f;
-    for (int c = 0; c < C; ++c) s += expf(__ldg(z + (size_t)c * HW) - mx);
+    for (int c = 0; c < C; ++c) s += expf(__ldg(z + (size_t)c * sc) - mx);
     const float lse = mx + logf(s);
     const float w = cw ? __ldg(cw + t) : 1.f;
-    num += (double)(w * (lse - __ldg(z + (size_t)t * HW)));
+    num += (double)(w * (lse - __ldg(z + (size_t)t * sc)));
     den += (double)w;
   }
 #pragma unroll
@@ -430,28 +432,29 @@ __global__ void ce_finalize_kernel(const double* __restrict__ part, int blocks, 
   }
 }
 __global__ void __launch_bounds__(BW_THREADS)
-ce_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ target, int N, int C, long long HW,
-               long long ignore_index, const float* __restrict__ cw, const float* __restrict__ loss_wsum, float scale,
-               float* __restrict__ dlogits) {
+ce_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ target, int N, int C, int Cstore, long long HW,
+               long long sn, long long sc, long long sp, long long ignore_index, const float* __restrict__ cw,
+               const float* __restrict__ loss_wsum, float scale, float* __restrict__ dlogits) {
   const long long total = (long long)N * HW;
   const float inv = scale / loss_wsum[1];
   for (long long i = blockIdx.x * (long long)BW_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * BW_THREADS) {
     const long long t = target[i];
     const int n = (int)(i / HW); const long long pix = i - (long long)n * HW;
-    const float* z = logits + (size_t)n * C * HW + pix;
-    float* g = dlogits + (size_t)n * C * HW + pix;
+    const float* z = logits + (size_t)n * sn + (size_t)pix * sp;
+    float* g = dlogits + (size_t)n * sn + (size_t)pix * sp;
+    for (int c = C; c < Cstore; ++c) g[(size_t)c * sc] = 0.f;           // padding channels carry no gradient
     if (t == ignore_index || t < 0 || t >= C) {
-      for (int c = 0; c < C; ++c) g[(size_t)c * HW] = 0.f;
+      for (int c = 0; c < C; ++c) g[(size_t)c * sc] = 0.f;
       continue;
     }
     float mx = -INFINITY;
-    for (int c = 0; c < C; ++c) mx = fmaxf(mx, __ldg(z + (size_t)c * HW));
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, __ldg(z + (size_t)c * sc));
     float s = 0.f;
-    for (int c = 0; c < C; ++c) s += expf(__ldg(z + (size_t)c * HW) - mx);
+    for (int c = 0; c < C; ++c) s += expf(__ldg(z + (size_t)c * sc) - mx);
     const float w = (cw ? __ldg(cw + t) : 1.f) * inv, rs = 1.f / s;
     for (int c = 0; c < C; ++c) {
-      const float pr = expf(__ldg(z + (size_t)c * HW) - mx) * rs;
-      g[(size_t)c * HW] = w * (pr - (c == t ? 1.f : 0.f));
+      const float pr = expf(__ldg(z + (size_t)c * sc) - mx) * rs;
+      g[(size_t)c * sc] = w * (pr - (c == t ? 1.f : 0.f));
     }
   }
 }
@@ -461,7 +464,9 @@ ce_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ t
 // (nesterov) or buf; p -= lr * g.  One launch for all parameters: blockIdx.y = tensor.
 struct SgdEntry { float* p; const float* g; float* buf; long long n; };
 __global__ void __launch_bounds__(BW_THREADS)
-sgd_kernel(const SgdEntry* __restrict__ tab, float lr, float momentum, float wd, int nesterov, int first_step) {
+sgd_kernel(const SgdEntry* __restrict__ tab, float lr, const float* __restrict__ lr_dev, float momentum, float wd, int nesterov,
+           int first_step) {
+  if (lr_dev) lr = __ldg(lr_dev);              // the poly schedule changes lr every iteration: a captured graph reads it here
   const SgdEntry e = tab[blockIdx.y];
   for (long long i = blockIdx.x * (long long)BW_THREADS + threadIdx.x; i < e.n; i += (long long)gridDim.x * BW_THREADS) {
     float g = e.g[i] + wd * e.p[i];
@@ -599,14 +604,15 @@ extern "C" int add_bn_bwd_reduce(const add_tensor_t* dy, const add_tensor_t* x, 
 }
 extern "C" int add_bn_bwd_apply(const add_tensor_t* dy, const add_tensor_t* x, const float* mean, const float* inv_std,
                                 const float* gamma, const float* beta, const double* sums, double inv_count,
-                                const float* var_term, uint32_t flags, const add_tensor_t* dx, void* stream) {
+                                const float* count_dev, const float* var_term, uint32_t flags, const add_tensor_t* dx,
+                                void* stream) {
   ADD_CHECK_ARG(tensor_ok(dy) && tensor_ok(x) && tensor_ok(dx) && mean && inv_std && sums);
   ADD_CHECK_ARG(dy->n == x->n && dy->h == x->h && dy->w == x->w && dy->c == x->c && dx->c == x->c && dx->n == x->n);
   ADD_CHECK_SUP(f32_vec4(dy) && f32_vec4(x) && f32_vec4(dx));
   const long long P = (long long)x->n * x->h * x->w;
   bn_bwd_apply_kernel<<<bw_blocks(P * (x->c / 4)), BW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       (const float*)dy->ptr, dy->pix_stride, (const float*)x->ptr, x->pix_stride, mean, inv_std, gamma, beta, sums, inv_count,
-      var_term, P, x->c, (flags & ADD_RELU_OUT) ? 1 : 0, (float*)dx->ptr, dx->pix_stride);
+      count_dev, var_term, P, x->c, (flags & ADD_RELU_OUT) ? 1 : 0, (float*)dx->ptr, dx->pix_stride);
   ADD_RETURN_LAUNCH();
 }
 
@@ -653,9 +659,12 @@ extern "C" int64_t add_ce_loss_workspace_bytes(int n, int h, int w) {
   if (n <= 0 || h <= 0 || w <= 0) return ADD_ERR_BAD_ARG;
   return (int64_t)ce_blocks((long long)n * h * w) * 2 * sizeof(double);
 }
-/* loss_wsum: float[2] = (mean loss, sum of the valid pixels' class weights).  dlogits NULL: forward only.
+/* logits element (n, c, pixel) lives at n*stride_n + c*stride_c + pixel*stride_pix (NCHW: HW*C, HW, 1; NHWC with padded
+ * channels: HW*Cs, 1, Cs); channels [num_class, c_store) are padding: ignored, zero gradient.
+ * loss_wsum: float[2] = (mean loss, sum of the valid pixels' class weights).  dlogits NULL: forward only (same strides).
  * grad_scale multiplies the gradient (1/C for the mean over the C exits, train.py:233). */
 extern "C" int add_ce_loss_fwd_bwd(const float* logits, const int64_t* target, int n, int num_class, int h, int w,
+                                   int64_t stride_n, int64_t stride_c, int64_t stride_pix, int c_store,
                                    int64_t ignore_index, const float* class_weight, float grad_scale, float* loss_wsum,
                                    float* dlogits, void* workspace, int64_t workspace_bytes, void* stream) {
   ADD_CHECK_ARG(logits && target && loss_wsum && workspace && n > 0 && num_class > 0 && h > 0 && w > 0);
@@ -663,23 +672,25 @@ extern "C" int add_ce_loss_fwd_bwd(const float* logits, const int64_t* target, i
   const long long HW = (long long)h * w;
   const int B = ce_blocks(HW * n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  ce_partial_kernel<<<B, BW_THREADS, 0, s>>>(logits, (const long long*)target, n, num_class, HW, ignore_index, class_weight,
-                                             (double*)workspace);
+  ADD_CHECK_ARG(c_store >= num_class && stride_c > 0 && stride_pix > 0 && stride_n > 0);
+  ce_partial_kernel<<<B, BW_THREADS, 0, s>>>(logits, (const long long*)target, n, num_class, HW, stride_n, stride_c, stride_pix,
+                                             ignore_index, class_weight, (double*)workspace);
   ce_finalize_kernel<<<1, 32, 0, s>>>((const double*)workspace, B, loss_wsum);
   if (dlogits)
-    ce_grad_kernel<<<bw_blocks(HW * n), BW_THREADS, 0, s>>>(logits, (const long long*)target, n, num_class, HW, ignore_index,
-                                                            class_weight, loss_wsum, grad_scale, dlogits);
+    ce_grad_kernel<<<bw_blocks(HW * n), BW_THREADS, 0, s>>>(logits, (const long long*)target, n, num_class, c_store, HW, stride_n,
+                                                            stride_c, stride_pix, ignore_index, class_weight, loss_wsum,
+                                                            grad_scale, dlogits);
   ADD_RETURN_LAUNCH();
 }
 
 /* table: device array of n_tensors {float* param, const float* grad, float* momentum_buf, int64 numel} (32 bytes each) */
-extern "C" int add_sgd_nesterov(const void* table_dev, int n_tensors, int64_t max_numel, float lr, float momentum,
-                                float weight_decay, int nesterov, int first_step, void* stream) {
+extern "C" int add_sgd_nesterov(const void* table_dev, int n_tensors, int64_t max_numel, float lr, const float* lr_dev,
+                                float momentum, float weight_decay, int nesterov, int first_step, void* stream) {
   ADD_CHECK_ARG(table_dev && n_tensors > 0 && max_numel > 0);
   ADD_CHECK_SUP(n_tensors < 65536);
   long long bx = (max_numel + BW_THREADS * 4 - 1) / (BW_THREADS * 4);
   if (bx > 64) bx = 64;
   sgd_kernel<<<dim3((unsigned)bx, (unsigned)n_tensors), BW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      (const SgdEntry*)table_dev, lr, momentum, weight_decay, nesterov, first_step);
+      (const SgdEntry*)table_dev, lr, lr_dev, momentum, weight_decay, nesterov, first_step);
   ADD_RETURN_LAUNCH();
 }

@@ -41,6 +41,75 @@ def reduce_stats(packed: torch.Tensor, group: Optional[dist.ProcessGroup] = None
     return packed
 
 
+class PeerExchange:
+    """The one-kernel all-reduce of csrc/peer.cu for one process group: a symmetric buffer (two slots) + signal pad from
+    torch.distributed._symmetric_memory, mapped into every peer; `all_reduce_(vec)` launches ONE kernel on the current
+    stream.  NVLink-connected GPUs, one rank per GPU."""
+    CAP = 64 * 1024                     # bytes per slot: vectors are 2C+1 floats / 2C doubles (C <= 1280 on this network)
+    _instances: dict = {}
+
+    def __init__(self, group=None):
+        import numpy as np
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm_mem.empty(2 * self.CAP, dtype=torch.uint8, device=dev)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.buf_ptrs = np.array([int(p) for p in self.hdl.buffer_ptrs], dtype=np.uint64)
+        self.sig_ptrs = np.array([int(p) for p in self.hdl.signal_pad_ptrs], dtype=np.uint64)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)     # call counter, incremented by the kernel (graph-replayable)
+        self.calls = 0
+
+    @classmethod
+    def get(cls, group=None) -> "PeerExchange":
+        key = id(group) if group is not None else 0
+        if key not in cls._instances:
+            cls._instances[key] = cls(group)
+        return cls._instances[key]
+
+    def all_reduce_(self, vec: torch.Tensor) -> torch.Tensor:
+        assert vec.is_cuda and vec.is_contiguous() and vec.dtype in (torch.float32, torch.float64)
+        self.calls += 1
+        s = ctypes.c_void_p(torch.cuda.current_stream(vec.device).cuda_stream)
+        check(lib.add_peer_allreduce(vec.data_ptr(), vec.numel(), vec.element_size(), self.buf_ptrs.ctypes.data, self.sig_ptrs.ctypes.data,
+                                     self.rank, self.world, 0, self.epoch_dev.data_ptr(), self.CAP, self.status.data_ptr(), s),
+              "peer_allreduce")
+        return vec
+
+    def check_status(self) -> None:
+        """Host-side check (a device sync): raises if any exchange timed out waiting for a peer."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("add_b200 peer exchange: a peer rank did not arrive (timed out)")
+
+
+_EXCHANGE = {"mode": "auto"}     # 'auto': peer-memory kernel on NCCL groups of CUDA ranks, dist.all_reduce otherwise; 'nccl'; 'peer'
+
+
+def set_exchange_mode(mode: str) -> None:
+    assert mode in ("auto", "nccl", "peer")
+    _EXCHANGE["mode"] = mode
+
+
+def exchange_sum(vec: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """vec <- sum over the ranks, in place: the per-layer SynchronizedBatchNorm2d exchange (forward [sum | ssum | n],
+    backward [sum dy | sum dy*xhat]).  On GPUs it is ONE peer-memory kernel (PeerExchange); on the CPU / gloo tests and as
+    a fallback when symmetric memory cannot be set up it is `dist.all_reduce`."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) <= 1:
+        return vec
+    mode = _EXCHANGE["mode"]
+    if vec.is_cuda and mode in ("auto", "peer") and dist.get_backend(group) == "nccl":
+        try:
+            return PeerExchange.get(group).all_reduce_(vec)
+        except Exception:
+            if mode == "peer":
+                raise
+            _EXCHANGE["mode"] = "nccl"          # symmetric memory unavailable on this system: fall back for good
+    dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+    return vec
+
+
 def _desc(t: torch.Tensor) -> AddTensor:
     """NHWC view descriptor of a logical-NCHW channels_last tensor."""
     n, c, h, w = t.shape
@@ -74,11 +143,11 @@ def batch_norm_forward(bn: nn.BatchNorm2d, x: torch.Tensor, relu: bool = False, 
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         packed = torch.empty(2 * c + 1, dtype=torch.float32, device=x.device)
         check(lib.add_bn_stats_fwd(ctypes.byref(xd), packed.data_ptr(), ws.data_ptr(), ws_bytes, stream), "bn_stats")
-        packed[-1] = float(n * h * w)
+        packed[-1:].fill_(float(n * h * w))      # (a Python-scalar setitem is a host-to-device copy: not graph-capturable)
         if sync is None:
             sync = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         if sync:
-            reduce_stats(packed, group)
+            exchange_sum(packed, group)
         momentum = 0.0
         rm = rv = None
         if bn.training and bn.track_running_stats:

@@ -37,22 +37,29 @@ def _stream(dev) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def _pix_stride(t: torch.Tensor) -> int:
+    n, c, h, w = t.shape
+    return t.stride(3) if w > 1 else (t.stride(2) if h > 1 else (t.stride(0) if n > 1 else c))
+
+
 def _nhwc(t: torch.Tensor) -> torch.Tensor:
     """A logical-NCHW fp32 tensor whose memory is NHWC with unit channel stride (a channels_last tensor or a channel
-    slice of one); anything else is brought into channels_last."""
+    slice of one) is passed through; anything else is copied into channels_last."""
     n, c, h, w = t.shape
     sn, sc, sh, sw = t.stride()
-    ok = t.dtype == torch.float32 and (sc == 1 or c == 1) and sh == w * sw and sn == h * sh and sw % 4 == 0 and sw >= c \
-        and t.data_ptr() % 16 == 0
+    ps = _pix_stride(t)
+    ok = (t.dtype == torch.float32 and (sc == 1 or c == 1) and (w == 1 or h == 1 or sh == w * sw)
+          and (n == 1 or sn == h * w * ps or (h == 1 and w == 1)) and ps % 4 == 0 and ps >= c and t.data_ptr() % 16 == 0)
     if ok:
         return t
-    return t.float().contiguous(memory_format=CL) if not (t.dtype == torch.float32 and t.is_contiguous(memory_format=CL) and c % 4 == 0) \
-        else t
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=t.device, memory_format=CL)
+    out.copy_(t)
+    return out
 
 
 def _desc(t: torch.Tensor) -> AddTensor:
     n, c, h, w = t.shape
-    return AddTensor(t.data_ptr(), n, h, w, c, t.stride(3), ADD_F32)
+    return AddTensor(t.data_ptr(), n, h, w, c, _pix_stride(t), ADD_F32)
 
 
 def _new(n, c, h, w, dev) -> torch.Tensor:
@@ -201,7 +208,7 @@ class _BatchNorm(torch.autograd.Function):
         ws = _ws(lib.add_bn_stats_workspace_bytes(n, h, w, c), dev)
         packed = torch.empty(2 * c + 1, dtype=torch.float32, device=dev)
         check(lib.add_bn_stats_fwd(ctypes.byref(xd), packed.data_ptr(), ws.data_ptr(), ws.numel(), s), "train.bn_stats")
-        packed[-1] = float(n * h * w)
+        packed[-1:].fill_(float(n * h * w))      # (a Python-scalar setitem is a host-to-device copy: not graph-capturable)
         if sync:
             sbn.exchange_sum(packed, group)
         if bn.num_batches_tracked is not None:
@@ -240,15 +247,14 @@ class _BatchNorm(torch.autograd.Function):
                                     sums.data_ptr(), ws.data_ptr(), ws.numel(), s), "train.bn_bwd_reduce")
         dgamma = sums[c:].to(torch.float32) if weight is not None else None       # this rank's (DDP averages parameter grads)
         dbeta = sums[:c].to(torch.float32) if bias is not None else None
-        count = float(n * h * w)
         if sync:
             sums = sums.clone()
-            sbn.exchange_sum(sums, group)
-            count = float(packed[-1].item()) if False else sbn.global_count(packed)
+            sbn.exchange_sum(sums, group)          # [sum dy, sum dy * xhat] over all ranks (batchnorm.py's autograd does the same)
         dx = _new(n, c, h, w, dev)
+        # the element count of the (synchronised) batch is read on the device: packed[2C] holds it after the forward exchange
         check(lib.add_bn_bwd_apply(ctypes.byref(_desc(dy)), ctypes.byref(_desc(x)), mean.data_ptr(), inv_std.data_ptr(), wp, bp,
-                                   sums.data_ptr(), 1.0 / count, var_term.data_ptr() if var_term is not None else None, flags,
-                                   ctypes.byref(_desc(dx)), s), "train.bn_bwd_apply")
+                                   sums.data_ptr(), 0.0, packed.data_ptr() + 8 * c, var_term.data_ptr() if var_term is not None else None,
+                                   flags, ctypes.byref(_desc(dx)), s), "train.bn_bwd_apply")
         return dx, dgamma, dbeta, None, None, None, None
 
 
@@ -385,8 +391,9 @@ class _GlobalAvgPool(torch.autograd.Function):
         n, c, h, w = x.shape
         g = dy.reshape(n, c, 1, 1).contiguous(memory_format=CL)
         dx = _new(n, c, h, w, x.device)
+        # broadcast the 1x1 gradient (bilinear from a 1-pixel source is an exact copy), then scale by 1 / (H*W) in place
         check(lib.add_bilinear_fwd(ctypes.byref(_desc(g)), ctypes.byref(_desc(dx)), 0, _stream(x.device)), "train.gap_bwd_broadcast")
-        dx.mul_(1.0 / float(h * w)) if False else _copy_into(dx, dx, scale=1.0 / float(h * w))
+        _copy_into(dx, dx, scale=1.0 / float(h * w))
         if ctx.relu_in:
             check(lib.add_relu_mask_bwd(ctypes.byref(_desc(x)), ctypes.byref(_desc(dx)), _stream(x.device)), "train.relu_mask")
         return dx, None
@@ -631,6 +638,7 @@ class SGD:
         self.table = torch.from_numpy(np.array(rows, dtype=np.int64)).to(dev)
         self.max_numel = max(r[3] for r in rows)
         self.steps = 0
+        self.lr_dev = torch.full((1,), self.lr, dtype=torch.float32, device=dev)   # read by the kernel (graph-replayable)
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -642,10 +650,16 @@ class SGD:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
             self.flat_grad.mul_(1.0 / dist.get_world_size(group))
 
+    def set_lr(self, lr: float) -> None:
+        self.lr = float(lr)
+        self.lr_dev.fill_(self.lr)
+
     def step(self, lr: Optional[float] = None):
-        lr = self.lr if lr is None else float(lr)
-        check(lib.add_sgd_nesterov(self.table.data_ptr(), len(self.params), self.max_numel, lr, self.momentum, self.weight_decay,
-                                   1 if self.nesterov else 0, 1 if self.steps == 0 else 0, _stream(self.flat_grad.device)), "train.sgd")
+        if lr is not None and float(lr) != self.lr:
+            self.set_lr(lr)
+        check(lib.add_sgd_nesterov(self.table.data_ptr(), len(self.params), self.max_numel, self.lr, self.lr_dev.data_ptr(), self.momentum,
+                                   self.weight_decay, 1 if self.nesterov else 0, 1 if self.steps == 0 else 0,
+                                   _stream(self.flat_grad.device)), "train.sgd")
         self.steps += 1
         from . import runtime as rt
         rt.bump_generation()                     # parameters moved: folded eval-mode weights / recorded plans are stale
@@ -661,9 +675,45 @@ def poly_lr(base_lr: float, it: int, total_iters: int, power: float = 0.9, min_l
 
 def train_step(net, optimizer: SGD, x, target, lr=None, class_weight=None, group=None):
     """One iteration of train.py:216-247.  Returns the loss (a device scalar)."""
+    if lr is not None:
+        optimizer.set_lr(lr)
     optimizer.zero_grad()
     loss, _ = add_loss(net, x, target, class_weight)
     loss.backward()
     optimizer.all_reduce_grads(group)
-    optimizer.step(lr)
+    optimizer.step()
     return loss.detach()
+
+
+class GraphedTrainStep:
+    """The whole iteration — forward, loss, backward, SyncBN exchanges, gradient all-reduce, SGD — as ONE CUDA graph.
+    Eagerly the step is ~5000 kernel launches issued from Python (host-bound: ~250 ms whatever the GPU does); captured,
+    the launches replay back to back.  The first `warmup` calls run eagerly (they are real training steps; they also build
+    the bilinear tables and the peer-exchange buffers), the next call captures the step and from then on every call copies
+    its batch into the static input buffers, sets the learning rate on the device and replays.  Everything that changes
+    between iterations is read on the device: the batch, lr (`add_sgd_nesterov`'s lr_dev), the peer exchange's call counter."""
+
+    def __init__(self, net, optimizer: SGD, class_weight=None, group=None, warmup: int = 2):
+        self.net, self.opt, self.cw, self.group, self.warmup = net, optimizer, class_weight, group, max(1, int(warmup))
+        self.calls = 0
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.x = self.gt = self.loss = None
+
+    def __call__(self, x: torch.Tensor, target: torch.Tensor, lr: Optional[float] = None) -> torch.Tensor:
+        self.calls += 1
+        if self.calls <= self.warmup:
+            return train_step(self.net, self.opt, x, target, lr, self.cw, self.group)
+        if lr is not None:
+            self.opt.set_lr(lr)
+        if self.graph is None:
+            self.x, self.gt = x.clone(), target.clone()
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = train_step(self.net, self.opt, self.x, self.gt, None, self.cw, self.group)
+        else:
+            self.x.copy_(x, non_blocking=True)
+            self.gt.copy_(target, non_blocking=True)
+        self.graph.replay()
+        self.opt.steps += 1
+        return self.loss

@@ -274,8 +274,8 @@ int64_t add_bn_bwd_workspace_bytes(int n, int h, int w, int c);
 int add_bn_bwd_reduce(const add_tensor_t* dy, const add_tensor_t* x, const float* mean, const float* inv_std, const float* gamma,
                       const float* beta, uint32_t flags, double* sums, void* workspace, int64_t workspace_bytes, void* stream);
 int add_bn_bwd_apply(const add_tensor_t* dy, const add_tensor_t* x, const float* mean, const float* inv_std, const float* gamma,
-                     const float* beta, const double* sums, double inv_count, const float* var_term, uint32_t flags,
-                     const add_tensor_t* dx, void* stream);
+                     const float* beta, const double* sums, double inv_count, const float* count_dev, const float* var_term,
+                     uint32_t flags, const add_tensor_t* dx, void* stream);   /* count_dev (device fp32, or NULL): M read on the device */
 /* adjoint of add_bilinear_fwd (F.interpolate bilinear, align_corners=False): per-axis tables built once per (in, out) size */
 int add_bilinear_bwd_tables(int in_size, int out_size, int32_t* i0, int32_t* i1, float* l0, float* l1, int32_t* lo, int32_t* hi,
                             void* stream);
@@ -285,16 +285,27 @@ int add_bilinear_bwd(const add_tensor_t* dy, const add_tensor_t* dx, const int32
 /* 3x3 pool backward (operations.py:9-10): mode 0 avg (count_include_pad=False), 1 max (first maximum) */
 int add_pool3x3_bwd(const add_tensor_t* x, const add_tensor_t* dy, const add_tensor_t* dx, int mode, int stride, uint32_t flags,
                     void* stream);
-/* nn.CrossEntropyLoss(weight, ignore_index) on NCHW fp32 logits (utils/loss.py:16-25; train.py:229-233): loss_wsum[0] = mean
- * loss, [1] = weight sum of the valid pixels; dlogits (or NULL) = grad_scale * d loss / d logits */
+/* nn.CrossEntropyLoss(weight, ignore_index) on fp32 logits (utils/loss.py:16-25; train.py:229-233).  Element (n, c, pixel) at
+ * n*stride_n + c*stride_c + pixel*stride_pix (NCHW or NHWC with channels padded to c_store); loss_wsum[0] = mean loss,
+ * [1] = weight sum of the valid pixels; dlogits (or NULL, same strides) = grad_scale * d loss / d logits */
 int64_t add_ce_loss_workspace_bytes(int n, int h, int w);
-int add_ce_loss_fwd_bwd(const float* logits, const int64_t* target, int n, int num_class, int h, int w, int64_t ignore_index,
-                        const float* class_weight, float grad_scale, float* loss_wsum, float* dlogits, void* workspace,
-                        int64_t workspace_bytes, void* stream);
+int add_ce_loss_fwd_bwd(const float* logits, const int64_t* target, int n, int num_class, int h, int w, int64_t stride_n,
+                        int64_t stride_c, int64_t stride_pix, int c_store, int64_t ignore_index, const float* class_weight,
+                        float grad_scale, float* loss_wsum, float* dlogits, void* workspace, int64_t workspace_bytes, void* stream);
 /* torch.optim.SGD(momentum, weight_decay, nesterov) (train.py:126-127) over a device table of
  * {float* param, const float* grad, float* momentum_buf, int64 numel} entries, one launch */
-int add_sgd_nesterov(const void* table_dev, int n_tensors, int64_t max_numel, float lr, float momentum, float weight_decay,
-                     int nesterov, int first_step, void* stream);
+int add_sgd_nesterov(const void* table_dev, int n_tensors, int64_t max_numel, float lr, const float* lr_dev, float momentum,
+                     float weight_decay, int nesterov, int first_step, void* stream);   /* lr_dev (or NULL): lr read on the device */
+
+/* ---- SynchronizedBatchNorm2d exchange over NVLink peer memory (sync_batchnorm/batchnorm.py:90-111) -------------------------
+ * One-shot all-reduce of a short vector in ONE kernel, no NCCL: each rank writes its vector into its symmetric buffer, signals
+ * every peer, waits for all peers' signals and sums the ranks' vectors in rank order (bit-identical on all ranks).
+ * buf_ptrs / signal_ptrs: HOST arrays of `world` peer-mapped addresses (symmetric buffer = 2 slots of cap_bytes; signal pad =
+ * >= world zero-initialised uint32 words); epoch = 1, 2, 3, ... the same on every rank; status_dev: set to 1 when a peer did
+ * not arrive within ~2 s (never hangs).  vec is fp32 (elem_bytes 4) or fp64 (8). */
+int add_peer_allreduce(void* vec, int n, int elem_bytes, const uint64_t* buf_ptrs, const uint64_t* signal_ptrs, int rank, int world,
+                       uint32_t epoch, uint32_t* epoch_dev, int64_t cap_bytes, int* status_dev, void* stream);
+/* epoch_dev (or NULL): device call counter incremented by the kernel itself — the launch is then CUDA-graph replayable */
 
 #ifdef __cplusplus
 }

@@ -322,7 +322,90 @@ def gen_io_edges():
     print("io_edges.npz", len(g), "arrays")
 
 
+def gen_train_ops_grad():
+    """Backward of the conv operators in TRAINING mode: the unmodified reference modules, loss = sum(y * cotangent),
+    `.backward()` -> input gradient and every parameter gradient."""
+    g = {}
+    for name in util.TRAIN_OP_CASES:
+        spec = util.OP_CASES[name]
+        ours, x, cot = util.make_op_grad_case(name)
+        kind, args = spec["kind"], spec["args"]
+        if kind == "OPS":
+            ref = ref_ops.OPS[args[0]](args[1], args[2] if len(args) > 2 else 1, BN, 1e-5, 0.1, True)
+        else:
+            ref = getattr(ref_ops, kind)(*args, BN)
+        ref.load_state_dict(ours.state_dict(), strict=True)
+        ref.train()
+        xr = x.clone().requires_grad_(True)
+        y = ref(xr)
+        (y * cot).sum().backward()
+        g[f"{name}/y"] = f32(y)
+        g[f"{name}/dx"] = f32(xr.grad)
+        for k, p_ in ref.named_parameters():
+            g[f"{name}/grad/{k}"] = f32(p_.grad)
+    np.savez_compressed(OUT / "train_ops_grad.npz", **g)
+    print("train_ops_grad.npz", len(g), "arrays", os.path.getsize(OUT / "train_ops_grad.npz") / 1e6, "MB")
+
+
+def gen_train_step():
+    """Two iterations of train.py:216-247 with the unmodified reference ADD in train mode: forward (batch-statistics
+    BatchNorm), loss = mean over the exits of nn.CrossEntropyLoss(ignore_index=255) (utils/loss.py), backward,
+    torch.optim.SGD(momentum, weight_decay, nesterov) (train.py:126-127).  Stored: the losses, per parameter the sum and
+    abs-sum of its first-step gradient (full tensors for a few), and per parameter / running statistic the sum and abs-sum
+    after each step."""
+    spec = util.TRAIN_STEP
+    ours, x, gt = util.make_train_case()
+    na, ci, low = util.net_arch(spec)
+    ref = RefADD(na, ci, util.cell_arch(), 19, SimpleNamespace(F=spec["F"], B=5, sync_bn=False), low)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ref.train()
+    opt = torch.optim.SGD(ref.parameters(), lr=spec["lr"], momentum=spec["momentum"], weight_decay=spec["weight_decay"],
+                          nesterov=spec["nesterov"])
+    crit = torch.nn.CrossEntropyLoss(ignore_index=255)
+    g = {}
+    for step in range(spec["steps"]):
+        opt.zero_grad()
+        outs = ref(x)
+        losses = [crit(o, gt) for o in outs]
+        loss = sum(losses) / len(losses)
+        loss.backward()
+        g[f"step{step}/loss"] = np.float64(loss.item())
+        g[f"step{step}/exit_losses"] = np.array([l.item() for l in losses], dtype=np.float64)
+        if step == 0:
+            names, sums, asums = [], [], []
+            for k, p_ in ref.named_parameters():
+                names.append(k); sums.append(p_.grad.double().sum().item()); asums.append(p_.grad.double().abs().sum().item())
+                if k in util.TRAIN_FULL_GRADS:
+                    g[f"grad/{k}"] = f32(p_.grad)
+            g["grad_names"] = np.array(names)
+            g["grad_sum"] = np.array(sums, dtype=np.float64)
+            g["grad_abs_sum"] = np.array(asums, dtype=np.float64)
+            # conditioning of this gradient: the reference's OWN first-step gradients when the input is perturbed by 1e-6
+            # relative (a random-init 12-cell network with BatchNorm over small batches is chaotic: they move by percents)
+            import copy
+            ref_p = copy.deepcopy(ref)
+            ref_p.zero_grad()
+            xp = x * (1 + 1e-6 * torch.randn(x.shape, generator=torch.Generator().manual_seed(62)))
+            outs_p = ref_p(xp)
+            (sum(crit(o, gt) for o in outs_p) / len(outs_p)).backward()
+            g["grad_abs_sum_pert"] = np.array([p_.grad.double().abs().sum().item() for _, p_ in ref_p.named_parameters()], dtype=np.float64)
+            g["grad_rel_change_pert"] = np.array([float((p_.grad - q_.grad).abs().max() / q_.grad.abs().max().clamp_min(1e-30))
+                                                  for (_, p_), (_, q_) in zip(ref_p.named_parameters(), ref.named_parameters())], dtype=np.float64)
+        opt.step()
+        sd = ref.state_dict()
+        keys = [k for k, v in sd.items() if v.dtype.is_floating_point]
+        g[f"step{step}/state_names"] = np.array(keys)
+        g[f"step{step}/state_sum"] = np.array([sd[k].double().sum().item() for k in keys], dtype=np.float64)
+        g[f"step{step}/state_abs_sum"] = np.array([sd[k].double().abs().sum().item() for k in keys], dtype=np.float64)
+    np.savez_compressed(OUT / "train_step.npz", **g)
+    print("train_step.npz", len(g), "arrays", os.path.getsize(OUT / "train_step.npz") / 1e6, "MB", "losses", g["step0/loss"], g["step1/loss"])
+
+
 if __name__ == "__main__":
+    if "--only-train" in sys.argv:
+        gen_train_ops_grad()
+        gen_train_step()
+        sys.exit(0)
     if "--only-io" in sys.argv:
         gen_io_edges()
         sys.exit(0)
@@ -342,3 +425,5 @@ if __name__ == "__main__":
     gen_mixed_op()
     gen_gates()
     gen_io_edges()
+    gen_train_step()
+    gen_train_ops_grad()

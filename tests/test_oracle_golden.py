@@ -179,3 +179,47 @@ def test_io_edges_oracle_matches_reference():
         assert t.shape == IO[f"{name}/image"].shape and np.array_equal(t.numpy(), IO[f"{name}/image"])    # bit-identical
         assert np.array_equal(m.numpy(), IO[f"{name}/label"])
         assert np.array_equal(orc.decode_segmap(enc.astype(np.int64)), IO[f"{name}/decoded"])
+
+
+TRAIN = np.load(util.ROOT / "tests/golden/train_step.npz")
+
+
+def test_train_step_oracle_matches_reference():
+    """train.py:216-247 restated with the oracle (its functional graph under `bn_training` + torch autograd + the SGD
+    formulas) against the fixture made by the unmodified reference: loss, every parameter's gradient (sum / |sum|, a few
+    in full) and every parameter / running statistic after each of two SGD-nesterov steps."""
+    spec = util.TRAIN_STEP
+    net, x, gt = util.make_train_case()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    params = [k for k, _ in net.named_parameters()]
+    for k in params:
+        sd[k].requires_grad_(True)
+    bufs = {k: torch.zeros_like(sd[k]) for k in params}
+    arch = util.oracle_arch(spec)
+    for step in range(spec["steps"]):
+        with orc.bn_training(momentum=0.1):
+            outs = orc.add_forward(sd, arch, x)
+        losses = [torch.nn.functional.cross_entropy(o, gt, ignore_index=255) for o in outs]
+        loss = sum(losses) / len(losses)
+        grads = torch.autograd.grad(loss, [sd[k] for k in params])
+        assert float(loss) == pytest.approx(float(TRAIN[f"step{step}/loss"]), rel=1e-5)
+        if step == 0:
+            want = {str(k): float(a_) for k, a_ in zip(TRAIN["grad_names"], TRAIN["grad_abs_sum"])}
+            assert sorted(want) == sorted(params)
+            for k, g_ in zip(params, grads):
+                assert float(g_.double().abs().sum()) == pytest.approx(want[k], rel=2e-3, abs=1e-7), k
+                if k in util.TRAIN_FULL_GRADS:
+                    ref = torch.from_numpy(TRAIN[f"grad/{k}"])
+                    assert util.rel_err(g_, ref) < 2e-3, k
+        with torch.no_grad():                      # torch.optim.SGD (train.py:126-127): wd, momentum buffer, nesterov
+            for k, g_ in zip(params, grads):
+                d = g_ + spec["weight_decay"] * sd[k]
+                bufs[k] = d.clone() if step == 0 else spec["momentum"] * bufs[k] + d
+                d = d + spec["momentum"] * bufs[k]
+                sd[k] -= spec["lr"] * d
+        # step 0 starts from bit-identical inputs: tight.  The second step's gradient is ill-conditioned (BatchNorm over the
+        # 50 samples of the stride-32 level amplifies the 1e-7 differences of the updated parameters: reference against
+        # itself-as-oracle differs by up to 1e-1 on single tensors there), so after it only a loose bound holds
+        tol = 1e-4 if step == 0 else 5e-2
+        for k, a_ in zip(TRAIN[f"step{step}/state_names"], TRAIN[f"step{step}/state_abs_sum"]):
+            assert float(sd[str(k)].detach().double().abs().sum()) == pytest.approx(float(a_), rel=tol, abs=1e-6), (step, k)

@@ -258,3 +258,34 @@ def make_io_case(name):
     ids = torch.randint(0, 40, (spec["h"], spec["w"]), generator=g, dtype=torch.int64)
     ids.view(-1)[:256] = torch.arange(256)
     return img.numpy(), ids.to(torch.uint8).numpy()
+
+
+# ---- training step (train.py:216-247) ----------------------------------------------------------------
+TRAIN_STEP = dict(network="searched-dense", C=2, F=20, n=2, size=(129, 129), seed=61, lr=0.01, momentum=0.9, weight_decay=4e-5,
+                  nesterov=True, steps=2)
+# parameters whose full gradients are stored in the fixture (the rest: sum and |sum| per tensor)
+TRAIN_FULL_GRADS = ["stem0.0.weight", "stem1.1.weight", "cells.0.preprocess.conv_2.weight", "cells.0._ops.0.op.1.weight",
+                    "cells.0._ops.1.op.1.weight", "cells.0._ops.1.op.6.weight", "cells.0._ops.1.op.7.bias",
+                    "cells.3.pre_preprocess.1.op.1.weight", "cells.5.preprocess.op.1.weight", "cells.11._ops.6.op.5.weight",
+                    "cells.11.pre_preprocess_1x1.op.2.weight", "low_level_conv.1.weight", "aspp.aspp5.weight",
+                    "aspp.aspp5_bn.weight", "aspp.aspp3_bn.bias", "decoder._conv.2.weight", "decoder._conv.5.bias",
+                    "decoder._conv.7.weight", "decoder._conv.7.bias"]
+
+
+def make_train_case():
+    spec = TRAIN_STEP
+    net = make_net(spec)                       # randomised BN affine parameters and running statistics
+    g = torch.Generator().manual_seed(spec["seed"])
+    x = torch.randn(spec["n"], 3, *spec["size"], generator=g)
+    gt = torch.randint(0, 19, (spec["n"], *spec["size"]), generator=g, dtype=torch.int64)
+    gt[torch.rand(spec["n"], *spec["size"], generator=g) < 0.1] = 255
+    return net, x, gt
+
+
+def make_op_grad_case(name):
+    """(module in train mode, input, seeded cotangent of the output's shape): loss = sum(output * cotangent)."""
+    m, x = make_op_case(name)
+    m.train()
+    g = torch.Generator().manual_seed(700 + sorted(OP_CASES).index(name))
+    n, c, h, w = m.out_shape(*x.shape)
+    return m, x, torch.randn(n, c, h, w, generator=g)

@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""BASELINE config 3: fixed-architecture train step with SynchronizedBatchNorm2d, 769x769 crops, batch 16 in total
+sharded over the ranks (strong scaling: 16 / world images per GPU), fp32.  One step = train.py:216-247: forward (train
+mode) -> mean-over-exits cross entropy -> backward -> gradient all-reduce -> SGD-nesterov (add_b200.training).
+Collectives: per BN layer and direction ONE peer-memory exchange kernel over NVLink (csrc/peer.cu; --exchange nccl uses
+dist.all_reduce instead), plus ONE NCCL all-reduce of the flat gradient buffer per step.
+
+    python tools/train_bench.py [--steps K] [--warmup W] [--batch 16] [--size 769]           # 1 GPU
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_bench.py ...
+
+Prints one JSON line on rank 0 (not the driver's headline metric: that is bench.py)."""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--batch", type=int, default=16, help="TOTAL batch over all ranks")
+ap.add_argument("--size", type=int, default=769)
+ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"])
+ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying it as one CUDA graph")
+ap.add_argument("--check", action="store_true", help="also verify the peer exchange against dist.all_reduce and SyncBN against one rank")
+a = ap.parse_args()
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+import __graft_entry__ as g  # noqa: E402
+if rank == 0:
+    g.build()
+if world > 1:
+    dist.barrier()
+import add_b200  # noqa: E402
+from add_b200 import training as T, sync_batchnorm as sbn  # noqa: E402
+
+sbn.set_exchange_mode(a.exchange)
+na, ci, low = add_b200.NETWORKS["searched-dense"][2]
+torch.manual_seed(1)
+net = add_b200.ADD(na, ci, add_b200.AUTODEEPLAB_CELL.copy(), 19, add_b200.Args(20, 5, sync_bn=True), low).to(dev).train()
+opt = T.SGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=4e-5, nesterov=True)
+per = a.batch // world
+x, gt = add_b200.synthetic_batch(per, a.size, a.size, seed=1234 + rank)
+x, gt = x.to(dev), gt.to(dev)
+result = {}
+if a.check and world > 1:
+    # (1) the peer-memory kernel against NCCL on random vectors, fp32 and fp64
+    ok = True
+    for dt in (torch.float32, torch.float64):
+        v = torch.randn(2 * 1280 + 1, dtype=dt, device=dev, generator=torch.Generator(device=dev).manual_seed(10 + rank))
+        w = v.clone()
+        sbn.PeerExchange.get(None).all_reduce_(v)
+        dist.all_reduce(w)
+        ok = ok and bool(((v - w).abs().max() <= 1e-5 * w.abs().max()).item())
+    sbn.PeerExchange.get(None).check_status()
+    result["peer_exchange_matches_nccl"] = ok
+    # (2) SynchronizedBatchNorm2d forward / backward over the ranks == one rank on the concatenated batch
+    bn = add_b200.SynchronizedBatchNorm2d(40).to(dev).train()
+    xs = torch.randn(2, 40, 9, 11, device=dev, generator=torch.Generator(device=dev).manual_seed(20 + rank)).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = T.batch_norm(bn, xs, relu=True)
+    cot = torch.randn(y.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(30 + rank))
+    (y * cot).sum().backward()
+    gather = lambda t: torch.cat([u for u in _all_gather(t)], 0)
+
+    def _all_gather(t):
+        out = [torch.empty_like(t.contiguous()) for _ in range(world)]
+        dist.all_gather(out, t.contiguous())
+        return out
+    X, C = gather(xs.detach()), gather(cot)
+    Xr = X.clone().requires_grad_(True)
+    ref_bn = torch.nn.BatchNorm2d(40).to(dev).train()
+    yr = torch.relu(ref_bn(Xr))
+    (yr * C).sum().backward()
+    sl = slice(2 * rank, 2 * rank + 2)
+    e_y = float((y.detach() - yr.detach()[sl]).abs().max() / yr.abs().max())
+    e_dx = float((xs.grad - Xr.grad[sl]).abs().max() / Xr.grad.abs().max())
+    result["syncbn_fwd_rel_err"], result["syncbn_dx_rel_err"] = e_y, e_dx
+
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+step_fn = (lambda: T.train_step(net, opt, x, gt)) if a.no_graph else (lambda _s=T.GraphedTrainStep(net, opt, warmup=1): _s(x, gt))
+for _ in range(max(a.warmup, 3)):        # eager warm-up, the capture, one replay
+    step_fn()
+barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter()
+e0.record()
+for _ in range(a.steps):
+    loss = step_fn()
+e1.record()
+barrier()
+ms = e0.elapsed_time(e1)
+if world > 1:
+    t = torch.tensor([ms], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+calls = sbn.PeerExchange._instances[0].calls if sbn.PeerExchange._instances else 0
+if rank == 0:
+    print(json.dumps({"metric": "ADD fixed-arch train step images/sec (BASELINE config 3)", "value": a.batch * a.steps / (ms / 1e3),
+                      "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+                      "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"searched-dense ADD C=2 F=20 train step, {a.batch}x3x{a.size}x{a.size} total "
+                                             f"({per} per GPU), SynchronizedBatchNorm2d, CE ignore 255, SGD nesterov",
+                                 "syncbn_exchange": ("peer-memory one-shot all-reduce kernel (csrc/peer.cu), one per BN layer and direction"
+                                                     if calls else ("dist.all_reduce per BN layer and direction" if world > 1 else "single rank")),
+                                 "peer_exchange_calls": calls, "cuda_graph": not a.no_graph, "grad_allreduce": "one NCCL all-reduce of the flat gradient buffer" if world > 1 else None},
+                      "loss": float(loss), **result}))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
