@@ -9,13 +9,15 @@ from .runtime import (set_default_precision, default_precision, set_tc_enabled, 
                       ConvWeights)
 from .genotypes import PRIMITIVES, AUTODEEPLAB_CELL, NETWORKS
 from .operations import (OPS, ReLUConvBN, DilConv, SepConv, Identity, Zero, FactorizedReduce,
-                         DoubleFactorizedReduce, SynchronizedBatchNorm2d, normalized_shannon_entropy,
+                         DoubleFactorizedReduce, SynchronizedBatchNorm2d, ASPP, normalized_shannon_entropy,
                          confidence_max)
 from .aspp_train import ASPP_train
 from .decoder import Decoder
 from .ADD import ADD, Cell, EDM
 from .baseline_model import Baselin_Model, AutoDeepLab, Cell_baseline, Cell_AutoDeepLab
-from .cell_level_search import MixedOp
+from .cell_level_search import MixedOp, softmax_rows
+from . import cell_level_search
+from . import training
 from .metrics import Evaluator
 from .factory import build_add, Args, synthetic_batch, synthetic_batch_u8, normalize_u8_hwc_host
 from .pipeline import HostPipeline, ResidentPipeline

@@ -95,6 +95,12 @@ _SIGS = {
                                     c_float, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "add_sgd_nesterov": (c_int, [c_void_p, c_int, c_int64, c_float, c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
     "add_peer_allreduce": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_uint32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "add_mixed_light_fwd": (c_int, [TP, TP, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "add_weighted_sum_fwd": (c_int, [c_void_p, c_int, c_void_p, TP, c_void_p]),
+    "add_weighted_sum_workspace_bytes": (c_int64, [c_int] * 4),
+    "add_weighted_sum_bwd": (c_int, [TP, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "add_softmax_rows_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "add_softmax_rows_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "add_widen_labels_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "add_confusion_workspace_bytes": (c_int64, [c_int64, c_int]),
     "add_confusion_matrix": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),

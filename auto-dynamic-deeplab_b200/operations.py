@@ -360,6 +360,68 @@ class DoubleFactorizedReduce(_FactorizedReduceBase):
         super().__init__(C_in, C_out, BatchNorm, _bn_kwargs=dict(affine=affine))
 
 
+class ASPP(AddModule):
+    """The search-time head (reference operations.py:122-158): relu; conv11 (1x1+BN+ReLU), conv33 (dilated 3x3+BN+ReLU),
+    conv_p on the global-average-pooled map (1x1+BN+ReLU, up-sampled with align_corners=True = broadcast); cat; concate_conv
+    (1x1+BN+ReLU); final_conv (1x1, no BN, no bias).  Same attribute names / state_dict keys.  Training mode runs (and
+    differentiates) through `training.py`; eval mode is six fused launches (the pooled branch enters the concat 1x1 as a
+    per-image bias, like ASPP_train)."""
+
+    def __init__(self, in_channels, out_channels, paddings, dilations, BatchNorm=nn.BatchNorm2d, momentum=0.0003):
+        super().__init__()
+        C = in_channels
+        self.relu = nn.ReLU()
+        self.conv11 = nn.Sequential(_conv_holder(C, C, 1), BatchNorm(C), nn.ReLU(inplace=True))
+        self.conv33 = nn.Sequential(_conv_holder(C, C, 3, padding=paddings, dilation=dilations), BatchNorm(C), nn.ReLU(inplace=True))
+        self.conv_p = nn.Sequential(_conv_holder(C, C, 1), BatchNorm(C), nn.ReLU(inplace=True))
+        self.concate_conv = nn.Sequential(_conv_holder(C * 3, C, 1), BatchNorm(C), nn.ReLU(inplace=True))
+        self.final_conv = _conv_holder(C, out_channels, 1)
+        self._C, self._out, self._pad, self._dil = C, out_channels, paddings, dilations
+
+    def _prepare(self):
+        self.cw11 = ConvWeights(self.conv11[0].weight, self.conv11[1])
+        self.cw33 = ConvWeights(self.conv33[0].weight, self.conv33[1])
+        self.cwp = ConvWeights(self.conv_p[0].weight, self.conv_p[1])
+        cwc = ConvWeights(self.concate_conv[0].weight, self.concate_conv[1])
+        C, dev = self._C, cwc.w.device
+        self.cwc_main = ConvWeights.from_folded(cwc.w_h[:, :, :2 * C, :].contiguous(), cwc.bias_h, dev)
+        self.wc_pool = rt.host_to(cwc.w_h[0, 0, 2 * C:, :], dev)
+        self.bias_c = cwc.bias
+        self.cwf = ConvWeights(self.final_conv.weight)
+
+    def out_shape(self, n, c, h, w):
+        return n, self._out, h, w
+
+    def emit(self, b, x, y, flags=0):
+        self._ensure_prepared()
+        C = self._C
+        rin = 0 if flags & IN_RELUD else RELU_IN
+        cat = b.scratch(x.n, x.h, x.w, 2 * C)
+        b.conv(x, cat.slice(0, C), self.cw11, 1, 0, 1, rin | RELU_OUT, "ASPP.conv11")
+        b.conv(x, cat.slice(C, C), self.cw33, 1, self._pad, self._dil, rin | RELU_OUT, "ASPP.conv33")
+        pooled = b.raw((x.n, C), torch.float32)
+        b.gap(x, pooled, rin, "ASPP.gap")
+        bias_n = b.raw((x.n, C), torch.float32)
+        b.aspp_pool_bias(pooled, self.cwp, self.wc_pool, self.bias_c, bias_n, "ASPP.pool_bias")
+        t = b.scratch(x.n, x.h, x.w, C)
+        b.conv(cat, t, self.cwc_main, 1, 0, 1, RELU_OUT, "ASPP.concate_conv", image_bias=bias_n)
+        b.conv(t, y, self.cwf, 1, 0, 1, 0, "ASPP.final_conv")
+        b.release(cat)
+        b.release(t)
+
+    def _forward_train(self, x):
+        from . import training as T
+        h, w = x.shape[2], x.shape[3]
+        a = T.batch_norm(self.conv11[1], T.conv2d(x, self.conv11[0].weight, relu_in=True), relu=True)
+        c33 = self.conv33[0]
+        bq = T.batch_norm(self.conv33[1], T.conv2d(x, c33.weight, None, 1, c33.padding[0], c33.dilation[0], relu_in=True), relu=True)
+        p = T._GlobalAvgPool.apply(x, True)
+        p = T.batch_norm(self.conv_p[1], T.conv2d(p, self.conv_p[0].weight), relu=True)
+        cat = T.cat([a, bq, T._Broadcast.apply(p, h, w)])
+        y = T.batch_norm(self.concate_conv[1], T.conv2d(cat, self.concate_conv[0].weight), relu=True)
+        return T.conv2d(y, self.final_conv.weight)
+
+
 # ---- confidence scalars (operations.py:161-180) ------------------------------------------------
 
 def _confidence(x: torch.Tensor, threshold: float, num_class: int):

@@ -140,6 +140,11 @@ class _Conv(torch.autograd.Function):
 
 
 def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1, relu_in=False, cout_pad=None):
+    cout = weight.shape[0]
+    if cout_pad is None and cout % 4:
+        # the backward kernels read gradients as 4-channel vectors: carry zero channels up to a multiple of 4 and hand
+        # out the channel slice (its gradient comes back zero-padded)
+        return _Conv.apply(x, weight, bias, stride, pad, dil, relu_in, (cout + 3) // 4 * 4)[:, :cout]
     return _Conv.apply(x, weight, bias, stride, pad, dil, relu_in, cout_pad)
 
 

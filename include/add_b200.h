@@ -307,6 +307,23 @@ int add_peer_allreduce(void* vec, int n, int elem_bytes, const uint64_t* buf_ptr
                        uint32_t epoch, uint32_t* epoch_dev, int64_t cap_bytes, int* status_dev, void* stream);
 /* epoch_dev (or NULL): device call counter incremented by the kernel itself — the launch is then CUDA-graph replayable */
 
+/* ---- supernet edge: MixedOp = sum_k w_k * op_k(x) over the eight PRIMITIVES (cell_level_search.py:10-29) -- */
+/* The four parameter-free primitives of an edge in ONE kernel, x read once:
+ *   y (+)= w[0] * (x * 0) + w[1] * BN(maxpool3x3(x)) + w[2] * BN(avgpool3x3(x)) + w[3] * x        (PRIMITIVES order)
+ * w8_dev: device fp32 [8] (the softmaxed alphas of the edge; entries 4..7 belong to the conv primitives, which add
+ * w_k * op_k(x) in their own epilogues); BN(affine=False) after each pool as per-channel (mean, inv_std) device vectors. */
+int add_mixed_light_fwd(const add_tensor_t* x, const add_tensor_t* y, const float* w8_dev, const float* max_mean,
+                        const float* max_inv_std, const float* avg_mean, const float* avg_inv_std, uint32_t flags, void* stream);
+/* y = sum_k w[k] * y_k, the k weights read on the device; ys: HOST array of k descriptors (NULL entry = primitive skipped).
+ * Backward: dys[k] (NULL = not needed) = w[k] * dy, dw[k] = <dy, y_k> (deterministic).  fp32. */
+int add_weighted_sum_fwd(const add_tensor_t* const* ys, int k, const float* w_dev, const add_tensor_t* out, void* stream);
+int64_t add_weighted_sum_workspace_bytes(int n, int h, int w, int c);
+int add_weighted_sum_bwd(const add_tensor_t* dy, const add_tensor_t* const* ys, const add_tensor_t* const* dys, int k,
+                         const float* w_dev, float* dw_dev, void* workspace, int64_t workspace_bytes, void* stream);
+/* softmax over the last dimension of a [rows, k] fp32 matrix, k <= 32 (alphas / betas, model_net_search.py:294-310) */
+int add_softmax_rows_fwd(const float* x, float* y, int rows, int k, void* stream);
+int add_softmax_rows_bwd(const float* y, const float* dy, float* dx, int rows, int k, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -195,6 +195,66 @@ def factorized_reduce(sd: SD, p: str, x: torch.Tensor, step: int = 2) -> torch.T
     return _bn(sd, p + '.bn', out)
 
 
+def _search_scale_dimension(dim: int, scale: float) -> int:
+    """cell_level_search.py:81-83."""
+    return int((float(dim) - 1.0) * scale + 1.0) if dim % 2 else int(dim * scale)
+
+
+def search_cell_forward(sd: SD, p: str, B: int, s0, s1_down, s1_same, s1_up, n_alphas: torch.Tensor,
+                        pre_preprocess_sample_rate: float = 1) -> List[torch.Tensor]:
+    """cell_level_search.py:96-155 — the supernet cell: preprocess each present s1 (down: FactorizedReduce, same: 1x1,
+    up: bilinear x2 then 1x1), resize + pre_preprocess s0, then for each s1 list B steps of MixedOp edges (ops shared
+    between the lists), concat of the last B states per list."""
+    size = None
+    if s1_down is not None:
+        s1_down = factorized_reduce(sd, p + '.preprocess_down', s1_down, 2)
+        size = s1_down.shape[2:]
+    if s1_same is not None:
+        s1_same = relu_conv_bn(sd, p + '.preprocess_same', s1_same)
+        size = s1_same.shape[2:]
+    if s1_up is not None:
+        s1_up = _bilinear(s1_up, (_search_scale_dimension(s1_up.shape[2], 2), _search_scale_dimension(s1_up.shape[3], 2)))
+        s1_up = relu_conv_bn(sd, p + '.preprocess_up', s1_up)
+        size = s1_up.shape[2:]
+    if s0 is not None:
+        if s0.shape[2] < size[0] or s0.shape[3] < size[1]:
+            s0 = _bilinear(s0, size)
+        if pre_preprocess_sample_rate >= 1:
+            s0 = relu_conv_bn(sd, p + '.pre_preprocess', s0)
+        else:
+            s0 = factorized_reduce(sd, p + '.pre_preprocess', s0, 2 if pre_preprocess_sample_rate == 0.5 else 4)
+    outs = []
+    for s1 in (s1_down, s1_same, s1_up):
+        if s1 is None:
+            continue
+        states = [s0 if s0 is not None else 0, s1]
+        offset = 0
+        for i in range(B):
+            new = []
+            for j, h in enumerate(states):
+                b = offset + j
+                if s0 is None and j == 0:          # `_ops[b] is None` (prev_prev_C == -1, :73-75)
+                    continue
+                new.append(mixed_op(sd, f'{p}._ops.{b}', h, n_alphas[b]))
+            states.append(sum(new))
+            offset += len(states) - 1
+        outs.append(torch.cat(states[-B:], dim=1))
+    return outs
+
+
+def search_aspp(sd: SD, p: str, x: torch.Tensor, padding: int, dilation: int) -> torch.Tensor:
+    """operations.py:122-158 — the search-time ASPP head."""
+    x = F.relu(x)
+    a = F.relu(_bn(sd, p + '.conv11.1', F.conv2d(x, sd[p + '.conv11.0.weight'])))
+    b = F.relu(_bn(sd, p + '.conv33.1', F.conv2d(x, sd[p + '.conv33.0.weight'], None, 1, padding, dilation)))
+    g = F.adaptive_avg_pool2d(x, 1)
+    g = F.relu(_bn(sd, p + '.conv_p.1', F.conv2d(g, sd[p + '.conv_p.0.weight'])))
+    g = F.interpolate(g, size=x.shape[2:], mode='bilinear', align_corners=True)
+    y = torch.cat([a, b, g], dim=1)
+    y = F.relu(_bn(sd, p + '.concate_conv.1', F.conv2d(y, sd[p + '.concate_conv.0.weight'])))
+    return F.conv2d(y, sd[p + '.final_conv.weight'])
+
+
 # --------------------------------------------------------------------------------------
 # blocks
 # --------------------------------------------------------------------------------------

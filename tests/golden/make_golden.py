@@ -322,6 +322,57 @@ def gen_io_edges():
     print("io_edges.npz", len(g), "arrays")
 
 
+def gen_search_cell():
+    """The supernet cell (cell_level_search.py:32-155) and the search-time ASPP head (operations.py:122-158), the
+    unmodified reference: eval-mode forward, training-mode forward + backward (loss = sum of outputs x cotangents) with
+    the alphas softmaxed as in model_net_search.py:294-310 — gradients of the inputs, the raw alphas and every weight,
+    and the running statistics after the training forward."""
+    from modeling.cell_level_search import Cell as RefSearchCell
+    g = {}
+    c = util.SEARCH_CELL
+    ours, s0, s1_same, s1_up, alphas, cots = util.make_search_cell_case()
+    ref = RefSearchCell(c["B"], c["prev_prev_C"], c["prev_C_down"], c["prev_C_same"], c["prev_C_up"], c["C_out"])
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ref.eval()
+    with torch.no_grad():
+        outs = ref(s0.clone(), None, s1_same.clone(), s1_up.clone(), torch.softmax(alphas, dim=-1))
+    for i, o in enumerate(outs):
+        g[f"cell/eval/out{i}"] = f32(o)
+    ref.train()
+    ins = [t.clone().requires_grad_(True) for t in (s0, s1_same, s1_up)]
+    al = alphas.clone().requires_grad_(True)
+    outs = ref(ins[0], None, ins[1], ins[2], torch.softmax(al, dim=-1))
+    sum((o * ct).sum() for o, ct in zip(outs, cots)).backward()
+    for i, o in enumerate(outs):
+        g[f"cell/train/out{i}"] = f32(o)
+    for nme, t in zip(("s0", "s1_same", "s1_up"), ins):
+        g[f"cell/train/d_{nme}"] = f32(t.grad)
+    g["cell/train/d_alphas"] = f32(al.grad)
+    for k, p_ in ref.named_parameters():
+        g[f"cell/train/grad/{k}"] = f32(p_.grad)
+    for k, v in ref.state_dict().items():
+        if "running_" in k:
+            g[f"cell/train/sd/{k}"] = f32(v)
+    # search-time ASPP
+    a = util.SEARCH_ASPP
+    ours, x, cot = util.make_search_aspp_case()
+    ref = ref_ops.ASPP(a["C"], a["out"], a["pad"], a["dil"])
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ref.eval()
+    with torch.no_grad():
+        g["aspp/eval/y"] = f32(ref(x.clone()))
+    ref.train()
+    xr = x.clone().requires_grad_(True)
+    y = ref(xr)
+    (y * cot).sum().backward()
+    g["aspp/train/y"] = f32(y)
+    g["aspp/train/dx"] = f32(xr.grad)
+    for k, p_ in ref.named_parameters():
+        g[f"aspp/train/grad/{k}"] = f32(p_.grad)
+    np.savez_compressed(OUT / "search_cell.npz", **g)
+    print("search_cell.npz", len(g), "arrays", os.path.getsize(OUT / "search_cell.npz") / 1e6, "MB")
+
+
 def gen_train_ops_grad():
     """Backward of the conv operators in TRAINING mode: the unmodified reference modules, loss = sum(y * cotangent),
     `.backward()` -> input gradient and every parameter gradient."""
@@ -402,6 +453,9 @@ def gen_train_step():
 
 
 if __name__ == "__main__":
+    if "--only-search" in sys.argv:
+        gen_search_cell()
+        sys.exit(0)
     if "--only-train" in sys.argv:
         gen_train_ops_grad()
         gen_train_step()
@@ -427,3 +481,4 @@ if __name__ == "__main__":
     gen_io_edges()
     gen_train_step()
     gen_train_ops_grad()
+    gen_search_cell()

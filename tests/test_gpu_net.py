@@ -296,8 +296,13 @@ def test_three_gated_exits_plan_cache_lineage():
         _, _, _, cv = net.dynamic_inference(xd[i:i + 1], threshold=1e30, confidence='edm', edm=edm)   # exits at gate 1
         firsts.append(float(cv))
     srt = sorted(firsts)
+    lasts = []
+    for i in range(n):
+        _, _, _, cv = net.dynamic_inference(xd[i:i + 1], threshold=-1e30, confidence='edm', edm=edm)  # never exits: last gate's value
+        lasts.append(float(cv))
+    mid_last = float(np.median(lasts))
     patterns_seen = set()
-    for thr in (0.5 * (srt[1] + srt[2]), 0.5 * (srt[3] + srt[4]), srt[0] - 1.0, 0.5 * (srt[2] + srt[3]), 0.5 * (srt[1] + srt[2])):
+    for thr in (0.5 * (srt[1] + srt[2]), -1e30, mid_last, 0.5 * (srt[3] + srt[4]), mid_last, 0.5 * (srt[1] + srt[2])):
         ref = []
         for i in range(n):                       # clone at once: the logits alias plan buffers the next call overwrites
             y1, e1, _, c1 = net.dynamic_inference(xd[i:i + 1], threshold=thr, confidence='edm', edm=edm)

@@ -289,3 +289,52 @@ def make_op_grad_case(name):
     g = torch.Generator().manual_seed(700 + sorted(OP_CASES).index(name))
     n, c, h, w = m.out_shape(*x.shape)
     return m, x, torch.randn(n, c, h, w, generator=g)
+
+
+# ---- supernet cell / search-time ASPP -----------------------------------------------------------------
+SEARCH_CELL = dict(B=2, prev_prev_C=16, prev_C_down=None, prev_C_same=24, prev_C_up=32, C_out=16, n=2, h=12, w=16, seed=71)
+SEARCH_ASPP = dict(C=24, out=19, pad=6, dil=6, x=(2, 24, 11, 13), seed=72)
+
+
+def _randomize_running(m, g):
+    with torch.no_grad():
+        for k, v in m.state_dict().items():
+            if k.endswith("running_mean"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+            elif k.endswith("running_var"):
+                v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+    return m
+
+
+def make_search_cell_case():
+    """(our search Cell, s0, s1_same, s1_up, raw alphas [n_edges, 8], cotangents of the two concats)."""
+    c = SEARCH_CELL
+    torch.manual_seed(c["seed"])
+    m = add_b200.cell_level_search.Cell(c["B"], c["prev_prev_C"], c["prev_C_down"], c["prev_C_same"], c["prev_C_up"], c["C_out"])
+    g = torch.Generator().manual_seed(c["seed"] + 100)
+    _randomize_running(m, g)
+    n, h, w = c["n"], c["h"], c["w"]
+    s0 = torch.randn(n, c["prev_prev_C"], h, w, generator=g)
+    s1_same = torch.randn(n, c["prev_C_same"], h, w, generator=g)
+    s1_up = torch.randn(n, c["prev_C_up"], h // 2, w // 2, generator=g)
+    n_edges = sum(2 + i for i in range(c["B"]))
+    alphas = torch.randn(n_edges, 8, generator=g) * 0.5
+    cots = [torch.randn(n, c["B"] * c["C_out"], h, w, generator=g) for _ in range(2)]
+    return m, s0, s1_same, s1_up, alphas, cots
+
+
+def make_search_aspp_case():
+    c = SEARCH_ASPP
+    torch.manual_seed(c["seed"])
+    m = add_b200.ASPP(c["C"], c["out"], c["pad"], c["dil"])
+    g = torch.Generator().manual_seed(c["seed"] + 100)
+    _randomize_running(m, g)
+    with torch.no_grad():
+        for k, v in m.state_dict().items():
+            if k.endswith(".1.weight"):
+                v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+            elif k.endswith(".1.bias"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+    x = torch.randn(*c["x"], generator=g)
+    cot = torch.randn(c["x"][0], c["out"], c["x"][2], c["x"][3], generator=g)
+    return m, x, cot
