@@ -176,20 +176,3 @@ def test_normalize_u8_hwc_is_bit_identical_to_the_reference_loader(shape):
     assert _lib.add_normalize_u8_hwc_to_nchw(src.data_ptr(), dst.data_ptr(), n, h, w, m0, m1, m2, s0, s1, s2, None) == 0
     torch.cuda.synchronize()
     assert np.array_equal(dst.cpu().numpy(), want)
-
-
-@pytest.mark.parametrize("c,dtype", [(40, torch.float32), (400, torch.bfloat16), (2048, torch.bfloat16), (3200, torch.bfloat16),
-                                     (3200, torch.float32), (1028, torch.float32)])
-def test_global_avgpool_wide_channels(c, dtype):
-    """add_global_avgpool_fwd (ASPP image pool, aspp_train.py:49-50; EDM, ADD.py:521) incl. inputs wider than one channel
-    group (BASELINE config 5: ASPP at Cin = 3200) against torch.mean in fp64; ReLU-on-load variant too."""
-    from add_b200.runtime import Builder, View, RELU_IN
-    g = torch.Generator().manual_seed(c)
-    x = torch.randn(2, 9, 13, c, generator=g).to(DEV).to(dtype)
-    b = Builder(torch.device(DEV), dtype)
-    for flags in (0, RELU_IN):
-        out = torch.empty((2, c), dtype=torch.float32, device=DEV)
-        b.gap(View(x), out, flags)
-        xr = x.double().clamp_min(0) if flags else x.double()
-        want = xr.mean(dim=(1, 2))
-        assert float((out.double() - want).abs().max()) < 1e-5

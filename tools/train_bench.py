@@ -121,4 +121,10 @@ if rank == 0:
                       "loss": float(loss), **result}))
 if world > 1:
     dist.barrier()
-    dist.destroy_process_group()
+torch.cuda.synchronize()
+# No orderly teardown: at 8 ranks (r4) the process hung AFTER the line above was printed — destroy_process_group / the
+# interpreter's destructors with the symmetric-memory rendezvous of PeerExchange still mapped — until the 600 s timeout
+# killed it.  The measurement is complete here; leave without running destructors.
+sys.stdout.flush()
+sys.stderr.flush()
+os._exit(0)
