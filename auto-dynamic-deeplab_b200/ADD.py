@@ -379,7 +379,15 @@ class ADD(AddModule):
 
     # ---- public API (reference signatures) --------------------------------------------------
     def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
-        """ADD.py:277-325: list of C logits tensors [N, num_classes, H, W] (fp32)."""
+        """ADD.py:277-325: list of C logits tensors [N, num_classes, H, W] (fp32).
+        In `.train()` (what train.py:227 calls) the dense-wired ADD runs the training-mode forward of `training.py`
+        (batch-statistics BatchNorm, autograd through libadd_b200's backward kernels); the sibling wirings have no
+        training forward and refuse."""
+        if self.training and self.DENSE:
+            rt.require_cuda(x)
+            from . import training as T
+            nc = self._num_classes
+            return [o[:, :nc] for o in T.add_forward(self, x)]      # channel nc.. of the padded classifier output is padding
         self._check_eval()
         rt.require_cuda(x)
         plan = self._get_plan(x, "forward")

@@ -71,8 +71,10 @@ def test_training_mode_is_refused_where_it_is_not_built():
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 40, 4, 4))
     net = util.make_net(util.NET_CASES["searched-dense-C2"]).train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):          # ADD.forward in .train() is training.add_forward: built, but no CPU path
         net(torch.zeros(1, 3, 33, 65))
+    with pytest.raises(NotImplementedError):   # the fused evaluate / gating paths are inference only
+        net.evaluate(torch.zeros(1, 3, 33, 65), torch.zeros(1, 33, 65, dtype=torch.int64))
     m2, x = util.make_op_case("dil_conv_3x3_c40")
     with pytest.raises(RuntimeError):          # it has a training forward, but no CPU path exists
         m2.train()(x)
