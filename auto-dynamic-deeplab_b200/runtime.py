@@ -141,9 +141,14 @@ class ConvWeights:
         """The conv restricted to output channels [c0, c0 + g) (cached)."""
         cache = self.__dict__.setdefault("_cout_slices", {})
         if (c0, g) not in cache:
-            cache[(c0, g)] = ConvWeights.from_folded(self.w_h[..., c0:c0 + g].contiguous(),
-                                                     None if self.bias_h is None else self.bias_h[c0:c0 + g].contiguous(),
-                                                     self.w.device)
+            cs = ConvWeights.from_folded(self.w_h[..., c0:c0 + g].contiguous(),
+                                         None if self.bias_h is None else self.bias_h[c0:c0 + g].contiguous(),
+                                         self.w.device)
+            if self.bias is not None:
+                # `bias` is a public attribute (callers may have replaced the device vector after construction): the
+                # slice reads the CURRENT device bias — a view, no copy kernel; c0 is a multiple of 256 -> 16-byte aligned
+                cs.bias = self.bias[c0:c0 + g]
+            cache[(c0, g)] = cs
         return cache[(c0, g)]
 
     def packed_tc(self) -> torch.Tensor:

@@ -117,3 +117,22 @@ def test_unknown_footprint_is_a_barrier():
     plan = _fake_plan([([(1, 0, 8)], [(2, 0, 8)]), ([], []), ([(3, 0, 8)], [(4, 0, 8)])])
     deps = plan.dependencies()
     assert deps[1] == [0] and 1 in deps[2]
+
+
+def test_cout_slice_reads_the_current_bias():
+    """Builder.conv runs convs with more than 256 output channels as 256-channel groups of `ConvWeights.cout_slice`.
+    `bias` is a public attribute that callers replace after construction (tests/test_gpu_tc.py does): a slice must read
+    the CURRENT bias vector, not the (possibly absent) master it was folded from, and must not copy it."""
+    from add_b200.runtime import ConvWeights
+    w = torch.randn(320, 8, 1, 1, generator=torch.Generator().manual_seed(4))
+    cw = ConvWeights(w)                          # no bias at construction
+    assert cw.bias is None and cw.cout_slice(256, 64).bias is None
+    cw2 = ConvWeights(w)
+    cw2.bias = torch.arange(320, dtype=torch.float32)
+    s0, s1 = cw2.cout_slice(0, 256), cw2.cout_slice(256, 64)
+    assert torch.equal(s0.bias, cw2.bias[:256]) and torch.equal(s1.bias, cw2.bias[256:])
+    assert s1.bias.data_ptr() == cw2.bias.data_ptr() + 256 * 4 and s1.bias.data_ptr() % 16 == 0      # a view, 16-byte aligned
+    assert torch.equal(s1.w_h, cw2.w_h[..., 256:]) and (s1.cin, s1.cout) == (8, 64)
+    bn = torch.nn.BatchNorm2d(320).eval()
+    cw3 = ConvWeights(w, bn, bias=torch.ones(320))
+    assert torch.allclose(cw3.cout_slice(256, 64).bias, cw3.bias_h[256:])
