@@ -294,6 +294,52 @@ def gen_gates():
     print("gates.npz", len(g), "entries", os.path.getsize(OUT / "gates.npz") / 1e6, "MB")
 
 
+def gen_three_gates():
+    """`dynamic_inference(confidence='edm')` through a network with THREE gated exits (ADD.py:394-438: the loop keeps going
+    while edm(y) > threshold; conv_aspp_iter counts the skipped exits; EDM's in-place ReLU is seen by every later cell),
+    the unmodified reference, image by image (its gate is batch-1).  Thresholds are derived from the reference's own
+    gate values: between the 2nd/3rd and the 4th/5th smallest first-gate values, never-exit, and the median of the
+    last-gate values (images leave at gate 3 or run to the end).  Stored for every (threshold, image): earlier_exit,
+    the confidence value returned, sum|y| and the argmax histogram; the logits themselves for images 0 and 3."""
+    g = {}
+    ours, edm, x, _ = util.make_three_gate_case()
+    c = util.THREE_GATES
+    ref = RefADD(c["network_arch"], c["C_index"], util.cell_arch(), 19, SimpleNamespace(F=c["F"], B=c["B"], sync_bn=False),
+                 c["low_level_layer"])
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ref.eval()
+    redm = RefEDM()
+    redm.load_state_dict(edm.state_dict(), strict=True)
+    redm.eval()
+
+    def run(i, thr):
+        with torch.no_grad():
+            y, ee, _, cv = ref.dynamic_inference(x[i:i + 1].clone(), threshold=thr, confidence='edm', edm=redm)
+        return y, int(ee), float(cv)
+    n = c["n"]
+    firsts = [run(i, 1e30)[2] for i in range(n)]            # exits at the first gate: its value
+    lasts = [run(i, -1e30)[2] for i in range(n)]            # never exits: the last gate's value
+    srt = sorted(firsts)
+    thresholds = [0.5 * (srt[1] + srt[2]), -1e30, float(np.median(lasts)), 0.5 * (srt[3] + srt[4])]
+    g["thresholds"] = np.array(thresholds, dtype=np.float64)
+    g["first_gate_values"] = np.array(firsts, dtype=np.float64)
+    g["last_gate_values"] = np.array(lasts, dtype=np.float64)
+    for t, thr in enumerate(thresholds):
+        for i in range(n):
+            y, ee, cv = run(i, thr)
+            k = f"t{t}/img{i}"
+            g[k + "/exit"] = np.int64(ee)
+            g[k + "/conf"] = np.float64(cv)
+            g[k + "/y_abs_sum"] = np.float64(y.double().abs().sum().item())
+            g[k + "/argmax_hist"] = np.bincount(y.argmax(1).flatten().numpy(), minlength=19).astype(np.int64)
+            if i in (0, 3):
+                g[k + "/y"] = f32(y)
+    g["wsum"] = np.float64(util.weight_checksum(ours.state_dict()))
+    np.savez_compressed(OUT / "three_gates.npz", **g)
+    print("three_gates.npz", len(g), "entries", os.path.getsize(OUT / "three_gates.npz") / 1e6, "MB",
+          "exit flags per threshold:", [[int(g[f"t{t}/img{i}/exit"]) for i in range(n)] for t in range(len(thresholds))])
+
+
 def gen_io_edges():
     """Loader / dump edges, the unmodified reference: CityscapesSegmentation.encode_segmap (cityscapes.py:85-91; the
     class is constructed with its file glob stubbed — the dataset is not here), full_image_eval_preprocess
@@ -465,6 +511,10 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--only-gates" in sys.argv:
         gen_gates()
+        gen_three_gates()
+        sys.exit(0)
+    if "--only-three-gates" in sys.argv:
+        gen_three_gates()
         sys.exit(0)
     if "--only-syncbn" in sys.argv:
         gen_syncbn()
@@ -478,6 +528,7 @@ if __name__ == "__main__":
     gen_train_ops()
     gen_mixed_op()
     gen_gates()
+    gen_three_gates()
     gen_io_edges()
     gen_train_step()
     gen_train_ops_grad()

@@ -223,3 +223,30 @@ def test_train_step_oracle_matches_reference():
         tol = 1e-4 if step == 0 else 5e-2
         for k, a_ in zip(TRAIN[f"step{step}/state_names"], TRAIN[f"step{step}/state_abs_sum"]):
             assert float(sd[str(k)].detach().double().abs().sum()) == pytest.approx(float(a_), rel=tol, abs=1e-6), (step, k)
+
+
+G3 = np.load(util.ROOT / "tests/golden/three_gates.npz")
+
+
+@pytest.mark.parametrize("t", range(4))
+def test_three_gated_exits_match_reference(t):
+    """ADD.py:394-438 with THREE gated exits (C_index = [3, 6, 9]): for every image and threshold of the fixture the oracle
+    takes the reference's decision, returns its confidence value (the value of the gate where the image left, or of the
+    last gate) and its logits.  Covers exits at the 1st, 2nd and 3rd gate and the run to the final head."""
+    net, edm, x, _ = util.make_three_gate_case()
+    assert util.weight_checksum(net.state_dict()) == pytest.approx(float(G3["wsum"]), rel=1e-12)
+    c = util.THREE_GATES
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    edm_sd = {k: v.detach() for k, v in edm.state_dict().items()}
+    arch = orc.Arch(c["network_arch"], c["C_index"], util.cell_arch(), 19, c["F"], c["B"], c["low_level_layer"])
+    thr = float(G3["thresholds"][t])
+    for i in range(c["n"]):
+        with torch.no_grad():
+            y, ee, cv = orc.add_dynamic_inference(sd, arch, x[i:i + 1], thr, 'edm', edm_sd)
+        k = f"t{t}/img{i}"
+        assert ee == int(G3[k + "/exit"]), (t, i)
+        assert float(cv) == pytest.approx(float(G3[k + "/conf"]), rel=1e-4, abs=1e-6), (t, i)
+        assert float(y.double().abs().sum()) == pytest.approx(float(G3[k + "/y_abs_sum"]), rel=1e-4), (t, i)
+        if k + "/y" in G3.files:
+            assert util.rel_err(y, torch.from_numpy(G3[k + "/y"])) < TOL, (t, i)
+            assert np.array_equal(np.bincount(y.argmax(1).flatten().numpy(), minlength=19), G3[k + "/argmax_hist"]), (t, i)

@@ -14,40 +14,39 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+G3 = np.load(util.ROOT / "tests/golden/three_gates.npz")
+
+
 def test_three_gated_exits_plan_cache_lineage():
-    """A network with THREE EDM-gated exits and a batch of 6: with >= 3 gates several compacted segments share
-    (exit index, image count) and differ only in which earlier segment they continue — the recorded plans are keyed by
-    that lineage.  Calls with different exit patterns, back to back on the same runner, must each equal the batch-1
-    control flow (ADD.py:394-438) per image, and the oracle."""
-    na, ci = [1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2], [3, 6, 9]       # every gated exit at level 2: 400-channel features (EDM, ADD.py:508)
-    torch.manual_seed(1)
-    net = add_b200.ADD(na, ci, add_b200.AUTODEEPLAB_CELL.copy(), 19, add_b200.Args(20, 5), 0)
-    net = util._randomized(net, 21).to(DEV)
-    edm = util.make_edm().to(DEV)
-    n = 6
-    x, gt = util.make_input(n, 33, 65, seed=77)
+    """A network with THREE EDM-gated exits and a batch of 6 (fixture tests/golden/three_gates.npz, made by the unmodified
+    reference image by image): images leave at the 1st, 2nd and 3rd gate or run to the end.  With >= 3 gates several
+    compacted segments share (exit index, image count) and differ only in which earlier segment they continue — the recorded
+    plans are keyed by that lineage.  Calls with different exit patterns, back to back on the same runner, must each equal
+    (a) the reference's decision, confidence value and logits per image and (b) the batch-1 control flow of this library."""
+    net, edm, x, gt = util.make_three_gate_case()
+    assert util.weight_checksum(net.state_dict()) == pytest.approx(float(G3["wsum"]), rel=1e-12)
+    net, edm = net.to(DEV), edm.to(DEV)
+    n = util.THREE_GATES["n"]
     xd, gtd = x.to(DEV), gt.to(DEV)
-    # gate values of every image at every gate: run with thresholds that never exit, image by image, and record the trail
-    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
-    edm_sd = {k: v.detach().cpu() for k, v in edm.state_dict().items()}
-    arch = orc.Arch(na, ci, util.cell_arch(), 19, 20, 5, 0)
-    firsts = []
-    for i in range(n):
-        _, _, _, cv = net.dynamic_inference(xd[i:i + 1], threshold=1e30, confidence='edm', edm=edm)   # exits at gate 1
-        firsts.append(float(cv))
-    srt = sorted(firsts)
-    lasts = []
-    for i in range(n):
-        _, _, _, cv = net.dynamic_inference(xd[i:i + 1], threshold=-1e30, confidence='edm', edm=edm)  # never exits: last gate's value
-        lasts.append(float(cv))
-    mid_last = float(np.median(lasts))
-    patterns_seen = set()
-    for thr in (0.5 * (srt[1] + srt[2]), -1e30, mid_last, 0.5 * (srt[3] + srt[4]), mid_last, 0.5 * (srt[1] + srt[2])):
+    thr_index = {float(v): t for t, v in enumerate(G3["thresholds"])}
+    for thr in util.three_gate_thresholds(G3):
+        t = thr_index[thr]
         ref = []
         for i in range(n):                       # clone at once: the logits alias plan buffers the next call overwrites
             y1, e1, _, c1 = net.dynamic_inference(xd[i:i + 1], threshold=thr, confidence='edm', edm=edm)
             ref.append((y1.clone(), e1, float(c1)))
         ys, flags, confs = net.dynamic_inference_batch(xd, thr, 'edm', edm)
+        # (a) against the reference
+        assert flags == [int(G3[f"t{t}/img{i}/exit"]) for i in range(n)], (t, flags)
+        for i in range(n):
+            k = f"t{t}/img{i}"
+            assert float(confs[i]) == pytest.approx(float(G3[k + "/conf"]), rel=1e-3, abs=1e-4), (t, i)     # as test_gpu_net.py
+            assert float(ys[i].double().abs().sum()) == pytest.approx(float(G3[k + "/y_abs_sum"]), rel=1e-3), (t, i)
+            if k + "/y" in G3.files:
+                want = torch.from_numpy(G3[k + "/y"])
+                assert util.rel_err(ys[i], want) < 1e-3, (t, i)
+                assert float((ys[i].cpu().argmax(1) == want.argmax(1)).float().mean()) >= 0.999, (t, i)
+        # (b) against this library's own batch-1 control flow
         assert flags == [r[1] for r in ref]
         for i in range(n):
             assert util.rel_err(ys[i], ref[i][0]) < 1e-6, (thr, i)
@@ -57,17 +56,11 @@ def test_three_gated_exits_plan_cache_lineage():
         for i in range(n):
             want = orc.generate_matrix(gt[i].numpy(), ref[i][0].argmax(1).cpu().numpy())
             assert np.array_equal(cms[i].cpu().numpy(), want), (thr, i)
-        patterns_seen.add(tuple(flags))
-    # the exit flag is binary (an image that passes gate 1 usually leaves at gate 2 or 3), so the diversity of the runs is
-    # read off the plans that were recorded: segments / heads at several gates and image counts
+    # the diversity of the runs is read off the plans that were recorded: trunk segments at all four positions, early-exit
+    # heads at several gates and image counts
     runner = next(v for k, v in net._plans.items() if k[0] == "edm" and k[5] == "logits" and k[1][0] == n)
     assert len({k[0] for k in runner.segments}) >= 3 and len(runner.segments) >= 4, sorted(k[:2] for k in runner.segments)
     assert len({k[0] for k in runner.heads}) >= 2, sorted(k[:2] for k in runner.heads)
-    # one image against the oracle (reference control flow with three gates)
-    with torch.no_grad():
-        y_ref, ee_ref, cv_ref = orc.add_dynamic_inference(sd, arch, x[0:1], 0.5 * (srt[2] + srt[3]), 'edm', edm_sd)
-    y, ee, _, cv = net.dynamic_inference(xd[0:1], threshold=0.5 * (srt[2] + srt[3]), confidence='edm', edm=edm)
-    assert ee == ee_ref and util.rel_err(y, y_ref) < 1e-3
 
 
 @pytest.mark.parametrize("c,dtype", [(40, torch.float32), (400, torch.bfloat16), (2048, torch.bfloat16), (3200, torch.bfloat16),

@@ -338,3 +338,24 @@ def make_search_aspp_case():
     x = torch.randn(*c["x"], generator=g)
     cot = torch.randn(c["x"][0], c["out"], c["x"][2], c["x"][3], generator=g)
     return m, x, cot
+
+
+# ---- three EDM-gated exits (ADD.py:394-438 with len(C_index) = 3): the case of tests/golden/three_gates.npz -----------
+THREE_GATES = dict(network_arch=[1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2], C_index=[3, 6, 9], F=20, B=5, low_level_layer=0,
+                   n=6, h=33, w=65, input_seed=77)     # every gated exit at level 2: 400-channel features (EDM, ADD.py:508)
+
+
+def make_three_gate_case():
+    """(our ADD with BN-randomised weights, EDM, x [6,3,33,65], gt) — deterministic (CPU RNG, fixed seeds)."""
+    c = THREE_GATES
+    torch.manual_seed(1)
+    net = add_b200.ADD(c["network_arch"], c["C_index"], cell_arch(), 19, add_b200.Args(c["F"], c["B"]), c["low_level_layer"])
+    net = _randomized(net, 21)
+    x, gt = make_input(c["n"], c["h"], c["w"], seed=c["input_seed"])
+    return net, make_edm(), x, gt
+
+
+def three_gate_thresholds(G):
+    """The thresholds the fixture was made with, in the order the tests walk them (repeats on purpose: plans are reused)."""
+    t = [float(v) for v in G["thresholds"]]
+    return [t[0], t[1], t[2], t[3], t[2], t[0]]
