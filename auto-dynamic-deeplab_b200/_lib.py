@@ -104,6 +104,7 @@ _SIGS = {
     "add_widen_labels_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "add_confusion_workspace_bytes": (c_int64, [c_int64, c_int]),
     "add_confusion_matrix": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "add_confusion_set_impl": (c_int, [c_int]),
     "add_confidence_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "add_confidence_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
 }

@@ -377,6 +377,115 @@ confusion_finalize_kernel(const unsigned int* __restrict__ part, int B, int bins
   }
 }
 
+// ---- Evaluator._generate_matrix, variant B (opt-in: add_confusion_set_impl(1)) ---------------------------------
+// Thread-private histograms.  Variant A above privatises per WARP and resolves intra-warp collisions with match.any
+// (ncu r4i: 114 us for 268 MB = DRAM 29 %, bound by the MATCH + leader-add chain per pixel and 2.5 M bank conflicts;
+// its one-block finalize walks up to 1184 partial rows one dependent L2 round trip at a time and takes as long again).
+// Here every THREAD owns a private histogram in shared memory, so an update is a plain load / add / store that no other
+// thread can touch — no atomics, no match.any, no election.  Layout: word [bin pair p][thread t] holds bins 2p and 2p+1
+// as two 16-bit halves -> the 32 lanes of a warp hit 32 different banks whatever their bins (bank = t % 32), and 256
+// threads x <= 184 pairs x 4 B <= 184 KB fit one CTA per SM.  16-bit counters bound the pixels per thread: the grid is
+// sized so that no thread sees more than CF_MAX_PER_THREAD.  The block merge reads the rows rotated by the pair index
+// (conflict-free); the per-block partials are summed by a second kernel in fixed order with all loads of a thread
+// independent.  Integer arithmetic throughout: bit-exact and deterministic, like variant A.
+// Written after round 2's GPU budget was spent: OFF by default until tests/test_zz_gpu_late.py has pinned it bit-exact
+// against variant A on a B200 (bench.py reports both, `candidates.confusion_matrix_private`).
+constexpr int CF_THREADS = 256;
+constexpr int CF_MAX_PAIRS = (MAX_BINS + 1) / 2;
+constexpr long long CF_MAX_PER_THREAD = 60000;      // < 65536: a 16-bit private counter cannot wrap
+constexpr int CF_UNR = 8;
+
+__global__ void __launch_bounds__(CF_THREADS, 1)
+confusion_private_kernel(const long long* __restrict__ gt, const long long* __restrict__ pred, long long n_pix,
+                         int nc, unsigned int* __restrict__ part, int vec_ok) {
+  extern __shared__ unsigned int cf_words[];          // [pairs][CF_THREADS]
+  const int tid = threadIdx.x;
+  const int bins = nc * nc, pairs = (bins + 1) >> 1;
+  for (int p = 0; p < pairs; ++p) cf_words[p * CF_THREADS + tid] = 0u;   // own column only: no barrier needed before use
+  const long long per = ((n_pix + gridDim.x - 1) / gridDim.x + 1) & ~1ll;   // even -> 16 B aligned pairs
+  const long long start = blockIdx.x * per, end = (start + per < n_pix) ? start + per : n_pix;
+  // Two pixels per thread and step (one 16-byte load of gt and one of pred when both bases are 16-byte aligned, else
+  // 8-byte loads: a per-image slice of an odd-sized map starts 8 bytes off); CF_UNR steps' loads are issued before the
+  // first update, so a warp keeps 8 KB in flight.
+  for (long long base = start + (long long)tid * 2; base < end; base += (long long)CF_THREADS * 2 * CF_UNR) {
+    long long g[CF_UNR][2], q[CF_UNR][2];
+#pragma unroll
+    for (int u = 0; u < CF_UNR; ++u) {
+      const long long pix = base + (long long)u * CF_THREADS * 2;
+      g[u][0] = g[u][1] = -1; q[u][0] = q[u][1] = 0;
+      if (vec_ok && pix + 1 < end) {
+        const longlong2 gv = __ldcs(reinterpret_cast<const longlong2*>(gt + pix));
+        const longlong2 qv = __ldcs(reinterpret_cast<const longlong2*>(pred + pix));
+        g[u][0] = gv.x; g[u][1] = gv.y; q[u][0] = qv.x; q[u][1] = qv.y;
+      } else {
+        if (pix < end) { g[u][0] = __ldcs(gt + pix); q[u][0] = __ldcs(pred + pix); }
+        if (pix + 1 < end) { g[u][1] = __ldcs(gt + pix + 1); q[u][1] = __ldcs(pred + pix + 1); }
+      }
+    }
+    // labels / predictions outside [0,nc) have no cell in the matrix (metrics.py:35 masks the labels; a prediction out of
+    // range is dropped, never aliased into a valid bin): one unsigned compare each
+#pragma unroll
+    for (int u = 0; u < CF_UNR; ++u) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const unsigned long long gu = (unsigned long long)g[u][e], qu = (unsigned long long)q[u][e];
+        if (gu < (unsigned long long)nc && qu < (unsigned long long)nc) {
+          const int bin = (int)gu * nc + (int)qu;
+          unsigned int* w = cf_words + (bin >> 1) * CF_THREADS + tid;
+          *w += 1u << ((bin & 1) << 4);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // merge: thread p sums pair p over the 256 private columns, starting at column p (bank = (p + j) % 32: no conflicts),
+  // low and high halves separately (<= 256 x 65535 each: fits 32 bits)
+  for (int p = tid; p < pairs; p += CF_THREADS) {
+    unsigned int lo = 0, hi = 0;
+    for (int j = 0; j < CF_THREADS; ++j) {
+      const unsigned int w = cf_words[p * CF_THREADS + ((j + p) & (CF_THREADS - 1))];
+      lo += w & 0xffffu; hi += w >> 16;
+    }
+    part[(size_t)blockIdx.x * bins + 2 * p] = lo;
+    if (2 * p + 1 < bins) part[(size_t)blockIdx.x * bins + 2 * p + 1] = hi;
+  }
+}
+
+// Sum of the B per-block rows, int64 out.  One block of 16 warps: warp w takes rows w, w + 16, ...; up to 16 loads of a
+// thread are independent of each other (variant A's finalize issues them one dependent round trip at a time).
+constexpr int CFF_WARPS = 16;
+__global__ void __launch_bounds__(CFF_WARPS * 32)
+confusion_finalize_wide_kernel(const unsigned int* __restrict__ part, int B, int bins, long long* __restrict__ out) {
+  __shared__ unsigned long long red[CFF_WARPS][MAX_BINS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < bins; i0 += 128) {
+    unsigned long long s[4] = {0, 0, 0, 0};
+    for (int b = warp; b < B; b += 4 * CFF_WARPS) {
+      unsigned int v[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int br = b + r * CFF_WARPS;
+        const unsigned int* row = part + (size_t)(br < B ? br : b) * bins;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + lane; v[r][u] = (br < B && i < bins) ? __ldg(row + i) : 0u; }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] += v[r][u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + lane; if (i < bins) red[warp][i] = s[u]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += CFF_WARPS * 32) {
+    unsigned long long s = 0;
+#pragma unroll
+    for (int wv = 0; wv < CFF_WARPS; ++wv) s += red[wv][i];
+    out[i] = (long long)s;
+  }
+}
+
 // ---- confidence scalars on NCHW fp32 logits -----------------------------------------------------
 __global__ void __launch_bounds__(256)
 confidence_kernel(const float* __restrict__ logits, int n_img, int c, long long HW, float thr,
@@ -427,6 +536,16 @@ inline int confusion_blocks(long long n_pix) {
   long long b = (n_pix + 4095) / 4096;
   return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
 }
+// variant B: one CTA per SM (184 KB of private histograms each); more only when a thread would otherwise see more pixels
+// than its 16-bit counters can hold
+inline int confusion_private_blocks(long long n_pix) {
+  long long b = (n_pix + 4095) / 4096;
+  if (b > 148) b = 148;
+  const long long need = (n_pix + CF_THREADS * CF_MAX_PER_THREAD - 1) / (CF_THREADS * CF_MAX_PER_THREAD);
+  if (b < need) b = need;
+  return (int)(b < 1 ? 1 : b);
+}
+int g_confusion_impl = 0;     // 0 = variant A (per-warp, match.any; the measured default), 1 = variant B (thread-private)
 inline int confidence_blocks(long long total) {
   long long b = (total + 1023) / 1024;
   return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
@@ -502,7 +621,15 @@ static int upsample_argmax_impl(const add_tensor_t* x, int H, int W, const int64
 
 extern "C" int64_t add_confusion_workspace_bytes(int64_t n_pixels, int num_class) {
   if (n_pixels < 0 || num_class <= 0) return ADD_ERR_BAD_ARG;
-  return (int64_t)confusion_blocks(n_pixels) * num_class * num_class * sizeof(unsigned int);
+  const int a = confusion_blocks(n_pixels), b = confusion_private_blocks(n_pixels);      // enough for either variant
+  return (int64_t)(a > b ? a : b) * num_class * num_class * sizeof(unsigned int);
+}
+
+/* 0 = per-warp privatised histogram with match.any (default), 1 = thread-private histograms (opt-in, see head.cu). */
+extern "C" int add_confusion_set_impl(int impl) {
+  if (impl != 0 && impl != 1) return ADD_ERR_BAD_ARG;
+  g_confusion_impl = impl;
+  return ADD_OK;
 }
 
 extern "C" int add_confusion_matrix(const int64_t* gt, const int64_t* pred, int64_t n_pixels, int num_class,
@@ -513,8 +640,22 @@ extern "C" int add_confusion_matrix(const int64_t* gt, const int64_t* pred, int6
   ADD_CHECK_SUP(((uintptr_t)gt % 8 == 0) && ((uintptr_t)pred % 8 == 0));
   const int vec_ok = (((uintptr_t)gt % 16 == 0) && ((uintptr_t)pred % 16 == 0)) ? 1 : 0;
   if (workspace_bytes < add_confusion_workspace_bytes(n_pixels, num_class)) return ADD_ERR_WORKSPACE;
-  int B = confusion_blocks(n_pixels);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (g_confusion_impl == 1) {
+    const int Bp = confusion_private_blocks(n_pixels);
+    const size_t smem = (size_t)((num_class * num_class + 1) / 2) * CF_THREADS * sizeof(unsigned int);
+    static PerDeviceOnce once;
+    once_per_device(once, [] {
+      cudaFuncSetAttribute(confusion_private_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           CF_MAX_PAIRS * CF_THREADS * (int)sizeof(unsigned int));
+    });
+    confusion_private_kernel<<<Bp, CF_THREADS, smem, s>>>((const long long*)gt, (const long long*)pred, n_pixels, num_class,
+                                                          (unsigned int*)workspace, vec_ok);
+    confusion_finalize_wide_kernel<<<1, CFF_WARPS * 32, 0, s>>>((const unsigned int*)workspace, Bp, num_class * num_class,
+                                                                (long long*)cm_out);
+    ADD_RETURN_LAUNCH();
+  }
+  int B = confusion_blocks(n_pixels);
   confusion_kernel<<<B, HD_THREADS, 0, s>>>((const long long*)gt, (const long long*)pred, n_pixels, num_class,
                                             (unsigned int*)workspace, vec_ok);
   confusion_finalize_kernel<<<1, HD_THREADS, 0, s>>>((const unsigned int*)workspace, B, num_class * num_class,

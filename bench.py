@@ -63,6 +63,8 @@ def parse():
                          "region — as a deployment would use, so exit counts (and step times) differ per rank")
     ap.add_argument("--no-fp32-feed", action="store_true",
                     help="skip the second e2e measurement that feeds the reference loader's fp32 NCHW images + int64 labels")
+    ap.add_argument("--no-candidates", action="store_true",
+                    help="skip the child-process measurement of the opt-in candidate kernels (`candidates` in the JSON line)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0,
                     help="--impl reference: wall-clock budget of the whole run; the step shrinks to a bounded sample of the batch to fit")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel launch table (JSON) here")
@@ -368,6 +370,36 @@ def main_torch_cuda(a):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def run_candidates(timeout_s: float = 150.0) -> dict:
+    """Evaluator histogram kernels timed alone at the bench shape (8 x 1024 x 2048 int64 label / prediction pairs, 268 MB,
+    three rotating sets = larger than L2): the default (per-warp, match.any) and the opt-in thread-private variant, in a
+    child process.  Returns what the child measured, or why it could not."""
+    import subprocess
+    import tempfile
+    out = Path(tempfile.gettempdir()) / f"add_b200_candidates_{os.getpid()}.json"
+    note = ("opt-in kernels (add_confusion_set_impl(1)); not used by any default path, by `value` or by `e2e`; measured in a "
+            "child process after the timed region")
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "tools" / "head_bench.py"), "20", "--variants", "--json", str(out)],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout_s, cwd=str(ROOT))
+        res = json.loads(out.read_text()) if out.exists() else {}
+        res.update({"rc": r.returncode, "note": note})
+        if r.returncode != 0:
+            res["stderr_tail"] = r.stderr[-600:]
+        return res
+    except subprocess.TimeoutExpired:
+        res = json.loads(out.read_text()) if out.exists() else {}
+        res.update({"rc": None, "error": f"child exceeded {timeout_s:.0f} s", "note": note})
+        return res
+    except Exception as e:          # the candidates must never take the bench line down
+        return {"rc": None, "error": repr(e)[:300], "note": note}
+    finally:
+        try:
+            out.unlink()
+        except OSError:
+            pass
+
+
 def main_b200(a):
     # stdout carries exactly ONE JSON line: anything libraries print there meanwhile (NCCL's "NCCL version ..." banner
     # under torchrun) is diverted to stderr by pointing fd 1 at fd 2 until the line is printed
@@ -629,6 +661,13 @@ def main_b200(a):
         cpu = None
         if world == 1 and not a.no_cpu_baseline:
             cpu = run_cpu_sample(a, a.cpu_images, [True, False])   # same 50 % early-exit mix as the GPU arm
+        # ---- candidates: kernels written after the round's GPU budget was spent and therefore NOT on any default path.
+        # They are measured here — after every number of this line has been taken — in a SEPARATE process (its own CUDA
+        # context, a hard timeout: nothing it does can touch the main measurement), next to the default kernel they
+        # would replace, with a bit-identity check between the two.  tools/head_bench.py --variants.
+        candidates = None
+        if world == 1 and not a.no_candidates:
+            candidates = run_candidates()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": ms_res / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": a.precision, "data": "synthetic", "config": dict(workload_name(a), parallelism=f"batch-shard dp{world}",
@@ -644,7 +683,7 @@ def main_b200(a):
                           "ms_per_step": rank_ms, "early_exits_of_batch": rank_exits,
                           "slowest_rank_penalty": max(rank_ms) / (sum(rank_ms) / len(rank_ms))},
                 "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
-                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "candidates": candidates}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

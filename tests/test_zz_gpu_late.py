@@ -78,3 +78,59 @@ def test_global_avgpool_wide_channels(c, dtype):
         xr = x.double().clamp_min(0) if flags else x.double()
         want = xr.mean(dim=(1, 2))
         assert float((out.double() - want).abs().max()) < 1e-5
+
+
+# ---- Evaluator histogram, variant B (thread-private counters; opt-in) against variant A and the numpy oracle --------------
+@pytest.fixture
+def _confusion_variant_b():
+    from add_b200._lib import lib as _lib
+    assert _lib.add_confusion_set_impl(1) == 0
+    try:
+        yield _lib
+    finally:
+        assert _lib.add_confusion_set_impl(0) == 0
+
+
+def test_confusion_variant_b_matches_reference_goldens(_confusion_variant_b):
+    """The reference's own golden matrices (tests/golden/ops.npz, every Evaluator case incl. the edge cases)."""
+    OPS = np.load(util.ROOT / "tests/golden/ops.npz")
+    for cname, (gt, pred) in sorted(util.make_evaluator_cases().items()):
+        cm = add_b200.Evaluator(19)._generate_matrix(gt.to(DEV), pred.to(DEV))
+        assert np.array_equal(cm.cpu().numpy(), OPS[f"evaluator/{cname}/cm"]), cname
+
+
+def test_confusion_variant_b_is_bit_identical_to_variant_a():
+    """Same inputs through both histogram kernels: empty, tiny, odd, unaligned-base (8 bytes off), out-of-range labels and
+    predictions (negative and too large), 1025 x 2049 per-image slices, and the full 8 x 1024 x 2048 batch."""
+    from add_b200._lib import lib as _lib
+    g = torch.Generator().manual_seed(79)
+    cases = []
+    for n in (0, 1, 2, 3, 63, 64, 65, 511, 512, 513, 4095, 4097, 100001, 1025 * 2049):
+        gt = torch.randint(-2, 21, (n,), generator=g)
+        gt[torch.rand(n, generator=g) < 0.1] = 255
+        pred = torch.randint(-1, 20, (n,), generator=g)
+        cases.append((f"n={n}", gt, pred))
+    big_gt = torch.randint(0, 19, (8, 1024, 2048), generator=g)
+    big_gt[torch.rand(8, 1024, 2048, generator=g) < 0.1] = 255
+    cases.append(("8x1024x2048", big_gt, torch.randint(0, 19, (8, 1024, 2048), generator=g)))
+    skew = torch.zeros(3_000_000, dtype=torch.int64)                    # one bin takes everything: the 16-bit counters' worst case
+    cases.append(("one bin", skew, skew.clone()))
+    for name, gt, pred in cases:
+        gtd, prd = gt.to(DEV), pred.to(DEV)
+        outs = []
+        for impl in (0, 1):
+            assert _lib.add_confusion_set_impl(impl) == 0
+            try:
+                outs.append(add_b200.Evaluator(19)._generate_matrix(gtd, prd).cpu().numpy())
+                if gt.numel() > 1 and gt.dim() == 1:                       # base pointers 8 bytes off a 16-byte boundary
+                    outs.append(add_b200.Evaluator(19)._generate_matrix(gtd[1:], prd[1:]).cpu().numpy())
+            finally:
+                _lib.add_confusion_set_impl(0)
+        half = len(outs) // 2
+        for a, b in zip(outs[:half], outs[half:]):
+            assert np.array_equal(a, b), name
+        # metrics.py:34-39 with the library's stated handling of predictions that have no cell (dropped, never aliased)
+        gn, pn = gt.numpy().reshape(-1), pred.numpy().reshape(-1)
+        keep = (gn >= 0) & (gn < 19) & (pn >= 0) & (pn < 19)
+        want = np.bincount(19 * gn[keep] + pn[keep], minlength=361).reshape(19, 19)
+        assert np.array_equal(outs[0], want), name

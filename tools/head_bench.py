@@ -3,7 +3,8 @@
   * add_confusion_matrix            Evaluator._generate_matrix on int64 gt / pred  [8,1024,2048]   (16 B / pixel)
   * add_upsample_argmax_u8_fwd      x8 upsample + argmax + confusion matrix        4 images, logits [4,128,256,19] fp32
 Prints achieved algorithmic GB/s against MEASURED_PEAKS.json.  Also the target of `ncu --set full -k regex:confusion_kernel|upsample_argmax`.
-Usage: python tools/head_bench.py [reps]"""
+Usage: python tools/head_bench.py [reps] [--json out.json] [--variants]
+--variants: time add_confusion_matrix with both histogram kernels (add_confusion_set_impl 0 / 1) and check them bit-identical."""
 import ctypes
 import json
 import sys
@@ -16,7 +17,12 @@ sys.path.insert(0, str(ROOT))
 import add_b200  # noqa: E402
 from add_b200.runtime import Builder, View  # noqa: E402
 
-reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+_args = [a for a in sys.argv[1:] if not a.startswith("--")]
+_json_out = sys.argv[sys.argv.index("--json") + 1] if "--json" in sys.argv else None
+if _json_out in _args:
+    _args.remove(_json_out)
+reps = int(_args[0]) if _args else 20
+RESULT = {}
 dev = torch.device("cuda:0")
 peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
 g = torch.Generator().manual_seed(1)
@@ -42,9 +48,25 @@ def timed(fn, n):
     return e0.elapsed_time(e1) / n
 
 
-ms = timed(lambda i: ev._generate_matrix(*sets[i % 3]), reps)
 by = N * H * W * 16
-print(f"confusion_matrix   {N}x{H}x{W} int64: {ms * 1e3:8.1f} us  {by / ms / 1e6:8.1f} GB/s  = {by / ms / 1e6 / peak:.3f} of measured HBM peak ({by / 1e6:.0f} MB algorithmic)")
+from add_b200._lib import lib as _lib  # noqa: E402
+_variants = [(0, "per-warp match.any (default)")] + ([(1, "thread-private counters (opt-in)")] if "--variants" in sys.argv else [])
+_cms = []
+for impl, label in _variants:
+    assert _lib.add_confusion_set_impl(impl) == 0
+    try:
+        ms = timed(lambda i: ev._generate_matrix(*sets[i % 3]), reps)
+        _cms.append(ev._generate_matrix(*sets[0]).cpu())
+    finally:
+        _lib.add_confusion_set_impl(0)
+    print(f"confusion_matrix   {N}x{H}x{W} int64, {label}: {ms * 1e3:8.1f} us  {by / ms / 1e6:8.1f} GB/s  = {by / ms / 1e6 / peak:.3f} of measured HBM peak ({by / 1e6:.0f} MB algorithmic)")
+    RESULT[f"confusion_matrix_impl{impl}"] = {"variant": label, "us": ms * 1e3, "gbs": by / ms / 1e6, "frac_of_hbm_peak": by / ms / 1e6 / peak,
+                                              "algorithmic_bytes": by, "default": impl == 0}
+if len(_cms) == 2:
+    RESULT["confusion_variants_bit_identical"] = bool(torch.equal(_cms[0], _cms[1]))
+    print("variants bit-identical:", RESULT["confusion_variants_bit_identical"])
+if _json_out:
+    Path(_json_out).write_text(json.dumps(RESULT))          # written early: the fused-head part below may be skipped by the caller's timeout
 
 # fused head: low-res logits with spatially smooth classes (like a network's output) and a noisy variant (worst case)
 n2 = 4
@@ -70,6 +92,7 @@ for name, smooth in (("smooth logits", True), ("iid-random logits", False)):
     ms = timed(lambda i: plans[i % 3].run_eager(), reps)
     by = n2 * 128 * 256 * 19 * 4 + n2 * H * W
     print(f"upsample_argmax_cm {n2} images ({name}, uint8 labels): {ms * 1e3:8.1f} us  {by / ms / 1e6:8.1f} GB/s  = {by / ms / 1e6 / peak:.3f} of measured HBM peak ({by / 1e6:.1f} MB algorithmic)")
+    RESULT[f"upsample_argmax_cm_{'smooth' if smooth else 'iid'}"] = {"us": ms * 1e3, "gbs": by / ms / 1e6, "algorithmic_bytes": by, "images": n2}
     # bit-exact against materialised logits -> argmax -> Evaluator
     v, gt8, cm = bufs[0]
     out = torch.empty(n2, 19, H, W, device=dev)
@@ -77,4 +100,6 @@ for name, smooth in (("smooth logits", True), ("iid-random logits", False)):
     for j in range(n2):
         want = add_b200.Evaluator(19)._generate_matrix(gt8[j].long(), out[j:j + 1].argmax(1)[0])
         assert torch.equal(want, cm[j]), (name, j)
+if _json_out:
+    Path(_json_out).write_text(json.dumps(RESULT))
 print("ok")
