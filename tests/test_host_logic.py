@@ -136,3 +136,26 @@ def test_cout_slice_reads_the_current_bias():
     bn = torch.nn.BatchNorm2d(320).eval()
     cw3 = ConvWeights(w, bn, bias=torch.ones(320))
     assert torch.allclose(cw3.cout_slice(256, 64).bias, cw3.bias_h[256:])
+
+
+def test_product_never_imports_the_oracle_or_the_reference():
+    """The oracle (oracle/) and the staged reference (baseline/_ref) are CHECKERS: only tests/, smoke() and bench.py's CPU
+    legs may load them.  A fresh interpreter that imports the whole product (every submodule of add_b200) must end up with
+    neither in sys.modules, and no product source file may name them in an import statement."""
+    import subprocess
+    import sys
+    mods = sorted(p.stem for p in (util.ROOT / "auto-dynamic-deeplab_b200").glob("*.py") if p.stem not in ("__init__", "_build"))
+    code = "\n".join([
+        "import sys, importlib",
+        f"sys.path.insert(0, {str(util.ROOT)!r})",
+        "import add_b200",
+        f"for m in {mods!r}: importlib.import_module('add_b200.' + m)",
+        "bad = [k for k in sys.modules if k == 'oracle' or k.startswith(('oracle.', 'modeling', 'baseline'))]",
+        "print('BAD' if bad else 'CLEAN', bad)"])
+    out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=str(util.ROOT))
+    assert out.returncode == 0, out.stderr[-800:]
+    assert out.stdout.strip().startswith("CLEAN"), out.stdout
+    import re
+    for src in sorted((util.ROOT / "auto-dynamic-deeplab_b200").glob("*.py")):
+        for ln in src.read_text().splitlines():
+            assert not re.match(r"\s*(from|import)\s+(oracle|baseline|modeling)\b", ln), (src.name, ln)
