@@ -1,0 +1,144 @@
+"""CPU: the host logic above the launch layer, checked NUMERICALLY without a GPU (tests/sim_backend.py replaces the op
+methods of `Builder` by plain-PyTorch closures for the duration of a test; see its header for what that does and does not
+cover).  Plans are recorded and replayed exactly as on the GPU — channel-slice concat, accumulate-into-slice node sums,
+ReLU-on-store bookkeeping, shared resized features, early-exit segments with host-filled gather indices, result scatter —
+and the results are held to the fixtures produced by the unmodified reference (tests/golden/*.npz)."""
+import numpy as np
+import pytest
+import torch
+
+import util
+import add_b200
+import sim_backend
+from util import orc
+
+NETS = np.load(util.ROOT / "tests/golden/nets.npz")
+SIBS = np.load(util.ROOT / "tests/golden/siblings.npz")
+G3 = np.load(util.ROOT / "tests/golden/three_gates.npz")
+TOL = 2e-4          # same ATen arithmetic as the reference up to BN folding and summation order
+
+
+@pytest.fixture(autouse=True)
+def _sim(monkeypatch):
+    sim_backend.install(monkeypatch)
+    yield
+
+
+def _agree(a, b):
+    return float((a.argmax(1) == b.argmax(1)).float().mean())
+
+
+@pytest.mark.parametrize("cname", sorted(util.NET_CASES))
+def test_forward_all_exits_and_fused_evaluate(cname):
+    spec = util.NET_CASES[cname]
+    net = util.make_net(spec)
+    for (h, w) in spec["sizes"]:
+        x, gt = util.make_input(1, h, w)
+        tag = f"{cname}/{h}x{w}"
+        outs = net(x)
+        assert len(outs) == len([k for k in NETS.files if k.startswith(f"{tag}/forward/")])
+        for e, o in enumerate(outs):
+            ref = torch.from_numpy(NETS[f"{tag}/forward/{e}"])
+            assert util.rel_err(o, ref) < TOL, (tag, e)
+            assert _agree(o, ref) >= 0.999
+        cm = net.evaluate(x, gt)
+        for e, o in enumerate(outs):
+            assert np.array_equal(cm[e].sum(0).numpy(), orc.generate_matrix(gt.numpy(), o.argmax(1).numpy())), (tag, e)
+
+
+def test_batch_rows_are_independent():
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec)
+    h, w = spec["sizes"][0]
+    x, _ = util.make_input(3, h, w, seed=5)
+    outs = [o.clone() for o in net(x)]
+    for i in range(3):
+        single = net(x[i:i + 1])
+        for e in range(len(outs)):
+            assert util.rel_err(outs[e][i:i + 1], single[e]) < 2e-5          # oneDNN picks batch-dependent blockings
+
+
+def test_get_feature_and_edm_gate_match_reference():
+    cname = "searched-dense-C2"
+    spec = util.NET_CASES[cname]
+    net = util.make_net(spec)
+    edm = util.make_edm()
+    for (h, w) in spec["sizes"]:
+        tag = f"{cname}/{h}x{w}"
+        x, _ = util.make_input(1, h, w)
+        lg, feat = net.get_feature(x)
+        assert util.rel_err(lg, torch.from_numpy(NETS[f"{tag}/get_feature/logits"])) < TOL
+        assert feat.double().abs().sum().item() == pytest.approx(float(NETS[f"{tag}/get_feature/feature_sum"]), rel=1e-4)
+        c0 = float(NETS[f"{tag}/edm_value"])
+        for label, thr in (("exit", c0 + 1.0), ("noexit", c0 - 1.0)):
+            y, ee, _, cv = net.dynamic_inference(x, threshold=thr, confidence='edm', edm=edm)
+            assert ee == (1 if label == "exit" else 0)
+            assert float(cv) == pytest.approx(float(NETS[f"{tag}/dynamic_edm/{label}/conf"]), rel=1e-3, abs=1e-4)
+            assert util.rel_err(y, torch.from_numpy(NETS[f"{tag}/dynamic_edm/{label}/y"])) < TOL
+
+
+def test_batched_gating_equals_per_image_control_flow():
+    """One gate, a batch of 5 with mixed decisions: gathers, compaction and the result scatter of `dynamic_evaluate`."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec)
+    edm = util.make_edm()
+    h, w = spec["sizes"][0]
+    x, gt = util.make_input(5, h, w, seed=31)
+    vals = [float(net.dynamic_inference(x[i:i + 1], threshold=1e30, confidence='edm', edm=edm)[3]) for i in range(5)]
+    for thr in (sorted(vals)[2] - 1e-4 * abs(sorted(vals)[2]) - 1e-6, 1e30, -1e30):
+        ref = []
+        for i in range(5):
+            y1, e1, _, c1 = net.dynamic_inference(x[i:i + 1], threshold=thr, confidence='edm', edm=edm)
+            ref.append((y1.clone(), e1, float(c1)))
+        ys, flags, confs = net.dynamic_inference_batch(x, thr, 'edm', edm)
+        assert flags == [r[1] for r in ref]
+        for i in range(5):
+            assert util.rel_err(ys[i], ref[i][0]) < 2e-5
+        cms, flags2, _ = net.dynamic_evaluate(x, gt, thr, edm)
+        assert flags2 == flags
+        for i in range(5):
+            assert np.array_equal(cms[i].numpy(), orc.generate_matrix(gt[i].numpy(), ref[i][0].argmax(1).numpy())), (thr, i)
+
+
+def test_three_gated_exits_match_reference_fixture():
+    """The body of tests/test_zz_gpu_late.py::test_three_gated_exits_plan_cache_lineage on the CPU stand-in: three gated
+    exits, a batch of 6, six calls with different exit patterns on one runner, against the reference fixture."""
+    net, edm, x, gt = util.make_three_gate_case()
+    n = util.THREE_GATES["n"]
+    thr_index = {float(v): t for t, v in enumerate(G3["thresholds"])}
+    for thr in util.three_gate_thresholds(G3):
+        t = thr_index[thr]
+        ys, flags, confs = net.dynamic_inference_batch(x, thr, 'edm', edm)
+        ys = [y.clone() for y in ys]
+        assert flags == [int(G3[f"t{t}/img{i}/exit"]) for i in range(n)], (t, flags)
+        for i in range(n):
+            k = f"t{t}/img{i}"
+            assert float(confs[i]) == pytest.approx(float(G3[k + "/conf"]), rel=1e-3, abs=1e-4), (t, i)
+            assert float(ys[i].double().abs().sum()) == pytest.approx(float(G3[k + "/y_abs_sum"]), rel=1e-3), (t, i)
+            if k + "/y" in G3.files:
+                want = torch.from_numpy(G3[k + "/y"])
+                assert util.rel_err(ys[i], want) < TOL, (t, i)
+                assert _agree(ys[i], want) >= 0.999
+        for i in range(n):                       # batch-1 control flow of this library
+            y1, e1, _, c1 = net.dynamic_inference(x[i:i + 1], threshold=thr, confidence='edm', edm=edm)
+            assert e1 == flags[i] and util.rel_err(ys[i], y1) < 2e-5, (t, i)
+        cms, flags2, _ = net.dynamic_evaluate(x, gt, thr, edm)
+        assert flags2 == flags
+        for i in range(n):
+            assert np.array_equal(cms[i].numpy(), orc.generate_matrix(gt[i].numpy(), ys[i].argmax(1).numpy())), (thr, i)
+    runner = next(v for k, v in net._plans.items() if k[0] == "edm" and k[5] == "logits" and k[1][0] == n)
+    assert len({k[0] for k in runner.segments}) >= 3 and len(runner.segments) >= 4, sorted(k[:2] for k in runner.segments)
+    assert len({k[0] for k in runner.heads}) >= 2, sorted(k[:2] for k in runner.heads)
+
+
+@pytest.mark.parametrize("cname", sorted(util.SIBLING_CASES))
+def test_sibling_wirings(cname):
+    spec = util.SIBLING_CASES[cname]
+    net = util.make_sibling(spec)
+    x, _ = util.make_input(1, *spec["size"])
+    outs = net(x)
+    if spec["cls"] == "AutoDeepLab":
+        assert outs[0] is None
+        outs = [outs[1]]
+    for e, o in enumerate(outs):
+        assert util.rel_err(o, torch.from_numpy(SIBS[f"{cname}/forward/{e}"])) < TOL
