@@ -142,3 +142,29 @@ def test_sibling_wirings(cname):
         outs = [outs[1]]
     for e, o in enumerate(outs):
         assert util.rel_err(o, torch.from_numpy(SIBS[f"{cname}/forward/{e}"])) < TOL
+
+
+OPS = np.load(util.ROOT / "tests/golden/ops.npz")
+
+
+@pytest.mark.parametrize("name", sorted(util.OP_CASES))
+def test_operator_modules(name):
+    """Every operator drop-in called on its own (BN folded on the host, flags, FactorizedReduce's merged 2x2 taps, pools)."""
+    m, x = util.make_op_case(name)
+    y = m(x)
+    ref = torch.from_numpy(OPS[name + "/y"])
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert util.rel_err(y, ref) < 5e-5
+
+
+def test_cell_aspp_decoder_edm_modules():
+    m, xpp, xp = util.make_cell_case()
+    _, concat, dense = m(xpp, xp)
+    assert util.rel_err(concat, torch.from_numpy(OPS["cell_mixed/concat"])) < 5e-5
+    assert util.rel_err(dense, torch.from_numpy(OPS["cell_mixed/dense"])) < 5e-5
+    m, x = util.make_aspp_case()
+    assert util.rel_err(m(x), torch.from_numpy(OPS["aspp/y"])) < 5e-5
+    m, x, low, size = util.make_decoder_case()
+    assert util.rel_err(m(x, low, size), torch.from_numpy(OPS["decoder/y"])) < 5e-5
+    m, x = util.make_edm_case()
+    assert util.rel_err(m(x), torch.from_numpy(OPS["edm/y"])) < 1e-4
