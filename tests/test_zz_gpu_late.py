@@ -80,6 +80,46 @@ def test_global_avgpool_wide_channels(c, dtype):
         assert float((out.double() - want).abs().max()) < 1e-5
 
 
+# ---- train.py:227-240 as written in the reference: model(image) in .train(), torch's own criterion and optimiser --------
+def test_reference_style_training_loop_through_model_call():
+    """`ADD.forward` in `.train()` is the training-mode forward (training.add_forward) with autograd attached, so the
+    reference's loop runs unchanged: output = model(image); loss = mean_k criterion(output[k], target); loss.backward();
+    optimizer.step() with torch.optim.SGD.  First-step loss against the unmodified reference (tests/golden/train_step.npz),
+    gradients equal to the library's own loss path (same forward, torch's CE instead of add_ce_loss_fwd_bwd)."""
+    from add_b200 import training as T
+    TRAIN = np.load(util.ROOT / "tests/golden/train_step.npz")
+    spec = util.TRAIN_STEP
+    net, x, gt = util.make_train_case()
+    net = net.to(DEV).train()
+    xd, gtd = x.to(DEV), gt.to(DEV)
+    outs = net(xd)
+    assert all(tuple(o.shape) == (spec["n"], 19, *spec["size"]) and o.requires_grad for o in outs)
+    crit = torch.nn.CrossEntropyLoss(ignore_index=255)
+    loss = sum(crit(o, gtd) for o in outs) / len(outs)                      # train.py:229-233
+    assert float(loss) == pytest.approx(float(TRAIN["step0/loss"]), rel=1e-4)
+    opt = torch.optim.SGD(net.parameters(), lr=spec["lr"], momentum=spec["momentum"], weight_decay=spec["weight_decay"],
+                          nesterov=spec["nesterov"])
+    opt.zero_grad()
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+    assert len(grads) > 500 and all(torch.isfinite(g).all() for g in grads.values())
+    # the library's own loss kernel on the same forward gives the same gradients
+    net2, _, _ = util.make_train_case()
+    net2 = net2.to(DEV).train()
+    loss2, _ = T.add_loss(net2, xd, gtd)
+    loss2.backward()
+    assert float(loss2) == pytest.approx(float(loss), rel=1e-5)
+    # tolerance: the noise floor of this chaotic random-init network (how far the REFERENCE's own gradient of each tensor
+    # moves under a 1e-6 relative input perturbation), as in tests/test_gpu_training.py
+    floor = {str(k): float(a) for k, a in zip(TRAIN["grad_names"], TRAIN["grad_rel_change_pert"])}
+    for (k, p) in net2.named_parameters():
+        if k in grads and p.grad is not None:
+            assert util.rel_err(grads[k], p.grad) < 3 * floor.get(k, 0.1) + 1e-3, k
+    opt.step()
+    net.eval()
+    assert all(torch.isfinite(o).all() for o in net(xd))
+
+
 # ---- Evaluator histogram, variant B (thread-private counters; opt-in) against variant A and the numpy oracle --------------
 @pytest.fixture
 def _confusion_variant_b():
@@ -134,43 +174,3 @@ def test_confusion_variant_b_is_bit_identical_to_variant_a():
         keep = (gn >= 0) & (gn < 19) & (pn >= 0) & (pn < 19)
         want = np.bincount(19 * gn[keep] + pn[keep], minlength=361).reshape(19, 19)
         assert np.array_equal(outs[0], want), name
-
-
-# ---- train.py:227-240 as written in the reference: model(image) in .train(), torch's own criterion and optimiser --------
-def test_reference_style_training_loop_through_model_call():
-    """`ADD.forward` in `.train()` is the training-mode forward (training.add_forward) with autograd attached, so the
-    reference's loop runs unchanged: output = model(image); loss = mean_k criterion(output[k], target); loss.backward();
-    optimizer.step() with torch.optim.SGD.  First-step loss against the unmodified reference (tests/golden/train_step.npz),
-    gradients equal to the library's own loss path (same forward, torch's CE instead of add_ce_loss_fwd_bwd)."""
-    from add_b200 import training as T
-    TRAIN = np.load(util.ROOT / "tests/golden/train_step.npz")
-    spec = util.TRAIN_STEP
-    net, x, gt = util.make_train_case()
-    net = net.to(DEV).train()
-    xd, gtd = x.to(DEV), gt.to(DEV)
-    outs = net(xd)
-    assert all(tuple(o.shape) == (spec["n"], 19, *spec["size"]) and o.requires_grad for o in outs)
-    crit = torch.nn.CrossEntropyLoss(ignore_index=255)
-    loss = sum(crit(o, gtd) for o in outs) / len(outs)                      # train.py:229-233
-    assert float(loss) == pytest.approx(float(TRAIN["step0/loss"]), rel=1e-4)
-    opt = torch.optim.SGD(net.parameters(), lr=spec["lr"], momentum=spec["momentum"], weight_decay=spec["weight_decay"],
-                          nesterov=spec["nesterov"])
-    opt.zero_grad()
-    loss.backward()
-    grads = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
-    assert len(grads) > 500 and all(torch.isfinite(g).all() for g in grads.values())
-    # the library's own loss kernel on the same forward gives the same gradients
-    net2, _, _ = util.make_train_case()
-    net2 = net2.to(DEV).train()
-    loss2, _ = T.add_loss(net2, xd, gtd)
-    loss2.backward()
-    assert float(loss2) == pytest.approx(float(loss), rel=1e-5)
-    # tolerance: the noise floor of this chaotic random-init network (how far the REFERENCE's own gradient of each tensor
-    # moves under a 1e-6 relative input perturbation), as in tests/test_gpu_training.py
-    floor = {str(k): float(a) for k, a in zip(TRAIN["grad_names"], TRAIN["grad_rel_change_pert"])}
-    for (k, p) in net2.named_parameters():
-        if k in grads and p.grad is not None:
-            assert util.rel_err(grads[k], p.grad) < 3 * floor.get(k, 0.1) + 1e-3, k
-    opt.step()
-    net.eval()
-    assert all(torch.isfinite(o).all() for o in net(xd))
