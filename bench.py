@@ -2,7 +2,7 @@
 """bench.py — ADD 1024x2048 inference images/sec on N B200s (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (libadd_b200, sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...  # reference's CPU path (oracle port), host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference (baseline/_ref) on the host cores
 
 One step = one pass of the hot path over one batch: BASELINE config 2 — searched-dense ADD (C=2,
 F=20), 8 synthetic 3x1024x2048 images per GPU, bf16, EDM-gated early exit applied per image
@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_cuda"],
-                    help="b200 = this repo; reference = the reference's CPU path (oracle port); torch_cuda = informational "
+                    help="b200 = this repo; reference = the UNMODIFIED reference on the host cores (baseline/_ref; the oracle port only if nothing was staged); torch_cuda = informational "
                          "stock PyTorch/cuDNN comparator on cuda:0")
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--height", type=int, default=1024)
