@@ -1,7 +1,14 @@
 """GPU: tests written at the very end of round 2, after the round's GPU budget was spent — they have had NO run on a
-B200 in their present form (the three-gate test ran in an earlier form whose thresholds never let an image past the
-second gate; the wide-channel GAP cases are new with the kernel).  The file name sorts last on purpose: under the
-driver's `pytest -x` a regression here must not hide the established suite that precedes it."""
+B200 in their present form:
+
+ * three gated exits against the reference fixture (an earlier form ran on the B200 with thresholds that never let an
+   image past the second gate; the host logic of this form is checked numerically on CPU, tests/test_sim_host_logic.py);
+ * the wide-channel global average pool (new with the kernel's channel-group grid);
+ * the reference-style training loop through `model(image)` in `.train()`;
+ * the opt-in thread-private Evaluator histogram (variant B) against the default kernel and the reference goldens.
+
+The file name sorts last on purpose: under the driver's `pytest -x` a regression here must not hide the established suite
+that precedes it; the opt-in kernel comes last of all."""
 import numpy as np
 import pytest
 import torch
