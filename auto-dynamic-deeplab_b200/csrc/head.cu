@@ -451,38 +451,38 @@ confusion_private_kernel(const long long* __restrict__ gt, const long long* __re
   }
 }
 
-// Sum of the B per-block rows, int64 out.  One block of 16 warps: warp w takes rows w, w + 16, ...; up to 16 loads of a
-// thread are independent of each other (variant A's finalize issues them one dependent round trip at a time).
-constexpr int CFF_WARPS = 16;
+// Sum of the B per-block rows, int64 out.  Block j sums bins [128 j, 128 j + 128); its 32 warps take rows w, w + 32, ...
+// four rows x four bins per thread and trip = 16 independent loads in flight (variant A's finalize walks the rows one
+// dependent L2 round trip at a time in a single block); the warps meet in shared memory in fixed order.
+constexpr int CFF_WARPS = 32;
 __global__ void __launch_bounds__(CFF_WARPS * 32)
 confusion_finalize_wide_kernel(const unsigned int* __restrict__ part, int B, int bins, long long* __restrict__ out) {
-  __shared__ unsigned long long red[CFF_WARPS][MAX_BINS];
+  __shared__ unsigned long long red[CFF_WARPS][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i0 = 0; i0 < bins; i0 += 128) {
-    unsigned long long s[4] = {0, 0, 0, 0};
-    for (int b = warp; b < B; b += 4 * CFF_WARPS) {
-      unsigned int v[4][4];
+  const int i0 = blockIdx.x * 128;
+  unsigned long long s[4] = {0, 0, 0, 0};
+  for (int b = warp; b < B; b += 4 * CFF_WARPS) {
+    unsigned int v[4][4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int br = b + r * CFF_WARPS;
-        const unsigned int* row = part + (size_t)(br < B ? br : b) * bins;
+    for (int r = 0; r < 4; ++r) {
+      const int br = b + r * CFF_WARPS;
+      const unsigned int* row = part + (size_t)(br < B ? br : b) * bins;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + lane; v[r][u] = (br < B && i < bins) ? __ldg(row + i) : 0u; }
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) s[u] += v[r][u];
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + lane; v[r][u] = (br < B && i < bins) ? __ldg(row + i) : 0u; }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = i0 + u * 32 + lane; if (i < bins) red[warp][i] = s[u]; }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < bins; i += CFF_WARPS * 32) {
-    unsigned long long s = 0;
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int wv = 0; wv < CFF_WARPS; ++wv) s += red[wv][i];
-    out[i] = (long long)s;
+      for (int u = 0; u < 4; ++u) s[u] += v[r][u];
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) red[warp][u * 32 + lane] = s[u];
+  __syncthreads();
+  if (threadIdx.x < 128 && i0 + (int)threadIdx.x < bins) {
+    unsigned long long t = 0;
+#pragma unroll
+    for (int wv = 0; wv < CFF_WARPS; ++wv) t += red[wv][threadIdx.x];
+    out[i0 + threadIdx.x] = (long long)t;
   }
 }
 
@@ -545,7 +545,8 @@ inline int confusion_private_blocks(long long n_pix) {
   if (b < need) b = need;
   return (int)(b < 1 ? 1 : b);
 }
-int g_confusion_impl = 0;     // 0 = variant A (per-warp, match.any; the measured default), 1 = variant B (thread-private)
+int g_confusion_impl = 0;     // 0 = variant A (per-warp, match.any; the measured default), 1 = variant B (thread-private) +
+                              // wide finalize, 2 = variant A's histogram kernel + the wide finalize
 inline int confidence_blocks(long long total) {
   long long b = (total + 1023) / 1024;
   return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
@@ -625,9 +626,10 @@ extern "C" int64_t add_confusion_workspace_bytes(int64_t n_pixels, int num_class
   return (int64_t)(a > b ? a : b) * num_class * num_class * sizeof(unsigned int);
 }
 
-/* 0 = per-warp privatised histogram with match.any (default), 1 = thread-private histograms (opt-in, see head.cu). */
+/* 0 = per-warp privatised histogram with match.any + one-block finalize (default), 1 = thread-private histograms + wide
+ * finalize, 2 = the default histogram kernel + wide finalize (1 and 2 opt-in, see head.cu). */
 extern "C" int add_confusion_set_impl(int impl) {
-  if (impl != 0 && impl != 1) return ADD_ERR_BAD_ARG;
+  if (impl < 0 || impl > 2) return ADD_ERR_BAD_ARG;
   g_confusion_impl = impl;
   return ADD_OK;
 }
@@ -651,15 +653,19 @@ extern "C" int add_confusion_matrix(const int64_t* gt, const int64_t* pred, int6
     });
     confusion_private_kernel<<<Bp, CF_THREADS, smem, s>>>((const long long*)gt, (const long long*)pred, n_pixels, num_class,
                                                           (unsigned int*)workspace, vec_ok);
-    confusion_finalize_wide_kernel<<<1, CFF_WARPS * 32, 0, s>>>((const unsigned int*)workspace, Bp, num_class * num_class,
-                                                                (long long*)cm_out);
+    confusion_finalize_wide_kernel<<<(num_class * num_class + 127) / 128, CFF_WARPS * 32, 0, s>>>(
+        (const unsigned int*)workspace, Bp, num_class * num_class, (long long*)cm_out);
     ADD_RETURN_LAUNCH();
   }
   int B = confusion_blocks(n_pixels);
   confusion_kernel<<<B, HD_THREADS, 0, s>>>((const long long*)gt, (const long long*)pred, n_pixels, num_class,
                                             (unsigned int*)workspace, vec_ok);
-  confusion_finalize_kernel<<<1, HD_THREADS, 0, s>>>((const unsigned int*)workspace, B, num_class * num_class,
-                                                     (long long*)cm_out);
+  if (g_confusion_impl == 2)
+    confusion_finalize_wide_kernel<<<(num_class * num_class + 127) / 128, CFF_WARPS * 32, 0, s>>>(
+        (const unsigned int*)workspace, B, num_class * num_class, (long long*)cm_out);
+  else
+    confusion_finalize_kernel<<<1, HD_THREADS, 0, s>>>((const unsigned int*)workspace, B, num_class * num_class,
+                                                       (long long*)cm_out);
   ADD_RETURN_LAUNCH();
 }
 

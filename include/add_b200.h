@@ -243,9 +243,10 @@ int add_widen_labels_u8(const uint8_t* src, int64_t* dst, int64_t n, void* strea
 int64_t add_confusion_workspace_bytes(int64_t n_pixels, int num_class);
 int add_confusion_matrix(const int64_t* gt, const int64_t* pred, int64_t n_pixels, int num_class,
                          int64_t* cm_out, void* workspace, int64_t workspace_bytes, void* stream);
-/* A/B switch (no effect on results): 0 = per-warp privatised histogram, intra-warp collisions resolved with match.any
- * (default: the variant measured on the B200), 1 = thread-private 16-bit histograms in shared memory, conflict-free,
- * one CTA per SM (opt-in until pinned on hardware). */
+/* A/B switch (no effect on results): 0 = per-warp privatised histogram, intra-warp collisions resolved with match.any,
+ * one-block finalize (default: the variant measured on the B200); 1 = thread-private 16-bit histograms in shared memory,
+ * conflict-free, one CTA per SM, many-loads-in-flight finalize; 2 = the default histogram kernel with that finalize
+ * (1 and 2 opt-in until pinned on hardware). */
 int add_confusion_set_impl(int impl);
 
 /* ---- confidence scalars on materialised NCHW fp32 logits (operations.py:161-180) ---------- */

@@ -128,10 +128,10 @@ def test_reference_style_training_loop_through_model_call():
 
 
 # ---- Evaluator histogram, variant B (thread-private counters; opt-in) against variant A and the numpy oracle --------------
-@pytest.fixture
-def _confusion_variant_b():
+@pytest.fixture(params=[1, 2], ids=["thread_private", "default_hist_wide_finalize"])
+def _confusion_variant_b(request):
     from add_b200._lib import lib as _lib
-    assert _lib.add_confusion_set_impl(1) == 0
+    assert _lib.add_confusion_set_impl(request.param) == 0
     try:
         yield _lib
     finally:
@@ -165,19 +165,20 @@ def test_confusion_variant_b_is_bit_identical_to_variant_a():
     for name, gt, pred in cases:
         gtd, prd = gt.to(DEV), pred.to(DEV)
         outs = []
-        for impl in (0, 1):
+        for impl in (0, 1, 2):            # default; thread-private histogram + wide finalize; default histogram + wide finalize
             assert _lib.add_confusion_set_impl(impl) == 0
             try:
-                outs.append(add_b200.Evaluator(19)._generate_matrix(gtd, prd).cpu().numpy())
+                o = [add_b200.Evaluator(19)._generate_matrix(gtd, prd).cpu().numpy()]
                 if gt.numel() > 1 and gt.dim() == 1:                       # base pointers 8 bytes off a 16-byte boundary
-                    outs.append(add_b200.Evaluator(19)._generate_matrix(gtd[1:], prd[1:]).cpu().numpy())
+                    o.append(add_b200.Evaluator(19)._generate_matrix(gtd[1:], prd[1:]).cpu().numpy())
+                outs.append(o)
             finally:
                 _lib.add_confusion_set_impl(0)
-        half = len(outs) // 2
-        for a, b in zip(outs[:half], outs[half:]):
-            assert np.array_equal(a, b), name
+        for impl in (1, 2):
+            for a, b in zip(outs[0], outs[impl]):
+                assert np.array_equal(a, b), (name, impl)
         # metrics.py:34-39 with the library's stated handling of predictions that have no cell (dropped, never aliased)
         gn, pn = gt.numpy().reshape(-1), pred.numpy().reshape(-1)
         keep = (gn >= 0) & (gn < 19) & (pn >= 0) & (pn < 19)
         want = np.bincount(19 * gn[keep] + pn[keep], minlength=361).reshape(19, 19)
-        assert np.array_equal(outs[0], want), name
+        assert np.array_equal(outs[0][0], want), name

@@ -50,7 +50,8 @@ def timed(fn, n):
 
 by = N * H * W * 16
 from add_b200._lib import lib as _lib  # noqa: E402
-_variants = [(0, "per-warp match.any (default)")] + ([(1, "thread-private counters (opt-in)")] if "--variants" in sys.argv else [])
+_variants = [(0, "per-warp match.any (default)")] + ([(1, "thread-private counters + wide finalize (opt-in)"), (2, "default histogram + wide finalize (opt-in)")]
+                                                           if "--variants" in sys.argv else [])
 _cms = []
 for impl, label in _variants:
     assert _lib.add_confusion_set_impl(impl) == 0
@@ -62,8 +63,8 @@ for impl, label in _variants:
     print(f"confusion_matrix   {N}x{H}x{W} int64, {label}: {ms * 1e3:8.1f} us  {by / ms / 1e6:8.1f} GB/s  = {by / ms / 1e6 / peak:.3f} of measured HBM peak ({by / 1e6:.0f} MB algorithmic)")
     RESULT[f"confusion_matrix_impl{impl}"] = {"variant": label, "us": ms * 1e3, "gbs": by / ms / 1e6, "frac_of_hbm_peak": by / ms / 1e6 / peak,
                                               "algorithmic_bytes": by, "default": impl == 0}
-if len(_cms) == 2:
-    RESULT["confusion_variants_bit_identical"] = bool(torch.equal(_cms[0], _cms[1]))
+if len(_cms) > 1:
+    RESULT["confusion_variants_bit_identical"] = bool(all(torch.equal(_cms[0], c) for c in _cms[1:]))
     print("variants bit-identical:", RESULT["confusion_variants_bit_identical"])
 if _json_out:
     Path(_json_out).write_text(json.dumps(RESULT))          # written early: the fused-head part below may be skipped by the caller's timeout
