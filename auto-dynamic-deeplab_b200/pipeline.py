@@ -36,8 +36,7 @@ class HostPipeline:
         # 3 slots: batch i+2 is being copied in while the trunk of batch i+1 and the exit heads of batch i compute
         self.depth = max(2 if edm is None else 3, int(depth))
         self.device = next(net.parameters()).device
-        if self.device.type != "cuda":
-            raise RuntimeError("HostPipeline needs the model on a CUDA device (add_b200 has no CPU fallback)")
+        rt.require_cuda_device(self.device, "HostPipeline")
         self.copy_stream = torch.cuda.Stream(self.device)
         self._slots: Optional[List[dict]] = None
         self._slot_sets: dict = {}

@@ -58,6 +58,11 @@ def require_cuda(t: torch.Tensor, what: str = "input") -> None:
                            "(the CPU oracle lives in oracle/ and is test infrastructure only)")
 
 
+def require_cuda_device(device: torch.device, what: str) -> None:
+    if device.type != "cuda":
+        raise RuntimeError(f"{what} needs the model on a CUDA device (add_b200 has no CPU fallback)")
+
+
 class View:
     """Channel-slice view of a dense NHWC buffer (torch tensor of shape [N,H,W,Ctot])."""
     __slots__ = ("buf", "c_off", "c", "relud")

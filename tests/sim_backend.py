@@ -14,6 +14,8 @@ What it does NOT test: the kernels (their parity is the `-m gpu` suite) and the 
 (tests/test_dry_run_plans.py hands every recorded launch to the real entry points for validation)."""
 from __future__ import annotations
 
+import contextlib
+
 import torch
 import torch.nn.functional as F
 
@@ -243,6 +245,9 @@ def install(monkeypatch) -> None:
             assert fn(*args, None) == 0, tag
     monkeypatch.setattr(Plan, "run_eager", run_eager)
     monkeypatch.setattr(rt, "require_cuda", lambda *a, **k: None)
+    monkeypatch.setattr(rt, "require_cuda_device", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: _Stream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
 
     def fresh_logits(self):
         n, nc, H, W = self.out_shape
@@ -257,4 +262,3 @@ def install(monkeypatch) -> None:
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
     monkeypatch.setattr(torch.cuda, "Event", _Event)
-    monkeypatch.setattr(rt, "set_tc_enabled", rt.set_tc_enabled)       # (restored to its own value: keeps the patch list explicit)

@@ -168,3 +168,35 @@ def test_cell_aspp_decoder_edm_modules():
     assert util.rel_err(m(x, low, size), torch.from_numpy(OPS["decoder/y"])) < 5e-5
     m, x = util.make_edm_case()
     assert util.rel_err(m(x), torch.from_numpy(OPS["edm/y"])) < 1e-4
+
+
+def test_host_pipeline_ragged_final_batch():
+    """HostPipeline over batches of 3, 3, 2, 1, 3 images (a loader's final, smaller batch): every batch equals the direct
+    call on that batch, nothing is broadcast into a full slot or counted twice, one slot set per batch shape.
+    Host images fp32 / labels int64 (the uint8 edges are direct kernel calls the stand-in does not model)."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec)
+    edm = util.make_edm()
+    sizes = [3, 3, 2, 1, 3]
+    batches = [util.make_input(n, 33, 65, seed=400 + i) for i, n in enumerate(sizes)]
+    _, _, confs = net.dynamic_evaluate(batches[0][0], batches[0][1], -1e30, edm)
+    thr = sorted(float(c) for c in confs)[1]
+    want = []
+    for x, gt in batches:
+        cm, flags, _ = net.dynamic_evaluate(x, gt, thr, edm)
+        want.append((cm.clone(), list(flags)))
+    pipe = add_b200.HostPipeline(net, edm, thr)
+    got = [(cm.clone(), list(flags)) for cm, flags in pipe.evaluate(iter(batches))]
+    assert [g[0].shape[1] for g in got] == sizes
+    for (cm_g, fl_g), (cm_w, fl_w), (x, gt) in zip(got, want, batches):
+        assert fl_g == fl_w and torch.equal(cm_g[0], cm_w)
+        assert int(cm_g[0].sum()) == int((gt != 255).sum())
+    assert len(pipe._slot_sets) == 3
+    pipe2 = add_b200.HostPipeline(net)
+    for (cm_g, fl), (x, gt) in zip(pipe2.evaluate(iter(batches[1:4])), batches[1:4]):
+        assert fl is None and torch.equal(cm_g, net.evaluate(x, gt))
+    # the resident-input pipeline over stable buffers gives the same matrices
+    rp = add_b200.ResidentPipeline(net, edm, thr)
+    bufs = [(batches[0][0].clone(), batches[0][1].clone()), (batches[1][0].clone(), batches[1][1].clone())]
+    outs = [(cm.clone(), list(fl)) for cm, fl in rp.evaluate(iter(bufs))]
+    assert torch.equal(outs[0][0], want[0][0]) and torch.equal(outs[1][0], want[1][0]) and outs[0][1] == want[0][1]

@@ -127,6 +127,36 @@ def test_reference_style_training_loop_through_model_call():
     assert all(torch.isfinite(o).all() for o in net(xd))
 
 
+# ---- HostPipeline: the loader's final, smaller batch (slots sized from the first batch broadcast a tail into N rows) -----
+def test_host_pipeline_ragged_final_batch():
+    """Batches of 3, 3 and then 2 and 1 images (500 Cityscapes val images in batches of 8 leave 4): every batch's result
+    equals the direct call on that batch, the tail is neither broadcast into a full slot nor counted more than once, and a
+    return to the first shape reuses that shape's slots."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec).to(DEV)
+    edm = util.make_edm().to(DEV)
+    sizes = [3, 3, 2, 1, 3]
+    batches = [util.make_input(n, 33, 65, seed=400 + i) for i, n in enumerate(sizes)]
+    _, _, confs = net.dynamic_evaluate(batches[0][0].to(DEV), batches[0][1].to(DEV), -1e30, edm)
+    thr = sorted(float(c) for c in confs)[1]
+    want = []
+    for x, gt in batches:
+        cm, flags, _ = net.dynamic_evaluate(x.to(DEV), gt.to(DEV), thr, edm)
+        want.append((cm.cpu().clone(), list(flags)))
+    pipe = add_b200.HostPipeline(net, edm, thr)
+    got = [(cm.clone(), list(flags)) for cm, flags in pipe.evaluate((x.pin_memory(), gt.pin_memory()) for x, gt in batches)]
+    assert [g[0].shape[1] for g in got] == sizes
+    for (cm_g, fl_g), (cm_w, fl_w), (x, gt) in zip(got, want, batches):
+        assert fl_g == fl_w
+        assert torch.equal(cm_g[0], cm_w)
+        assert int(cm_g[0].sum()) == int((gt != 255).sum())                 # every valid pixel counted exactly once
+    assert len(pipe._slot_sets) == 3                                        # one slot set per batch shape, reused on return
+    # multi-exit mode (no EDM) over the same ragged stream
+    pipe2 = add_b200.HostPipeline(net)
+    for (cm_g, fl), (x, gt) in zip(pipe2.evaluate((x.pin_memory(), gt.pin_memory()) for x, gt in batches[1:4]), batches[1:4]):
+        assert fl is None and torch.equal(cm_g, net.evaluate(x.to(DEV), gt.to(DEV)).cpu())
+
+
 # ---- Evaluator histogram, variant B (thread-private counters; opt-in) against variant A and the numpy oracle --------------
 @pytest.fixture(params=[1, 2], ids=["thread_private", "default_hist_wide_finalize"])
 def _confusion_variant_b(request):
