@@ -200,3 +200,35 @@ def test_host_pipeline_ragged_final_batch():
     bufs = [(batches[0][0].clone(), batches[0][1].clone()), (batches[1][0].clone(), batches[1][1].clone())]
     outs = [(cm.clone(), list(fl)) for cm, fl in rp.evaluate(iter(bufs))]
     assert torch.equal(outs[0][0], want[0][0]) and torch.equal(outs[1][0], want[1][0]) and outs[0][1] == want[0][1]
+
+
+def test_api_edge_returns_fresh_tensors_and_first_exit_in_layer_order():
+    """(1) `forward` / `get_feature` results must not alias plan buffers that the next call overwrites
+    (`o1 = model(a); o2 = model(b)`, as flip-TTA does); (2) `get_feature` takes the first exit in ASCENDING layer order
+    (ADD.py:366), whatever the order of C_index."""
+    spec = util.NET_CASES["searched-dense-C2"]
+    net = util.make_net(spec)
+    h, w = spec["sizes"][0]
+    xa, _ = util.make_input(1, h, w, seed=1)
+    xb, _ = util.make_input(1, h, w, seed=2)
+    oa = net(xa)
+    keep = [o.clone() for o in oa]
+    ob = net(xb)
+    assert all(torch.equal(a, k) for a, k in zip(oa, keep))                 # the second call did not overwrite the first result
+    assert all(a.data_ptr() != b.data_ptr() for a, b in zip(oa, ob)) and not torch.equal(oa[0], ob[0])
+    la, fa = net.get_feature(xa)
+    la_keep, fa_keep = la.clone(), fa.clone()
+    net.get_feature(xb)
+    assert torch.equal(la, la_keep) and torch.equal(fa, fa_keep)
+    # C_index in non-ascending order
+    c = util.THREE_GATES
+    torch.manual_seed(1)
+    net2 = add_b200.ADD(c["network_arch"], [9, 3, 6], util.cell_arch(), 19, add_b200.Args(c["F"], c["B"]), c["low_level_layer"])
+    net2 = util._randomized(net2, 21)
+    x, _ = util.make_input(1, 33, 65, seed=3)
+    lg, feat = net2.get_feature(x)
+    sd = {k: v.detach() for k, v in net2.state_dict().items()}
+    with torch.no_grad():
+        lg_ref, feat_ref = orc.add_get_feature(sd, orc.Arch(c["network_arch"], [9, 3, 6], util.cell_arch(), 19, c["F"], c["B"],
+                                                            c["low_level_layer"]), x)
+    assert util.rel_err(lg, lg_ref) < TOL and util.rel_err(feat, feat_ref) < TOL
