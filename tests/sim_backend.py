@@ -75,7 +75,10 @@ def conv(self, x, y, cw, stride=1, pad=0, dil=1, flags=0, tag="conv", image_bias
 
     def run():
         xin = _window(_x(x, flags & RELU_IN), y.h, y.w, cw.kh, cw.kw, stride, pad, dil)
-        out = F.conv2d(xin, cw.w_h.permute(3, 2, 0, 1).contiguous(), None, stride, 0, dil)
+        w = cw.w_h.permute(3, 2, 0, 1).contiguous()
+        if x.dtype == torch.bfloat16:            # the tcgen05 path multiplies bf16 weights (fp32 accumulate)
+            w = w.to(torch.bfloat16).float()
+        out = F.conv2d(xin, w, None, stride, 0, dil)
         if image_bias is not None:
             out = out + image_bias.float().view(x.n, cw.cout, 1, 1)
         elif cw.bias is not None:
@@ -92,7 +95,10 @@ def sepconv_half(self, x, y, w_dw, pw, k, flags, tag="sephalf"):
     def run():
         xin = _x(x, flags & RELU_IN)
         d = F.conv2d(xin, w_dw.float().permute(2, 0, 1).unsqueeze(1).contiguous(), None, 1, k // 2, 1, x.c)
-        out = F.conv2d(d, pw.w_h.permute(3, 2, 0, 1).contiguous())
+        w = pw.w_h.permute(3, 2, 0, 1).contiguous()
+        if x.dtype == torch.bfloat16:            # depthwise result rounded to bf16 (the UMMA A tile), bf16 pointwise weights
+            d, w = d.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()
+        out = F.conv2d(d, w)
         if pw.bias is not None:
             out = out + pw.bias.float().view(1, -1, 1, 1)
         _store(y, out, flags)
@@ -199,8 +205,17 @@ def edm_mlp(self, pooled, n, ws, out, tag="edm_mlp"):
     _do(self, run, tag, "EDM.mlp")
 
 
-def stem_nchw(self, *a, **k):
-    raise NotImplementedError("the fused bf16 stem has no stand-in: run the simulator in fp32")
+def stem_nchw(self, src, y, w_packed, bias, flags, tag="stem0"):
+    """The fused bf16 stem (NCHW fp32 image -> bf16 -> 3x3 s2 conv 3->64 + bias -> ReLU -> NHWC bf16).  `w_packed` is the
+    ConvWeights itself here: install() makes `rt.pack_stem_tc` the identity, the UMMA image is not decoded on CPU."""
+    cw = w_packed
+
+    def run():
+        xin = _window(src.to(torch.bfloat16).float(), y.h, y.w, 3, 3, 2, 1, 1)
+        w = cw.w_h[:, :, :3, :].to(torch.bfloat16).float().permute(3, 2, 0, 1).contiguous()
+        out = F.conv2d(xin, w, None, 2) + bias.float().view(1, -1, 1, 1)
+        _store(y, out, flags)
+    _do(self, run, tag, "stem_conv_tc")
 
 
 class _Stream:
@@ -246,6 +261,7 @@ def install(monkeypatch) -> None:
     monkeypatch.setattr(Plan, "run_eager", run_eager)
     monkeypatch.setattr(rt, "require_cuda", lambda *a, **k: None)
     monkeypatch.setattr(rt, "require_cuda_device", lambda *a, **k: None)
+    monkeypatch.setattr(rt, "pack_stem_tc", lambda cw: cw)
     monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: _Stream())
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
 

@@ -232,3 +232,39 @@ def test_api_edge_returns_fresh_tensors_and_first_exit_in_layer_order():
         lg_ref, feat_ref = orc.add_get_feature(sd, orc.Arch(c["network_arch"], [9, 3, 6], util.cell_arch(), 19, c["F"], c["B"],
                                                             c["low_level_layer"]), x)
     assert util.rel_err(lg, lg_ref) < TOL and util.rel_err(feat, feat_ref) < TOL
+
+
+def test_bf16_error_is_the_error_of_bf16_storage():
+    """What the bf16 path's distance from the fp32 reference is made of.  The stand-in run in bf16 is an IDEAL bf16-storage
+    implementation: every operator computes in fp32 on bf16-rounded operands and rounds only what it stores (activations,
+    the SepConv depthwise tile, weights) — no kernel, no tensor core, no summation-order effects worth the name.  On the
+    input and weights of tools/bf16_parity_probe.py (257 x 513, seed 4321) its error against the fp32 oracle must be the
+    error MEASURED for the tcgen05 path on the B200 (profiles/r4d_bf16_parity_probe.json, `precision: bf16`): rms within
+    0.75x .. 1.35x per exit and weight set, argmax agreement within 3 points.  I.e. the kernels add nothing to what bf16
+    storage alone costs on this random-init network."""
+    import json
+    probe = [r for r in json.loads((util.ROOT / "profiles" / "r4d_bf16_parity_probe.json").read_text())
+             if isinstance(r, dict) and r.get("precision") == "bf16" and r.get("size") == "257x513"]
+    measured = {(r["weights"], r["exit"]): r for r in probe}
+    na, ci, low = add_b200.NETWORKS["searched-dense"][2]
+    arch = orc.Arch(na, ci, low_level_layer=low)
+    x, _ = orc.synthetic_batch(1, 257, 513, seed=4321)
+    for wname in ("randomized_bn", "calibrated_bn"):
+        net = add_b200.build_add("searched-dense", 2, 20, seed=1)
+        sd = {k: v.clone() for k, v in net.state_dict().items()}
+        sd = orc.randomize_bn_(sd, 21) if wname == "randomized_bn" else orc.calibrate_bn_(sd, arch)
+        net.load_state_dict(sd)
+        net.eval()
+        with torch.no_grad():
+            ref = orc.add_forward(sd, arch, x)
+        net.set_precision("bf16")
+        for e, (o, r) in enumerate(zip(net(x), ref)):
+            o, r = o.double(), r.double()
+            scale = r.abs().max()
+            rms = float((o - r).pow(2).mean().sqrt() / scale)
+            agree = float((o.argmax(1) == r.argmax(1)).float().mean())
+            m = measured[(wname, e)]
+            print(f"bf16 storage model [{wname}] exit {e}: rms {rms:.4e} agree {agree:.4f} | measured on the B200: "
+                  f"rms {m['rms_rel']:.4e} agree {m['argmax_agree']:.4f}")
+            assert 0.75 * m["rms_rel"] <= rms <= 1.35 * m["rms_rel"], (wname, e, rms, m["rms_rel"])
+            assert abs(agree - m["argmax_agree"]) <= 0.03, (wname, e, agree, m["argmax_agree"])
