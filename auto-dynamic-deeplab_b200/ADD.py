@@ -387,7 +387,9 @@ class ADD(AddModule):
             rt.require_cuda(x)
             from . import training as T
             nc = self._num_classes
-            return [o[:, :nc] for o in T.add_forward(self, x)]      # channel nc.. of the padded classifier output is padding
+            outs = [o[:, :nc] for o in T.add_forward(self, x)]      # channel nc.. of the padded classifier output is padding
+            rt.bump_generation()          # running statistics moved: folded eval-mode weights / recorded plans are stale
+            return outs
         self._check_eval()
         rt.require_cuda(x)
         plan = self._get_plan(x, "forward")

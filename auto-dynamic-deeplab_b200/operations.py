@@ -45,6 +45,13 @@ class AddModule(nn.Module):
         """Call after mutating parameters in place (e.g. an optimizer step)."""
         rt.bump_generation()
 
+    def train(self, mode: bool = True):
+        # leaving training mode is where in-place parameter updates (any optimiser, torch's included) and moved running
+        # statistics meet the fused inference path: whatever was folded / recorded before is stale from here on
+        if bool(mode) != self.training:
+            rt.bump_generation()
+        return super().train(mode)
+
     def _ensure_prepared(self) -> None:
         if self._prep_gen != rt.generation():
             self._prepare()

@@ -159,3 +159,21 @@ def test_product_never_imports_the_oracle_or_the_reference():
     for src in sorted((util.ROOT / "auto-dynamic-deeplab_b200").glob("*.py")):
         for ln in src.read_text().splitlines():
             assert not re.match(r"\s*(from|import)\s+(oracle|baseline|modeling)\b", ln), (src.name, ln)
+
+
+def test_leaving_training_mode_invalidates_folded_weights():
+    """An optimiser step mutates parameters in place — torch.optim's too, which knows nothing of this library.  Switching
+    a module between .train() and .eval() therefore bumps the generation that folded weights and recorded plans are
+    stamped with; repeating the current mode does not."""
+    m, _ = util.make_op_case("relu_conv_bn_1x1")
+    m.eval()
+    g0 = rt.generation()
+    m.eval()
+    assert rt.generation() == g0
+    m.train()
+    g1 = rt.generation()
+    assert g1 > g0
+    with torch.no_grad():
+        m.op[1].weight.mul_(2.0)               # what an optimiser step does
+    m.eval()
+    assert rt.generation() > g1
