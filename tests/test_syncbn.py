@@ -89,6 +89,58 @@ def test_world2_packed_allreduce_gives_the_global_statistics(tmp_path):
     assert util.rel_err(inv_std, torch.from_numpy(GOLD[f"{name}/sync/inv_std"])) < 1e-5
 
 
+def _worker_bwd(rank, world, port, name, out_path):
+    """Backward of one SynchronizedBatchNorm2d layer on rank `rank`: the forward statistics through the packed exchange,
+    then the backward's ONE exchange of [sum dy | sum dy*xhat] (csrc/backward.cu: add_bn_bwd_reduce -> exchange_sum ->
+    add_bn_bwd_apply; here the per-rank sums are torch, the exchange is the library's gloo path) and
+    dx = gamma * inv_std * (dy - sum1/M - xhat * sum2/M)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shards, state = util.make_syncbn_case(name)
+    spec = util.SYNCBN_CASES[name]
+    x = shards[rank]
+    C = x.shape[1]
+    g = torch.Generator().manual_seed(900 + rank)
+    dy = torch.randn(x.shape, generator=g)
+    f = x.reshape(x.shape[0], C, -1)
+    packed = sbn.pack_stats(torch.cat([f.sum(dim=(0, 2)), (f ** 2).sum(dim=(0, 2))]), f.shape[0] * f.shape[2])
+    sbn.exchange_sum(packed)                                              # forward: [sum | ssum | n]
+    M = float(packed[-1])
+    mean = packed[:C] / M
+    inv_std = ((packed[C:2 * C] - packed[:C] * mean) / M).clamp(spec["eps"]) ** -0.5
+    xhat = (f - mean.view(1, C, 1)) * inv_std.view(1, C, 1)
+    d = dy.reshape(x.shape[0], C, -1)
+    sums = torch.cat([d.sum(dim=(0, 2)), (d * xhat).sum(dim=(0, 2))])
+    sbn.exchange_sum(sums)                                                # backward: [sum dy | sum dy*xhat]
+    gamma = state["weight"] if state.get("weight") is not None else torch.ones(C)
+    dx = (gamma * inv_std).view(1, C, 1) * (d - (sums[:C] / M).view(1, C, 1) - xhat * (sums[C:] / M).view(1, C, 1))
+    torch.save(dict(dx=dx.view(x.shape), dgamma=sums[C:].clone(), dbeta=sums[:C].clone()), f"{out_path}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_world2_backward_exchange_equals_autograd_on_the_whole_batch(tmp_path):
+    """The backward direction of the N > 1 path on CPU (gloo, world 2): two ranks, each with its shard and its cotangent,
+    exchange ONE [sum dy | sum dy*xhat] vector; every rank's dx, and dgamma / dbeta, equal torch autograd through the
+    reference's synchronised formulas (oracle `sync_batchnorm_train`) applied to both shards in one process."""
+    name = "c8_2shards"
+    out = tmp_path / "bwd"
+    mp.spawn(_worker_bwd, args=(2, _free_port(), name, str(out)), nprocs=2, join=True)
+    got = [torch.load(f"{out}.{r}") for r in range(2)]
+    shards, state = util.make_syncbn_case(name)
+    spec = util.SYNCBN_CASES[name]
+    xs = [s.clone().requires_grad_(True) for s in shards[:2]]
+    w = (state["weight"].clone() if state.get("weight") is not None else torch.ones(spec["C"])).requires_grad_(True)
+    b = (state["bias"].clone() if state.get("bias") is not None else torch.zeros(spec["C"])).requires_grad_(True)
+    outs, *_ = orc.sync_batchnorm_train(xs, w, b, state["running_mean"], state["running_var"], 0.1, spec["eps"], sync=True)
+    dys = [torch.randn(x.shape, generator=torch.Generator().manual_seed(900 + r)) for r, x in enumerate(xs)]
+    sum((o * dy).sum() for o, dy in zip(outs, dys)).backward()
+    for r in range(2):
+        assert util.rel_err(got[r]["dx"], xs[r].grad) < 1e-4, r
+        assert util.rel_err(got[r]["dgamma"], w.grad) < 1e-4 and util.rel_err(got[r]["dbeta"], b.grad) < 1e-4
+
+
 def test_pack_layout():
     p = sbn.pack_stats(torch.arange(6, dtype=torch.float32), 35)
     assert p.tolist() == [0, 1, 2, 3, 4, 5, 35]
