@@ -202,3 +202,20 @@ def test_benchmarked_step_at_full_size():
     _check_dag(s0.main, "trunk")
     _check_dag(s1.main, "continuation")
     _check_dag(h0.main, "head")
+
+
+@pytest.mark.parametrize("hw", [(1025, 2049), (769, 769), (513, 1025)])
+def test_other_full_sizes_record_and_validate(hw):
+    """The authors' real evaluation size (1025 x 2049: every map 2^k + 1), the training crop (769 x 769) and a half-size
+    image, bf16, gated: every launch of the three plans passes the library's validation (odd extents, ragged tiles,
+    flattened 1x1 tiling, non-multiple-of-8 widths)."""
+    net = add_b200.build_add("searched-dense", 2, 20, seed=1)
+    torch.manual_seed(203)
+    edm = add_b200.EDM().eval()
+    r = dyn._EdmRunner(net, (2, 3, *hw), CPU, "bf16", edm, "evaluate", "reference", label_dtype=torch.uint8)
+    s0 = r.segment(0, 2, None)
+    for name, obj in (("trunk", s0), ("head", r.head(0, 1, s0)), ("continuation", r.segment(1, 1, s0))):
+        codes = _validate(obj.builder, f"{hw} {name}")
+        assert codes[-3] > 0
+    kernels = collections.Counter(l[3]["kernel"] for l in s0.builder.launches)
+    assert not (set(kernels) & {"conv2d_ffma", "sepconv_half"}), kernels
