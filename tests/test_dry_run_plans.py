@@ -219,3 +219,44 @@ def test_other_full_sizes_record_and_validate(hw):
         assert codes[-3] > 0
     kernels = collections.Counter(l[3]["kernel"] for l in s0.builder.launches)
     assert not (set(kernels) & {"conv2d_ffma", "sepconv_half"}), kernels
+
+
+def _config5_cases():
+    """BASELINE config 5 (tools/microbench.py --sweep): sep_conv / dil_conv 3x3 / 5x5 and ASPP_train at F = 20 / 40 / 80
+    across strides 4 / 8 / 16 / 32 (C = F * stride / 4, spatial = 1024 x 2048 / stride; ASPP input = 5C channels)."""
+    out = []
+    for F in (20, 40, 80):
+        for lvl, stride in enumerate((4, 8, 16, 32)):
+            C, h, w = F * (1 << lvl), 1024 // stride, 2048 // stride
+            for op in ("sep_conv_3x3", "sep_conv_5x5", "dil_conv_3x3", "dil_conv_5x5"):
+                out.append((f"F{F}_s{stride}_{op}", "op", (op, C, h, w)))
+            out.append((f"F{F}_s{stride}_aspp_in{5 * C}", "aspp", (5 * C, h, w)))
+    return out
+
+
+@pytest.mark.parametrize("name,kind,a", _config5_cases(), ids=[c[0] for c in _config5_cases()])
+def test_config5_op_sweep_is_served(name, kind, a):
+    """Every shape of BASELINE config 5 records in bf16 and passes the library's validation (one image: the shapes, not
+    the batch, decide what the kernels take).  All of them run on the tcgen05 kernels except C = 20 (F = 20 at stride 4:
+    40-byte pixel rows cannot be TMA rows — the CUDA-core kernels serve it)."""
+    from add_b200.runtime import Builder, View
+    BN = torch.nn.BatchNorm2d
+    b = Builder(CPU, torch.bfloat16, record=True)
+    if kind == "op":
+        op, C, h, w = a
+        m = add_b200.OPS[op](C, 1, BN, 1e-5, 0.1, True).eval()
+        x = View(torch.empty(1, h, w, C, dtype=torch.bfloat16))
+        m.emit(b, x, b.alloc(1, h, w, C), 0)
+    else:
+        cin, h, w = a
+        C = cin
+        m = add_b200.ASPP_train(cin, 256, BN, mult=1).eval()
+        x = View(torch.empty(1, h, w, cin, dtype=torch.bfloat16))
+        m.emit(b, x, b.alloc(1, h, w, 256), 0)
+    _validate(b, name)
+    kernels = {l[3]["kernel"] for l in b.launches}
+    cuda_core = kernels & {"conv2d_ffma", "sepconv_half"}
+    if C % 8 == 0:
+        assert not cuda_core, (name, kernels)
+    else:
+        assert C in (20, 100) and cuda_core, (name, kernels)      # F = 20 at stride 4 (and its ASPP input 5 * 20)
