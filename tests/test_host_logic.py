@@ -177,3 +177,28 @@ def test_leaving_training_mode_invalidates_folded_weights():
         m.op[1].weight.mul_(2.0)               # what an optimiser step does
     m.eval()
     assert rt.generation() > g1
+
+
+def test_bench_arms_use_the_same_synthetic_batch_and_network():
+    """bench.py's reference arm builds its inputs and network WITHOUT importing the product (its process must not map
+    libadd_b200.so): the batch generator it carries must equal the product's and the oracle's (the fp32 feed; the default
+    uint8 feed of the b200 arm is the same generator's image quantised to PNG bytes), and its hard-coded searched-dense C=2
+    path must equal the product's table."""
+    import importlib.util
+    import sys
+    import add_b200
+    spec = importlib.util.spec_from_file_location("bench_under_test", util.ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    xb, gb = bench.cpu_synthetic_batch(2, 33, 65, seed=1234)
+    xp, gp = add_b200.synthetic_batch(2, 33, 65, seed=1234)
+    xo, go = orc.synthetic_batch(2, 33, 65, seed=1234)
+    assert torch.equal(xb, xp) and torch.equal(gb, gp) and torch.equal(xb, xo) and torch.equal(gb, go)
+    na, ci, low = add_b200.NETWORKS["searched-dense"][2]
+    assert (list(na), list(ci), low) == (list(bench.SEARCHED_DENSE_C2[0]), list(bench.SEARCHED_DENSE_C2[1]), bench.SEARCHED_DENSE_C2[2])
+    # the two arms describe the same workload
+    assert bench.METRIC == "ADD 1024x2048 inference images/sec" and bench.UNIT == "images/s"
