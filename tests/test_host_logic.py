@@ -182,7 +182,7 @@ def test_leaving_training_mode_invalidates_folded_weights():
 def test_bench_arms_use_the_same_synthetic_batch_and_network():
     """bench.py's reference arm builds its inputs and network WITHOUT importing the product (its process must not map
     libadd_b200.so): the batch generator it carries must equal the product's and the oracle's (the fp32 feed; the default
-    uint8 feed of the b200 arm is the same generator's image quantised to PNG bytes), and its hard-coded searched-dense C=2
+    uint8 feed of the b200 arm is an N(0,1) image of the same shape quantised to PNG bytes, `synthetic_batch_u8`), and its hard-coded searched-dense C=2
     path must equal the product's table."""
     import importlib.util
     import sys
